@@ -1,0 +1,889 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement (plain C + zlib + pthreads) of the
+ * read-counting path of MarcoMernberger/mbf_bam.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this.  The product
+ * (mbf_bam_b200/csrc) never links or calls it.
+ *
+ * Pinning status (same as oracle/py_oracle.py, which this file is checked against):
+ *   cigar blocks/introns ... pinned by the reference's 58 golden records
+ *                            (src/bam_ext.rs:50-604 -> tests/golden/cigar_golden.json)
+ *   count_reads_* / count_introns end to end ... PARITY UNPINNED by the reference's own
+ *                            tests (src/lib.rs:300-301); the Rust crate cannot be built here.
+ *   count_reads_weighted ... not in the reference; defined in DESIGN.md -- PARITY UNPINNED.
+ *
+ * Structure mirrors the reference on purpose, so that it doubles as the timed CPU
+ * baseline: identical chunk list, a thread pool over chunks, every task opens its own
+ * file handle, seeks through the BAI linear index and inflates with zlib
+ * (src/count_reads/counters.rs:217-259).
+ *
+ * Third-party behaviour restated from published APIs (sources not in the reference tree):
+ * rust-htslib 0.24.0 (+ bundled htslib): fetch/read/aux/aligned_blocks/introns;
+ * bio 0.25.0 IntervalTree::find: half-open overlap a.start < b.end && b.start < a.end.
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include "../include/mbfbam.h"
+
+#define CHUNK_SIZE 1000000u /* src/count_reads/chunked_genome.rs:75 */
+
+/* ------------------------------------------------------------------ BGZF reader */
+typedef struct {
+    FILE* f;
+    uint8_t* cbuf;
+    uint8_t* ubuf;
+    uint32_t ulen, upos;
+    uint64_t coff;      /* file offset of the block in ubuf */
+    uint64_t next_coff; /* file offset of the next block */
+    int eof;
+    int err;
+    z_stream zs;
+    int zs_init;
+} bgzf_t;
+
+static int bgzf_open(bgzf_t* b, const char* path) {
+    memset(b, 0, sizeof *b);
+    b->f = fopen(path, "rb");
+    if (!b->f) return -1;
+    b->cbuf = malloc(65536 + 64);
+    b->ubuf = malloc(65536 + 64);
+    return 0;
+}
+static void bgzf_close(bgzf_t* b) {
+    if (b->f) fclose(b->f);
+    if (b->zs_init) inflateEnd(&b->zs);
+    free(b->cbuf);
+    free(b->ubuf);
+}
+static int bgzf_load(bgzf_t* b, uint64_t coff) {
+    b->ulen = b->upos = 0;
+    if (fseeko(b->f, (off_t)coff, SEEK_SET)) return b->err = -1;
+    size_t n = fread(b->cbuf, 1, 18, b->f);
+    if (n == 0) { b->eof = 1; return 1; }
+    if (n < 18 || b->cbuf[0] != 0x1f || b->cbuf[1] != 0x8b || b->cbuf[2] != 8 || !(b->cbuf[3] & 4))
+        return b->err = -2;
+    uint32_t xlen = b->cbuf[10] | (b->cbuf[11] << 8);
+    /* general extra-field walk (htslib writes XLEN=6 with BC first) */
+    uint8_t* extra = b->cbuf + 12;
+    uint32_t have = 6;
+    if (xlen > 6) {
+        if (fread(b->cbuf + 18, 1, xlen - 6, b->f) != xlen - 6) return b->err = -2;
+        have = xlen;
+    }
+    int32_t bsize = -1;
+    for (uint32_t p = 0; p + 4 <= have;) {
+        uint32_t slen = extra[p + 2] | (extra[p + 3] << 8);
+        if (extra[p] == 66 && extra[p + 1] == 67 && slen == 2) bsize = extra[p + 4] | (extra[p + 5] << 8);
+        p += 4 + slen;
+    }
+    if (bsize < 0) return b->err = -2;
+    uint32_t csize = (uint32_t)bsize + 1;
+    uint32_t hdr = 12 + xlen;
+    if (csize < hdr + 8) return b->err = -2;
+    uint32_t rest = csize - hdr;
+    if (fread(b->cbuf + hdr, 1, rest, b->f) != rest) return b->err = -2;
+    uint32_t isize = b->cbuf[csize - 4] | (b->cbuf[csize - 3] << 8) | (b->cbuf[csize - 2] << 16) |
+                     ((uint32_t)b->cbuf[csize - 1] << 24);
+    if (isize > 65536) return b->err = -2;
+    if (!b->zs_init) {
+        memset(&b->zs, 0, sizeof b->zs);
+        if (inflateInit2(&b->zs, -15) != Z_OK) return b->err = -3;
+        b->zs_init = 1;
+    } else {
+        inflateReset(&b->zs);
+    }
+    b->zs.next_in = b->cbuf + hdr;
+    b->zs.avail_in = rest - 8;
+    b->zs.next_out = b->ubuf;
+    b->zs.avail_out = 65536;
+    int rc = inflate(&b->zs, Z_FINISH);
+    if (rc != Z_STREAM_END || b->zs.total_out != isize) return b->err = -2;
+    uint32_t crc = b->cbuf[csize - 8] | (b->cbuf[csize - 7] << 8) | (b->cbuf[csize - 6] << 16) |
+                   ((uint32_t)b->cbuf[csize - 5] << 24);
+    if ((uint32_t)crc32(crc32(0, NULL, 0), b->ubuf, isize) != crc) return b->err = -2;
+    b->coff = coff;
+    b->next_coff = coff + csize;
+    b->ulen = isize;
+    return 0;
+}
+static int bgzf_seek(bgzf_t* b, uint64_t voff) {
+    b->eof = 0;
+    int rc = bgzf_load(b, voff >> 16);
+    if (rc) return rc;
+    b->upos = (uint32_t)(voff & 0xffff);
+    return b->upos <= b->ulen ? 0 : -2;
+}
+static size_t bgzf_read(bgzf_t* b, void* dst_, size_t n) {
+    uint8_t* dst = dst_;
+    size_t got = 0;
+    while (got < n) {
+        if (b->upos >= b->ulen) {
+            if (b->eof || b->err) break;
+            if (bgzf_load(b, b->next_coff)) break;
+            continue;
+        }
+        size_t take = b->ulen - b->upos;
+        if (take > n - got) take = n - got;
+        memcpy(dst + got, b->ubuf + b->upos, take);
+        b->upos += (uint32_t)take;
+        got += take;
+    }
+    return got;
+}
+
+/* ------------------------------------------------------------------ header + BAI */
+typedef struct {
+    int32_t n_ref;
+    char** names;
+    uint32_t* lens;
+    /* BAI */
+    int32_t bai_n_ref;
+    int32_t* n_intv;
+    uint64_t** ioffset;
+    uint64_t* ref_beg; /* min chunk begin over real bins, 0 if none */
+    uint8_t* has_bins;
+} bamidx_t;
+
+static int read_header(const char* path, bamidx_t* h) {
+    bgzf_t b;
+    if (bgzf_open(&b, path)) return -1;
+    if (bgzf_load(&b, 0)) { bgzf_close(&b); return -2; }
+    char magic[4];
+    int32_t l_text;
+    if (bgzf_read(&b, magic, 4) != 4 || memcmp(magic, "BAM\1", 4) || bgzf_read(&b, &l_text, 4) != 4) {
+        bgzf_close(&b);
+        return -2;
+    }
+    char* text = malloc((size_t)l_text + 1);
+    bgzf_read(&b, text, (size_t)l_text);
+    free(text);
+    bgzf_read(&b, &h->n_ref, 4);
+    h->names = calloc((size_t)h->n_ref + 1, sizeof(char*));
+    h->lens = calloc((size_t)h->n_ref + 1, 4);
+    for (int i = 0; i < h->n_ref; i++) {
+        int32_t ln;
+        bgzf_read(&b, &ln, 4);
+        h->names[i] = malloc((size_t)ln + 1);
+        bgzf_read(&b, h->names[i], (size_t)ln);
+        h->names[i][ln] = 0;
+        int32_t l;
+        bgzf_read(&b, &l, 4);
+        h->lens[i] = (uint32_t)l;
+    }
+    int bad = b.err;
+    bgzf_close(&b);
+    return bad ? -2 : 0;
+}
+static int read_bai(const char* path, bamidx_t* h) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return -1;
+    char magic[4];
+    if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "BAI\1", 4)) { fclose(f); return -2; }
+    if (fread(&h->bai_n_ref, 4, 1, f) != 1) { fclose(f); return -2; }
+    int n = h->bai_n_ref;
+    h->n_intv = calloc((size_t)n + 1, 4);
+    h->ioffset = calloc((size_t)n + 1, sizeof(uint64_t*));
+    h->ref_beg = calloc((size_t)n + 1, 8);
+    h->has_bins = calloc((size_t)n + 1, 1);
+    for (int r = 0; r < n; r++) {
+        int32_t n_bin;
+        if (fread(&n_bin, 4, 1, f) != 1) { fclose(f); return -2; }
+        uint64_t mn = UINT64_MAX;
+        for (int i = 0; i < n_bin; i++) {
+            uint32_t bin;
+            int32_t n_chunk;
+            if (fread(&bin, 4, 1, f) != 1 || fread(&n_chunk, 4, 1, f) != 1) { fclose(f); return -2; }
+            for (int c = 0; c < n_chunk; c++) {
+                uint64_t be[2];
+                if (fread(be, 8, 2, f) != 2) { fclose(f); return -2; }
+                if (bin != 37450 && be[0] < mn) mn = be[0];
+            }
+        }
+        h->has_bins[r] = mn != UINT64_MAX;
+        h->ref_beg[r] = mn == UINT64_MAX ? 0 : mn;
+        if (fread(&h->n_intv[r], 4, 1, f) != 1) { fclose(f); return -2; }
+        h->ioffset[r] = malloc(((size_t)h->n_intv[r] + 1) * 8);
+        if (h->n_intv[r] && fread(h->ioffset[r], 8, (size_t)h->n_intv[r], f) != (size_t)h->n_intv[r]) {
+            fclose(f);
+            return -2;
+        }
+    }
+    fclose(f);
+    return 0;
+}
+static void free_idx(bamidx_t* h) {
+    for (int i = 0; i < h->n_ref; i++) free(h->names[i]);
+    free(h->names);
+    free(h->lens);
+    for (int i = 0; i < h->bai_n_ref; i++) free(h->ioffset[i]);
+    free(h->ioffset);
+    free(h->n_intv);
+    free(h->ref_beg);
+    free(h->has_bins);
+}
+static int find_tid(const bamidx_t* h, const char* name) {
+    for (int i = 0; i < h->n_ref; i++)
+        if (!strcmp(h->names[i], name)) return i;
+    return -1;
+}
+static char* default_bai(const char* bam, const char* bai) {
+    char* p;
+    if (bai) return strdup(bai);
+    if (asprintf(&p, "%s.bai", bam) < 0) return NULL;
+    FILE* f = fopen(p, "rb");
+    if (f) { fclose(f); return p; }
+    free(p);
+    size_t n = strlen(bam);
+    if (n > 4 && !strcmp(bam + n - 4, ".bam")) {
+        p = strdup(bam);
+        memcpy(p + n - 4, ".bai", 4);
+        return p;
+    }
+    return NULL;
+}
+
+/* ------------------------------------------------------------------ interval sets */
+typedef struct {
+    uint32_t n;
+    uint32_t *start, *end, *gene, *pmax; /* sorted by start; pmax = prefix max of end */
+    int8_t* strand;
+} ivset_t;
+
+typedef struct { uint32_t s, e, g; int8_t st; } ivrow_t;
+static int cmp_row(const void* a, const void* b) {
+    const ivrow_t *x = a, *y = b;
+    if (x->s != y->s) return x->s < y->s ? -1 : 1;
+    if (x->e != y->e) return x->e < y->e ? -1 : 1;
+    return x->g < y->g ? -1 : (x->g > y->g);
+}
+static void build_ivset(const mbfbam_intervals* iv, int c, ivset_t* s) {
+    uint64_t a = iv->iv_offsets[c], b = iv->iv_offsets[c + 1];
+    s->n = (uint32_t)(b - a);
+    ivrow_t* rows = malloc((s->n + 1) * sizeof *rows);
+    for (uint32_t i = 0; i < s->n; i++) {
+        rows[i].s = iv->iv_start[a + i];
+        rows[i].e = iv->iv_end[a + i];
+        rows[i].g = iv->iv_gene[a + i];
+        rows[i].st = iv->iv_strand[a + i];
+    }
+    qsort(rows, s->n, sizeof *rows, cmp_row);
+    s->start = malloc((s->n + 1) * 4);
+    s->end = malloc((s->n + 1) * 4);
+    s->gene = malloc((s->n + 1) * 4);
+    s->pmax = malloc((s->n + 1) * 4);
+    s->strand = malloc(s->n + 1);
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < s->n; i++) {
+        s->start[i] = rows[i].s;
+        s->end[i] = rows[i].e;
+        s->gene[i] = rows[i].g;
+        s->strand[i] = rows[i].st;
+        if (rows[i].e > m) m = rows[i].e;
+        s->pmax[i] = m;
+    }
+    free(rows);
+}
+static void free_ivset(ivset_t* s) {
+    free(s->start); free(s->end); free(s->gene); free(s->pmax); free(s->strand);
+}
+/* first index with start >= x */
+static uint32_t lower_start(const ivset_t* s, uint32_t x) {
+    uint32_t lo = 0, hi = s->n;
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (s->start[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+/* ------------------------------------------------------------------ chunk table */
+typedef struct { int32_t contig; int32_t tid; uint32_t start, stop; } chunk_t;
+
+/* src/count_reads/chunked_genome.rs:72-119.  When several gene intervals cover the provisional
+ * stop the reference takes whichever bio's tree yields first; the fixed point is the same for all
+ * choices except in 1-bp-abutting corner layouts, which the generators reject.
+ * We take the covering interval with the largest end. */
+static uint32_t extend_stop(const ivset_t* g, uint32_t stop) {
+    for (;;) {
+        uint32_t hi = lower_start(g, stop + 1); /* start <= stop */
+        uint32_t best = 0;
+        int found = 0;
+        for (uint32_t i = hi; i-- > 0;) {
+            if (g->pmax[i] <= stop) break;
+            if (g->end[i] > stop) { /* start <= stop < end */
+                if (!found || g->end[i] > best) best = g->end[i];
+                found = 1;
+            }
+        }
+        if (!found) return stop;
+        stop = best + 1;
+    }
+}
+static chunk_t* make_chunks(const bamidx_t* h, const mbfbam_intervals* genes, const ivset_t* gsets,
+                            size_t* n_out) {
+    size_t cap = 1024, n = 0;
+    chunk_t* out = malloc(cap * sizeof *out);
+    int n_contigs = genes ? genes->n_contigs : h->n_ref;
+    for (int c = 0; c < n_contigs; c++) {
+        int tid = genes ? find_tid(h, genes->contig_names[c]) : c;
+        if (tid < 0) continue; /* chunked_genome.rs:21-25 */
+        uint32_t len = h->lens[tid], start = 0;
+        do {
+            uint32_t stop = start + CHUNK_SIZE;
+            if (genes) stop = extend_stop(&gsets[c], stop);
+            if (n == cap) out = realloc(out, (cap *= 2) * sizeof *out);
+            out[n++] = (chunk_t){c, tid, start, stop};
+            start = stop;
+        } while (start < len);
+    }
+    *n_out = n;
+    return out;
+}
+
+/* ------------------------------------------------------------------ exact qname sets */
+typedef struct mmnode {
+    struct mmnode* next;
+    uint32_t gene;
+    uint16_t len;
+    uint8_t bucket;
+    uint8_t name[];
+} mmnode;
+typedef struct {
+    mmnode** tab;
+    size_t cap, n;
+    char** arenas;
+    size_t n_arenas, arena_used, arena_cap;
+} mmset_t;
+static void mm_init(mmset_t* s) {
+    memset(s, 0, sizeof *s);
+    s->cap = 1024;
+    s->tab = calloc(s->cap, sizeof(mmnode*));
+}
+static void* mm_alloc(mmset_t* s, size_t n) {
+    n = (n + 7) & ~(size_t)7;
+    if (!s->n_arenas || s->arena_used + n > s->arena_cap) {
+        s->arena_cap = n > (1 << 20) ? n : (1 << 20);
+        s->arenas = realloc(s->arenas, (s->n_arenas + 1) * sizeof(char*));
+        s->arenas[s->n_arenas++] = malloc(s->arena_cap);
+        s->arena_used = 0;
+    }
+    void* p = s->arenas[s->n_arenas - 1] + s->arena_used;
+    s->arena_used += n;
+    return p;
+}
+static void mm_free(mmset_t* s) {
+    for (size_t i = 0; i < s->n_arenas; i++) free(s->arenas[i]);
+    free(s->arenas);
+    free(s->tab);
+}
+static uint64_t fnv(const uint8_t* p, size_t n, uint64_t h) {
+    for (size_t i = 0; i < n; i++) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+}
+/* returns 1 if newly inserted */
+static int mm_insert(mmset_t* s, uint8_t bucket, uint32_t gene, const uint8_t* name, size_t len) {
+    uint64_t h = fnv(name, len, 1469598103934665603ull ^ ((uint64_t)gene << 1 | bucket));
+    if (s->n * 2 > s->cap) {
+        size_t ncap = s->cap * 4;
+        mmnode** nt = calloc(ncap, sizeof(mmnode*));
+        for (size_t i = 0; i < s->cap; i++)
+            for (mmnode* p = s->tab[i]; p;) {
+                mmnode* nx = p->next;
+                uint64_t hh = fnv(p->name, p->len, 1469598103934665603ull ^ ((uint64_t)p->gene << 1 | p->bucket));
+                p->next = nt[hh & (ncap - 1)];
+                nt[hh & (ncap - 1)] = p;
+                p = nx;
+            }
+        free(s->tab);
+        s->tab = nt;
+        s->cap = ncap;
+    }
+    mmnode** slot = &s->tab[h & (s->cap - 1)];
+    for (mmnode* p = *slot; p; p = p->next)
+        if (p->gene == gene && p->bucket == bucket && p->len == len && !memcmp(p->name, name, len)) return 0;
+    mmnode* nn = mm_alloc(s, sizeof(mmnode) + len);
+    nn->gene = gene;
+    nn->bucket = bucket;
+    nn->len = (uint16_t)len;
+    memcpy(nn->name, name, len);
+    nn->next = *slot;
+    *slot = nn;
+    s->n++;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ record helpers */
+static inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+static inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+/* htslib bam_aux_get + rust-htslib Aux::Integer.  returns 0 absent, 1 integer (*val), -1 present but
+ * not an integer (rust-htslib `.integer()` panics there), -2 malformed aux area. */
+static int aux_nh(const uint8_t* p, const uint8_t* e, int64_t* val) {
+    while (p + 3 <= e) {
+        int match = p[0] == 'N' && p[1] == 'H';
+        uint8_t t = p[2];
+        p += 3;
+        size_t sz;
+        switch (t) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'd': sz = 8; break;
+            case 'Z': case 'H': {
+                if (match) return -1;
+                while (p < e && *p) p++;
+                if (p >= e) return -2;
+                p++;
+                continue;
+            }
+            case 'B': {
+                if (match) return -1;
+                if (p + 5 > e) return -2;
+                uint8_t st = p[0];
+                uint32_t cnt = rd32(p + 1);
+                size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                p += 5 + (size_t)cnt * es;
+                continue;
+            }
+            default: return -2;
+        }
+        if (p + sz > e) return -2;
+        if (match) {
+            switch (t) {
+                case 'c': *val = (int8_t)p[0]; return 1;
+                case 'C': *val = p[0]; return 1;
+                case 's': *val = (int16_t)rd16(p); return 1;
+                case 'S': *val = rd16(p); return 1;
+                case 'i': *val = (int32_t)rd32(p); return 1;
+                case 'I': *val = rd32(p); return 1;
+                default: return -1;
+            }
+        }
+        p += sz;
+    }
+    return 0;
+}
+
+/* rust-htslib aligned_blocks / introns through src/bam_ext.rs:28-42. */
+int32_t oracle_cigar_pairs(const uint32_t* cigar, int32_t n_ops, int32_t pos, int32_t want_introns,
+                           uint32_t* out, int32_t cap) {
+    uint32_t p = (uint32_t)pos;
+    int32_t n = 0;
+    for (int i = 0; i < n_ops; i++) {
+        uint32_t op = cigar[i] & 15, len = cigar[i] >> 4;
+        int is_m = op == 0 || op == 7 || op == 8;
+        if ((is_m && !want_introns) || (op == 3 && want_introns)) {
+            if (n < cap) { out[2 * n] = p; out[2 * n + 1] = p + len; }
+            n++;
+        }
+        if (is_m || op == 2 || op == 3) p += len;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------ the counting job */
+typedef struct {
+    const char* bam_path;
+    bamidx_t* idx;
+    const mbfbam_intervals* iv;
+    ivset_t* sets;      /* per intervals-contig */
+    int32_t* tid2c;     /* header tid -> contig index in `iv` (-1) */
+    uint64_t* gene_base;
+    chunk_t* chunks;
+    size_t n_chunks;
+    size_t next_chunk;  /* atomic */
+    int mode;
+    int introns;
+    int nthreads;
+    int failed;
+    char err[256];
+    pthread_mutex_t mu;
+    /* outputs */
+    uint64_t *fwd, *rev;
+    double *wfwd, *wrev; /* nthreads private copies reduced at the end */
+    uint64_t outside;
+    uint64_t n_records;
+    /* introns: per-thread maps merged at the end */
+    struct imap* imaps;
+} job_t;
+
+/* (tid,start,stop) -> count, open addressing */
+typedef struct imap {
+    uint64_t* key; /* start | stop<<32 */
+    int32_t* tid;  /* -1 empty */
+    uint64_t* cnt;
+    size_t cap, n;
+} imap;
+static void imap_init(imap* m, size_t cap) {
+    m->cap = cap; m->n = 0;
+    m->key = malloc(cap * 8);
+    m->tid = malloc(cap * 4);
+    m->cnt = calloc(cap, 8);
+    for (size_t i = 0; i < cap; i++) m->tid[i] = -1;
+}
+static void imap_free(imap* m) { free(m->key); free(m->tid); free(m->cnt); }
+static void imap_add(imap* m, int32_t tid, uint32_t s, uint32_t e, uint64_t c);
+static void imap_grow(imap* m) {
+    imap o = *m;
+    imap_init(m, o.cap * 2);
+    for (size_t i = 0; i < o.cap; i++)
+        if (o.tid[i] >= 0) imap_add(m, o.tid[i], (uint32_t)o.key[i], (uint32_t)(o.key[i] >> 32), o.cnt[i]);
+    imap_free(&o);
+}
+static void imap_add(imap* m, int32_t tid, uint32_t s, uint32_t e, uint64_t c) {
+    if ((m->n + 1) * 2 > m->cap) imap_grow(m);
+    uint64_t k = (uint64_t)s | ((uint64_t)e << 32);
+    uint64_t h = (k ^ ((uint64_t)tid * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    size_t i = h & (m->cap - 1);
+    for (;; i = (i + 1) & (m->cap - 1)) {
+        if (m->tid[i] < 0) { m->tid[i] = tid; m->key[i] = k; m->cnt[i] = c; m->n++; return; }
+        if (m->tid[i] == tid && m->key[i] == k) { m->cnt[i] += c; return; }
+    }
+}
+
+typedef struct { uint32_t* v; size_t n, cap; } u32vec;
+static inline int vec_add_unique(u32vec* s, uint32_t x) {
+    for (size_t i = 0; i < s->n; i++) if (s->v[i] == x) return 0;
+    if (s->n == s->cap) s->v = realloc(s->v, (s->cap = s->cap ? s->cap * 2 : 16) * 4);
+    s->v[s->n++] = x;
+    return 1;
+}
+
+static void fail(job_t* j, const char* msg) {
+    pthread_mutex_lock(&j->mu);
+    if (!j->failed) { j->failed = 1; snprintf(j->err, sizeof j->err, "%s", msg); }
+    pthread_mutex_unlock(&j->mu);
+}
+
+/* one chunk == count_reads_in_region_{unstranded,stranded} (counters.rs:26-106,114-202)
+ * or count_introns (introns.rs:24-51) */
+static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, size_t* rcap) {
+    bamidx_t* h = j->idx;
+    int tid = ck->tid;
+    if (tid >= h->bai_n_ref || !h->has_bins[tid]) return;
+    uint32_t w = ck->start >> 14;
+    if ((int32_t)w >= h->n_intv[tid]) return; /* nothing at or right of start */
+    uint64_t voff = h->ioffset[tid][w];
+    if (voff == 0) voff = h->ref_beg[tid];
+    bgzf_t b;
+    if (bgzf_open(&b, j->bam_path)) { fail(j, "Could not read bam: open failed"); return; } /* counters.rs:223 */
+    if (bgzf_seek(&b, voff)) { bgzf_close(&b); fail(j, "Fetch error"); return; }
+    const ivset_t* set = j->introns ? NULL : &j->sets[ck->contig];
+    uint64_t gbase = j->introns ? 0 : j->gene_base[ck->contig];
+    uint32_t ngenes = j->introns ? 0 : j->iv->n_genes[ck->contig];
+    uint64_t* lf = NULL; uint64_t* lr = NULL;
+    double *wf = NULL, *wr = NULL;
+    if (!j->introns) {
+        if (j->mode == MBFBAM_MODE_WEIGHTED) {
+            size_t tot = (size_t)j->gene_base[j->iv->n_contigs];
+            wf = j->wfwd + (size_t)thread * tot + gbase;
+            wr = j->wrev + (size_t)thread * tot + gbase;
+        } else {
+            lf = calloc((size_t)ngenes + 1, 8);
+            lr = calloc((size_t)ngenes + 1, 8);
+        }
+    }
+    mmset_t mm;
+    mm_init(&mm);
+    u32vec seen[2] = {{0, 0, 0}, {0, 0, 0}};
+    uint64_t outside = 0, nrec = 0;
+    imap* im = j->introns ? &j->imaps[thread] : NULL;
+    for (;;) {
+        int32_t bs;
+        if (bgzf_read(&b, &bs, 4) != 4) break; /* Err(_) ends the loop, counters.rs:41 */
+        if (bs < 32) { fail(j, "corrupt BAM record"); break; }
+        if ((size_t)bs > *rcap) { *rcap = (size_t)bs * 2; *rbuf = realloc(*rbuf, *rcap); }
+        uint8_t* r = *rbuf;
+        if (bgzf_read(&b, r, (size_t)bs) != (size_t)bs) break;
+        int32_t rtid = (int32_t)rd32(r), pos = (int32_t)rd32(r + 4);
+        if (rtid != tid) {
+            if (rtid < tid && rtid >= 0) continue;
+            break; /* iterator ends at the next reference */
+        }
+        if (pos >= 0 && (uint32_t)pos >= ck->stop) break;
+        uint32_t upos = (uint32_t)pos;
+        if (upos < ck->start || upos >= ck->stop) continue; /* counters.rs:46-48 */
+        nrec++;
+        uint32_t l_qn = r[8], n_cig = rd16(r + 12), flag = rd16(r + 14), l_seq = rd32(r + 16);
+        const uint8_t* qn = r + 32;
+        const uint8_t* cig = qn + l_qn;
+        const uint8_t* aux = cig + 4 * (size_t)n_cig + (l_seq + 1) / 2 + l_seq;
+        const uint8_t* end = r + bs;
+        if (aux > end) { fail(j, "corrupt BAM record"); break; }
+        if (j->introns) {
+            /* introns.rs:38-48 */
+            uint32_t p = upos, k = 0;
+            for (uint32_t i = 0; i < n_cig; i++) {
+                uint32_t c = rd32(cig + 4 * i), op = c & 15, len = c >> 4;
+                if (op == 3) { imap_add(im, tid, p, p + len, 1); k++; }
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) p += len;
+            }
+            imap_add(im, tid, UINT32_MAX, UINT32_MAX - k, 1);
+            continue;
+        }
+        seen[0].n = seen[1].n = 0;
+        int hit = 0, have_nh = 0;
+        int64_t nh = 1;
+        uint32_t p = upos;
+        for (uint32_t i = 0; i < n_cig; i++) {
+            uint32_t c = rd32(cig + 4 * i), op = c & 15, len = c >> 4;
+            if (op == 0 || op == 7 || op == 8) {
+                uint32_t b0 = p, b1 = p + len;
+                p += len;
+                if (j->mode == MBFBAM_MODE_UNSTRANDED && b0 >= ck->stop) continue; /* counters.rs:52 */
+                uint32_t hi = lower_start(set, b1);
+                for (uint32_t k = hi; k-- > 0;) {
+                    if (set->pmax[k] <= b0) break;
+                    if (!(set->start[k] < b1 && b0 < set->end[k])) continue;
+                    hit = 1;
+                    if (!have_nh) {
+                        int rc = aux_nh(aux, end, &nh); /* counters.rs:65-66 */
+                        if (rc == 0) nh = 1;
+                        else if (rc < 0) { fail(j, rc == -1 ? "NH tag is not an integer" : "corrupt aux data"); nh = 1; }
+                        have_nh = 1;
+                    }
+                    int bucket = 0;
+                    if (j->mode != MBFBAM_MODE_UNSTRANDED) { /* counters.rs:151 */
+                        int rv = (flag & 0x10) != 0, st = set->strand[k];
+                        bucket = ((st == 1 && !rv) || (st != 1 && rv)) ? 0 : 1;
+                    }
+                    uint32_t g = set->gene[k];
+                    if (j->mode == MBFBAM_MODE_WEIGHTED || nh == 1) vec_add_unique(&seen[bucket], g);
+                    else mm_insert(&mm, (uint8_t)bucket, g, qn, l_qn ? l_qn - 1 : 0);
+                }
+            } else if (op == 2 || op == 3) {
+                p += len;
+            }
+        }
+        if (!hit) outside++;
+        if (j->mode == MBFBAM_MODE_WEIGHTED) {
+            double wgt = nh >= 1 ? 1.0 / (double)nh : 1.0;
+            for (size_t i = 0; i < seen[0].n; i++) wf[seen[0].v[i]] += wgt;
+            for (size_t i = 0; i < seen[1].n; i++) wr[seen[1].v[i]] += wgt;
+        } else {
+            for (size_t i = 0; i < seen[0].n; i++) lf[seen[0].v[i]]++;
+            for (size_t i = 0; i < seen[1].n; i++) lr[seen[1].v[i]]++;
+        }
+    }
+    if (b.err) fail(j, "corrupt BGZF block");
+    if (!j->introns && j->mode != MBFBAM_MODE_WEIGHTED) {
+        /* counters.rs:102-104 / :195-200: add the sizes of the multi-mapper sets */
+        for (size_t i = 0; i < mm.cap; i++)
+            for (mmnode* q = mm.tab[i]; q; q = q->next) (q->bucket ? lr : lf)[q->gene]++;
+        for (uint32_t g = 0; g < ngenes; g++) {
+            if (lf[g]) __atomic_fetch_add(&j->fwd[gbase + g], lf[g], __ATOMIC_RELAXED);
+            if (lr[g]) __atomic_fetch_add(&j->rev[gbase + g], lr[g], __ATOMIC_RELAXED);
+        }
+    }
+    __atomic_fetch_add(&j->outside, outside, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&j->n_records, nrec, __ATOMIC_RELAXED);
+    free(lf); free(lr);
+    free(seen[0].v); free(seen[1].v);
+    mm_free(&mm);
+    bgzf_close(&b);
+}
+
+typedef struct { job_t* j; int thread; } targ_t;
+static void* worker(void* a_) {
+    targ_t* a = a_;
+    job_t* j = a->j;
+    uint8_t* rbuf = NULL;
+    size_t rcap = 0;
+    for (;;) {
+        size_t i = __atomic_fetch_add(&j->next_chunk, 1, __ATOMIC_RELAXED);
+        if (i >= j->n_chunks) break;
+        run_chunk(j, a->thread, &j->chunks[i], &rbuf, &rcap);
+    }
+    free(rbuf);
+    return NULL;
+}
+static void run_pool(job_t* j) {
+    int nt = j->nthreads < 1 ? 1 : j->nthreads;
+    pthread_t* th = malloc((size_t)nt * sizeof *th);
+    targ_t* ta = malloc((size_t)nt * sizeof *ta);
+    for (int t = 0; t < nt; t++) { ta[t] = (targ_t){j, t}; pthread_create(&th[t], NULL, worker, &ta[t]); }
+    for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
+    free(th); free(ta);
+}
+
+static int open_idx(const char* bam, const char* bai, bamidx_t* idx, char* err, size_t errlen) {
+    memset(idx, 0, sizeof *idx);
+    if (read_header(bam, idx)) { snprintf(err, errlen, "Could not read bam: %s", bam); return MBFBAM_ERR_IO; }
+    char* bp = default_bai(bam, bai);
+    int rc = bp ? read_bai(bp, idx) : -1;
+    free(bp);
+    if (rc) { snprintf(err, errlen, "Could not read bam: index of %s", bam); return MBFBAM_ERR_IO; }
+    return 0;
+}
+
+/* counters.rs:204-260 / :276-323 without the String maps (assembled by the test helper).
+ * sample_chunks > 0: run only every k-th chunk so that about `sample_chunks` chunks run
+ * (bench.py's bounded CPU sample); n_records_out reports the records they owned. */
+int oracle_count_reads(const char* bam, const char* bai, const mbfbam_intervals* iv,
+                       const mbfbam_intervals* genes, int mode, int nthreads, int64_t sample_chunks,
+                       uint64_t* fwd, uint64_t* rev, double* wfwd, double* wrev, uint8_t* scanned,
+                       uint64_t* outside, uint64_t* n_records_out, int64_t* n_chunks_out, char* err,
+                       size_t errlen) {
+    bamidx_t idx;
+    int rc = open_idx(bam, bai, &idx, err, errlen);
+    if (rc) return rc;
+    job_t j;
+    memset(&j, 0, sizeof j);
+    pthread_mutex_init(&j.mu, NULL);
+    j.bam_path = bam; j.idx = &idx; j.iv = iv; j.mode = mode; j.nthreads = nthreads < 1 ? 1 : nthreads;
+    j.sets = calloc((size_t)iv->n_contigs + 1, sizeof(ivset_t));
+    j.gene_base = calloc((size_t)iv->n_contigs + 1, 8);
+    for (int c = 0; c < iv->n_contigs; c++) {
+        build_ivset(iv, c, &j.sets[c]);
+        j.gene_base[c + 1] = j.gene_base[c] + iv->n_genes[c];
+    }
+    size_t tot = (size_t)j.gene_base[iv->n_contigs];
+    ivset_t* gsets = calloc((size_t)genes->n_contigs + 1, sizeof(ivset_t));
+    for (int c = 0; c < genes->n_contigs; c++) build_ivset(genes, c, &gsets[c]);
+    size_t nck;
+    chunk_t* cks = make_chunks(&idx, genes, gsets, &nck);
+    /* chunk.contig currently indexes `genes`; remap to `iv` (counters.rs:224 trees.get(&chunk.chr).unwrap()) */
+    rc = 0;
+    for (size_t i = 0; i < nck; i++) {
+        const char* nm = genes->contig_names[cks[i].contig];
+        int c2 = -1;
+        for (int c = 0; c < iv->n_contigs; c++) if (!strcmp(iv->contig_names[c], nm)) { c2 = c; break; }
+        if (c2 < 0) { snprintf(err, errlen, "contig %s is in gene_intervals but not in intervals", nm); rc = MBFBAM_ERR_ARG; break; }
+        cks[i].contig = c2;
+        if (scanned) scanned[c2] = 1;
+    }
+    if (!rc) {
+        if (sample_chunks > 0 && (size_t)sample_chunks < nck) {
+            size_t step = nck / (size_t)sample_chunks, m = 0;
+            for (size_t i = 0; i < nck; i += step) cks[m++] = cks[i];
+            nck = m;
+        }
+        j.chunks = cks; j.n_chunks = nck;
+        j.fwd = fwd; j.rev = rev;
+        if (mode == MBFBAM_MODE_WEIGHTED) {
+            j.wfwd = calloc(tot * (size_t)j.nthreads + 1, 8);
+            j.wrev = calloc(tot * (size_t)j.nthreads + 1, 8);
+        }
+        run_pool(&j);
+        if (mode == MBFBAM_MODE_WEIGHTED) {
+            for (size_t g = 0; g < tot; g++) {
+                double a = 0, b = 0;
+                for (int t = 0; t < j.nthreads; t++) { a += j.wfwd[(size_t)t * tot + g]; b += j.wrev[(size_t)t * tot + g]; }
+                wfwd[g] = a; wrev[g] = b;
+            }
+            free(j.wfwd); free(j.wrev);
+        }
+        *outside = j.outside;
+        if (n_records_out) *n_records_out = j.n_records;
+        if (n_chunks_out) *n_chunks_out = (int64_t)nck;
+        if (j.failed) { snprintf(err, errlen, "%s", j.err); rc = MBFBAM_ERR_FORMAT; }
+    }
+    for (int c = 0; c < iv->n_contigs; c++) free_ivset(&j.sets[c]);
+    for (int c = 0; c < genes->n_contigs; c++) free_ivset(&gsets[c]);
+    free(j.sets); free(gsets); free(j.gene_base); free(cks);
+    free_idx(&idx);
+    return rc;
+}
+
+/* introns.rs:56-88.  Result arrays are malloc'ed; free with oracle_free. */
+int oracle_count_introns(const char* bam, const char* bai, int nthreads, uint64_t* n_out, int32_t** tid_out,
+                         uint32_t** start_out, uint32_t** stop_out, uint64_t** count_out,
+                         uint8_t* contig_seen, int32_t n_targets_cap, uint64_t* n_records_out, char* err,
+                         size_t errlen) {
+    bamidx_t idx;
+    int rc = open_idx(bam, bai, &idx, err, errlen);
+    if (rc) return rc;
+    job_t j;
+    memset(&j, 0, sizeof j);
+    pthread_mutex_init(&j.mu, NULL);
+    j.bam_path = bam; j.idx = &idx; j.introns = 1; j.nthreads = nthreads < 1 ? 1 : nthreads;
+    size_t nck;
+    chunk_t* cks = make_chunks(&idx, NULL, NULL, &nck);
+    j.chunks = cks; j.n_chunks = nck;
+    j.imaps = calloc((size_t)j.nthreads, sizeof(imap));
+    for (int t = 0; t < j.nthreads; t++) imap_init(&j.imaps[t], 1 << 12);
+    run_pool(&j);
+    imap all;
+    imap_init(&all, 1 << 12);
+    for (int t = 0; t < j.nthreads; t++) {
+        imap* m = &j.imaps[t];
+        for (size_t i = 0; i < m->cap; i++)
+            if (m->tid[i] >= 0) imap_add(&all, m->tid[i], (uint32_t)m->key[i], (uint32_t)(m->key[i] >> 32), m->cnt[i]);
+        imap_free(m);
+    }
+    free(j.imaps);
+    *n_out = all.n;
+    *tid_out = malloc((all.n + 1) * 4);
+    *start_out = malloc((all.n + 1) * 4);
+    *stop_out = malloc((all.n + 1) * 4);
+    *count_out = malloc((all.n + 1) * 8);
+    size_t k = 0;
+    for (size_t i = 0; i < all.cap; i++)
+        if (all.tid[i] >= 0) {
+            (*tid_out)[k] = all.tid[i];
+            (*start_out)[k] = (uint32_t)all.key[i];
+            (*stop_out)[k] = (uint32_t)(all.key[i] >> 32);
+            (*count_out)[k] = all.cnt[i];
+            k++;
+        }
+    imap_free(&all);
+    /* introns.rs:75-79: every chunk whose scan did not fail inserts its contig key */
+    for (int t = 0; t < idx.n_ref && t < n_targets_cap; t++) contig_seen[t] = 1;
+    if (n_records_out) *n_records_out = j.n_records;
+    if (j.failed) { snprintf(err, errlen, "%s", j.err); rc = MBFBAM_ERR_FORMAT; }
+    free(cks);
+    free_idx(&idx);
+    return rc;
+}
+void oracle_free(void* p) { free(p); }
+
+int64_t oracle_chunks(const char* bam, const char* bai, const mbfbam_intervals* genes, int32_t* tid,
+                      uint32_t* start, uint32_t* stop, int64_t cap) {
+    bamidx_t idx;
+    char err[64];
+    if (open_idx(bam, bai, &idx, err, sizeof err)) return -1;
+    ivset_t* gsets = NULL;
+    if (genes) {
+        gsets = calloc((size_t)genes->n_contigs + 1, sizeof(ivset_t));
+        for (int c = 0; c < genes->n_contigs; c++) build_ivset(genes, c, &gsets[c]);
+    }
+    size_t n;
+    chunk_t* cks = make_chunks(&idx, genes, gsets, &n);
+    for (size_t i = 0; i < n && (int64_t)i < cap; i++) { tid[i] = cks[i].tid; start[i] = cks[i].start; stop[i] = cks[i].stop; }
+    if (genes) { for (int c = 0; c < genes->n_contigs; c++) free_ivset(&gsets[c]); free(gsets); }
+    free(cks);
+    free_idx(&idx);
+    return (int64_t)n;
+}
+
+/* Inflate all BGZF members of a buffer with zlib: the known-answer side of the inflate parity test
+ * and the CPU inflate timing. returns total bytes or -1. */
+int64_t oracle_inflate_buffer(const uint8_t* in, uint64_t n, uint8_t* out, uint64_t cap) {
+    uint64_t off = 0, o = 0;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return -1;
+    while (off + 18 <= n) {
+        if (in[off] != 0x1f || in[off + 1] != 0x8b) { inflateEnd(&zs); return -1; }
+        uint32_t xlen = in[off + 10] | (in[off + 11] << 8);
+        uint32_t csize = (in[off + 16] | (in[off + 17] << 8)) + 1u;
+        if (off + csize > n) break;
+        uint32_t isize = rd32(in + off + csize - 4);
+        if (o + isize > cap) { inflateEnd(&zs); return -1; }
+        inflateReset(&zs);
+        zs.next_in = (Bytef*)(in + off + 12 + xlen);
+        zs.avail_in = csize - 12 - xlen - 8;
+        zs.next_out = out + o;
+        zs.avail_out = isize;
+        if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.total_out != isize) { inflateEnd(&zs); return -1; }
+        o += isize;
+        off += csize;
+    }
+    inflateEnd(&zs);
+    return (int64_t)o;
+}

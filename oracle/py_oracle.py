@@ -1,0 +1,256 @@
+"""TEST INFRASTRUCTURE ONLY -- pure-Python restatement of mbf_bam's counters.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
+this.  It is the slow, obviously-correct statement of the semantics; the C
+restatement (oracle/mbf_oracle.c) is checked against it on small inputs and is
+what the GPU path is compared with at larger sizes.
+
+Pinning status:
+  * cigar_blocks / cigar_introns: PINNED by the reference's 58 golden records
+    (reference src/bam_ext.rs:50-382 and :384-604 -> tests/golden/cigar_golden.json).
+  * count_reads_unstranded / count_reads_stranded / count_introns end to end:
+    PARITY UNPINNED by the reference's own tests (src/lib.rs:300-301 says the
+    tests live in the callers); the Rust crate cannot be built here (no cargo).
+    They restate src/count_reads/counters.rs, chunked_genome.rs, introns.rs
+    line by line (citations on each function).
+  * count_reads_weighted: does not exist in the reference (src/lib.rs:288-295);
+    defined here -- PARITY UNPINNED.
+
+Third-party behaviour restated from the published APIs (sources absent):
+rust-htslib 0.24.0 (fetch/read/aux/aligned_blocks/introns) and bio 0.25.0
+IntervalTree::find (half-open overlap).
+"""
+from __future__ import annotations
+
+import os
+import sys
+from collections import defaultdict
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mbf_bam_b200.synth.bamio import aux_get_int, read_bam  # noqa: E402
+
+CHUNK_SIZE = 1_000_000  # reference src/count_reads/chunked_genome.rs:75
+U32 = 0xFFFFFFFF
+
+
+def cigar_blocks(pos, cigar):
+    """rust-htslib aligned_blocks via reference src/bam_ext.rs:29-34: M/=/X emit, D/N advance."""
+    out = []
+    p = pos
+    for op, ln in cigar:
+        if op in (0, 7, 8):
+            out.append((p & U32, (p + ln) & U32))
+            p += ln
+        elif op in (2, 3):
+            p += ln
+    return out
+
+
+def cigar_introns(pos, cigar):
+    """rust-htslib introns via reference src/bam_ext.rs:36-41: N emits, M/=/X/D advance."""
+    out = []
+    p = pos
+    for op, ln in cigar:
+        if op == 3:
+            out.append((p & U32, (p + ln) & U32))
+            p += ln
+        elif op in (0, 2, 7, 8):
+            p += ln
+    return out
+
+
+def build_intervals(lst):
+    """reference src/count_reads/mod.rs:27-45: gene_no = list index; zip(starts, stops)."""
+    ivs = []
+    gene_ids = []
+    for gene_no, (gid, strand, starts, stops) in enumerate(lst):
+        gene_ids.append(gid)
+        for s, e in zip(starts, stops):
+            if s > e:
+                raise ValueError("interval start > end")
+            ivs.append((s, e, gene_no, strand))
+    return ivs, gene_ids
+
+
+def find(ivs, b0, b1):
+    """bio IntervalTree::find: overlap iff iv.start < b1 and b0 < iv.end (order-free here)."""
+    return [iv for iv in ivs if iv[0] < b1 and b0 < iv[1]]
+
+
+def chunk_fixed_points(gene_ivs, stop):
+    """All fixed points reachable by `while some iv covers stop: stop = iv.end + 1`
+    (reference chunked_genome.rs:93-109).  More than one => result depends on bio's
+    tree order; callers reject such gene sets."""
+    seen = set()
+    finals = set()
+    stack = [stop]
+    while stack:
+        s = stack.pop()
+        if s in seen:
+            continue
+        seen.add(s)
+        cov = [iv for iv in gene_ivs if iv[0] <= s < iv[1]]
+        if not cov:
+            finals.add(s)
+        for iv in cov:
+            stack.append(iv[1] + 1)
+    return finals
+
+
+def make_chunks(contigs, gene_sets):
+    """reference chunked_genome.rs:72-119. contigs: [(name, tid, length)]; gene_sets: name->ivs or None."""
+    chunks = []
+    for name, tid, length in contigs:
+        start = 0
+        while True:
+            stop = start + CHUNK_SIZE
+            if gene_sets is not None:
+                fin = chunk_fixed_points(gene_sets[name], stop)
+                if len(fin) != 1:
+                    raise ValueError("chunk edge depends on interval-tree order")
+                stop = fin.pop()
+            chunks.append((name, tid, start, stop))
+            start = stop
+            if start >= length:
+                break
+    return chunks
+
+
+def _nh(rec):
+    found, val = aux_get_int(rec.aux, b"NH")
+    if not found:
+        return 1  # counters.rs:66 map_or(1, ...)
+    if val is None:
+        raise ValueError("NH tag is not an integer")
+    return val
+
+
+def _count(path, intervals, gene_intervals, mode, each_read_counts_once=False):
+    if each_read_counts_once:
+        raise NotImplementedError("each_read_counts_once=True depends on bio's AVL order")
+    hdr, recs = read_bam(path)
+    name2tid = {n: i for i, (n, _) in enumerate(hdr.refs)}
+    trees = {c: build_intervals(l) for c, l in intervals.items()}
+    gene_trees = {c: build_intervals(l) for c, l in gene_intervals.items()}
+    contigs = [(c, name2tid[c], hdr.refs[name2tid[c]][1]) for c in gene_trees if c in name2tid]
+    for c, _, _ in contigs:
+        if c not in trees:
+            raise ValueError("contig %r is in gene_intervals but not in intervals" % c)
+    chunks = make_chunks(contigs, {c: gene_trees[c][0] for c, _, _ in contigs})
+    by_tid = defaultdict(list)
+    for r in recs:
+        by_tid[r.tid].append(r)
+    fwd = defaultdict(int)
+    rev = defaultdict(int)
+    weighted = mode == "weighted"
+    outside_total = 0
+    for chr_, tid, start, stop in chunks:
+        ivs, gene_ids = trees[chr_]
+        n = len(gene_ids)
+        res = [[0] * n, [0] * n]
+        mm = [defaultdict(set), defaultdict(set)]
+        outside = 0
+        for r in by_tid.get(tid, ()):
+            upos = r.pos & U32
+            if upos < start or upos >= stop:      # counters.rs:46-48 / :137-139
+                continue
+            seen = [set(), set()]
+            hit = False
+            for b0, b1 in cigar_blocks(r.pos, r.cigar):
+                if mode == "unstranded" and b0 >= stop:  # counters.rs:52 (live clause)
+                    continue
+                for (s, e, gene_no, strand) in find(ivs, b0, b1):
+                    hit = True
+                    nh = _nh(r)
+                    if mode == "unstranded":
+                        bucket = 0
+                    else:                          # counters.rs:151
+                        rv = bool(r.flag & 0x10)
+                        bucket = 0 if ((strand == 1 and not rv) or (strand != 1 and rv)) else 1
+                    if weighted or nh == 1:
+                        seen[bucket].add(gene_no)
+                    else:
+                        mm[bucket][gene_no].add(r.qname)
+            if not hit:
+                outside += 1
+            if weighted:
+                nh = _nh(r) if hit else 1
+                w = 1.0 / nh if nh >= 1 else 1.0
+            else:
+                w = 1
+            for b in (0, 1):
+                for g in seen[b]:
+                    res[b][g] += w
+        for b in (0, 1):
+            for g, s in mm[b].items():
+                res[b][g] += len(s)
+        # result assembly: counters.rs:236-254 (unstranded) / :262-273,:309-314 (stranded)
+        if mode == "unstranded":
+            d = {}
+            total = 0
+            for g, cnt in enumerate(res[0]):
+                d[gene_ids[g]] = cnt              # insert: last duplicate id wins
+                total += cnt
+            d["_total"] = total
+            d["_outside"] = outside
+            d["_" + chr_] = total
+            for k, v in d.items():
+                fwd[k] += v
+        else:
+            for b, tgt in ((0, fwd), (1, rev)):
+                d = defaultdict(int)
+                total = 0
+                for g, cnt in enumerate(res[b]):
+                    d[gene_ids[g]] += cnt
+                    total += cnt
+                d["_total"] = total
+                d["_" + chr_] = total
+                for k, v in d.items():
+                    tgt[k] += v
+            fwd["_outside"] += outside
+        outside_total += outside
+    if mode == "unstranded":
+        return dict(fwd)
+    return dict(fwd), dict(rev)
+
+
+def count_reads_unstranded(path, index_path, intervals, gene_intervals, each_read_counts_once=None):
+    """reference src/lib.rs:138-157 -> counters.rs:204-260, :26-106."""
+    return _count(path, intervals, gene_intervals, "unstranded", bool(each_read_counts_once))
+
+
+def count_reads_stranded(path, index_path, intervals, gene_intervals, each_read_counts_once=None):
+    """reference src/lib.rs:161-181 -> counters.rs:276-323, :114-202."""
+    return _count(path, intervals, gene_intervals, "stranded", bool(each_read_counts_once))
+
+
+def count_reads_weighted(path, index_path, intervals, gene_intervals, each_read_counts_once=None):
+    """NOT IN THE REFERENCE (north_star names it).  Definition: the stranded skeleton
+    (no block filter, strand rule of counters.rs:151); every record adds 1/NH (NH
+    missing or < 1 -> 1) once per distinct gene it hits, f64; no qname dedup;
+    `_total`/`_<chr>` are the float sums, `_outside` stays an integer count."""
+    return _count(path, intervals, gene_intervals, "weighted", bool(each_read_counts_once))
+
+
+def count_introns(path, index_path=None):
+    """reference src/lib.rs:216-225 -> introns.rs:56-88, :24-51."""
+    hdr, recs = read_bam(path)
+    contigs = [(n, i, l) for i, (n, l) in enumerate(hdr.refs)]
+    chunks = make_chunks(contigs, None)
+    by_tid = defaultdict(list)
+    for r in recs:
+        by_tid[r.tid].append(r)
+    out = {}
+    for chr_, tid, start, stop in chunks:
+        d = out.setdefault(chr_, {})
+        for r in by_tid.get(tid, ()):
+            upos = r.pos & U32
+            if upos < start or upos >= stop:
+                continue
+            k = 0
+            for s, e in cigar_introns(r.pos, r.cigar):
+                d[(s, e)] = d.get((s, e), 0) + 1
+                k += 1
+            key = (U32, U32 - k)
+            d[key] = d.get(key, 0) + 1
+    return out
