@@ -1,0 +1,9 @@
+"""Compatibility shim: `import mbf_bam` resolves to the B200 implementation, mirroring
+reference src/mbf_bam/__init__.py:11 (`from .mbf_bam import *`)."""
+from mbf_bam_b200 import (  # noqa: F401
+    __version__,
+    count_introns,
+    count_reads_stranded,
+    count_reads_unstranded,
+    count_reads_weighted,
+)

@@ -1,0 +1,33 @@
+"""mbf_bam_b200 -- B200-native (sm_100a) read counters with mbf_bam's Python API.
+
+Drop-in for the counting functions of `mbf_bam` (reference src/mbf_bam/__init__.py:11
+star-imports the native module; reference src/lib.rs:286-299 lists its functions):
+
+    count_reads_unstranded(filename, index_filename, intervals, gene_intervals, each_read_counts_once=None)
+    count_reads_stranded(...)      -> (forward_dict, reverse_dict)
+    count_reads_weighted(...)      -> (forward_dict, reverse_dict) of 1/NH weighted floats (new)
+    count_introns(filename, index_filename=None)
+
+The native module is built in-tree by `__graft_entry__.build()` (or `make -C mbf_bam_b200/csrc`).
+There is no CPU implementation behind these names: importing works anywhere, calling needs a GPU.
+"""
+try:
+    from .mbf_bam import (  # noqa: F401
+        Reader,
+        __version__,
+        cigar_expand,
+        count_introns,
+        count_reads_stranded,
+        count_reads_unstranded,
+        count_reads_weighted,
+        device_count,
+        inflate_buffer,
+        last_stats,
+    )
+except ImportError as e:  # pragma: no cover
+    raise ImportError(
+        "mbf_bam_b200: the native extension is not built (run `python -c 'import __graft_entry__ as g; "
+        "g.build()'` or `make -C mbf_bam_b200/csrc`): %s" % (e,)
+    ) from e
+
+MODE_UNSTRANDED, MODE_STRANDED, MODE_WEIGHTED = 0, 1, 2

@@ -1,0 +1,978 @@
+// libmbfbam_cuda.so: window pipeline + C ABI (include/mbfbam.h).
+//
+// Per job the host plans BGZF byte ranges from the BAI, then streams them through the GPU in
+// windows of W compressed bytes:
+//
+//   front stage (stream s_front):  H2D copy (or a view into the preloaded file) -> K0 block scan
+//                                  -> chain proof -> ISIZE scan -> WinMeta to the host
+//   main stage  (stream s_main):   K1 inflate -> K2 frame -> carry -> K3-5 count | K6 introns
+//
+// Window k+1's front stage runs while window k's main stage is executing.  All per-window device
+// arrays are double buffered.  The host reads WinMeta only to size buffers (U, record offsets, the
+// multi-mapper set, the intron map); it never touches alignment data.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <chrono>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "reader.hpp"
+
+using namespace mbf;
+
+#define MBFBAM_VERSION "0.1.0"
+
+namespace {
+
+std::string fmt(const char* f, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            throw Error(MBFBAM_ERR_CUDA, fmt("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), \
+                                             __FILE__, __LINE__, #expr));                          \
+    } while (0)
+
+double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (uint32_t)strtoul(v, nullptr, 10);
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    // grows without preserving contents
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        CK(cudaMalloc(&p, n));
+        cap = n;
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) CK(cudaFreeHost(p));
+        p = nullptr;
+        CK(cudaMallocHost(&p, n));
+        cap = n;
+    }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+template <class T>
+T* upload(DevBuf& b, const std::vector<T>& v, cudaStream_t s) {
+    b.ensure(std::max<size_t>(16, v.size() * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return b.as<T>();
+}
+
+// Where compressed bytes come from.
+struct Source {
+    virtual ~Source() {}
+    virtual uint64_t size() const = 0;
+    virtual void read(uint64_t off, size_t n, uint8_t* dst) const = 0;
+    virtual const uint8_t* resident(int device) const { return nullptr; }  // device copy of the whole file
+};
+struct FileSource : Source {
+    const Reader* r;
+    explicit FileSource(const Reader* r_) : r(r_) {}
+    uint64_t size() const override { return r->file_size; }
+    void read(uint64_t off, size_t n, uint8_t* dst) const override { r->pread_exact(dst, off, n); }
+    const uint8_t* resident(int device) const override { return r->preload_device == device ? r->preload_ptr : nullptr; }
+};
+struct MemSource : Source {
+    const uint8_t* p;
+    uint64_t n;
+    MemSource(const uint8_t* p_, uint64_t n_) : p(p_), n(n_) {}
+    uint64_t size() const override { return n; }
+    void read(uint64_t off, size_t len, uint8_t* dst) const override { memcpy(dst, p + off, len); }
+};
+
+enum JobKind { JOB_COUNT, JOB_INTRONS, JOB_INFLATE };
+
+struct WinBufs {
+    PinnedBuf h_c;
+    DevBuf d_c;
+    DevBuf tile_count, tile_base, cand_pos, cand_bsize;
+    DevBuf cpos, clen, isize, uoff;
+    DevBuf blk_start, blk_end, blk_nrec, rec_base, rec_off;
+    DevBuf mm_fp, mm_slot;
+    uint32_t mm_cap = 0;
+    const uint8_t* c_ptr = nullptr;  // device pointer of this window's bytes (d_c or a view of the preload)
+    uint64_t win_off = 0;
+    uint32_t scan_len = 0, avail = 0;
+    cudaEvent_t ev_front = nullptr, ev_main = nullptr;
+    cudaEvent_t t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool timed = false;
+    bool in_flight = false;
+    int range_start = 0;
+    uint64_t range_off = 0;
+    uint32_t first_uoff = 0;
+};
+
+struct Pipeline {
+    int device;
+    const Source* src;
+    JobKind kind;
+    mbfbam_stats st{};
+    uint32_t W;          // window size in compressed bytes
+    uint32_t cand_cap;
+    cudaStream_t s_front = nullptr, s_main = nullptr;
+    cudaEvent_t ev_reuse = nullptr;
+    WinBufs wb[2];
+    DevBuf U[2];
+    size_t U_cap = 0;    // data bytes (without prefix/slack)
+    DevBuf d_meta, d_chain, d_carry;
+    PinnedBuf h_meta_front, h_meta_main;
+    int sm_count = 148;
+    bool sync_debug = false;
+
+    // ---- counting job state
+    int mode = 0;
+    CountCtx cc{};
+    DevBuf d_tid2slot, d_slot_iv_off, d_iv_start, d_iv_end, d_iv_pmax, d_iv_gene, d_slot_chunk_off, d_chunk_stop;
+    DevBuf d_counts, d_wspill;
+    DevBuf d_set;
+    uint64_t set_cap = 0, set_ub = 0;
+    DevBuf d_set_size;
+    size_t n_genes = 0, n_count_words = 0;
+    // ---- intron job state
+    IntronCtx ic{};
+    DevBuf d_ref_chunk_off, d_map, d_hist, d_scalar;
+    unsigned long long* hist_ptr = nullptr;
+    uint64_t map_cap = 0, map_ub = 0;
+    // ---- inflate-only job
+    uint8_t* out_host = nullptr;
+    uint64_t out_cap = 0, out_len = 0;
+
+    Pipeline(int dev, const Source* s, JobKind k) : device(dev), src(s), kind(k) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw Error(MBFBAM_ERR_CUDA, fmt("no CUDA device available (%s); mbf_bam_b200 has no CPU path",
+                                             e == cudaSuccess ? "device count 0" : cudaGetErrorString(e)));
+        if (dev < 0 || dev >= n) throw Error(MBFBAM_ERR_ARG, fmt("device %d out of range (have %d)", dev, n));
+        CK(cudaSetDevice(dev));
+        CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        W = env_u32("MBF_BAM_WINDOW_MB", 32) << 20;
+        if (W < (1u << 20)) W = 1u << 20;
+        if (W > (1024u << 20)) W = 1024u << 20;
+        cand_cap = W / 64 + 1024;
+        sync_debug = env_u32("MBF_BAM_SYNC", 0) != 0;
+        CK(cudaStreamCreateWithFlags(&s_front, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s_main, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_reuse, cudaEventDisableTiming));
+        d_meta.ensure(2 * sizeof(WinMeta));
+        d_chain.ensure(sizeof(ChainState));
+        d_carry.ensure(16);
+        CK(cudaMemsetAsync(d_chain.p, 0, sizeof(ChainState), s_front));
+        CK(cudaMemsetAsync(d_carry.p, 0, 16, s_main));
+        h_meta_front.ensure(2 * sizeof(WinMeta));
+        h_meta_main.ensure(2 * sizeof(WinMeta));
+        for (int i = 0; i < 2; i++) {
+            WinBufs& w = wb[i];
+            CK(cudaEventCreateWithFlags(&w.ev_front, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&w.ev_main, cudaEventDisableTiming));
+            for (auto& t : w.t) CK(cudaEventCreate(&t));
+            size_t ntile = (size_t)W / SCAN_TILE + 2;
+            w.tile_count.ensure(ntile * 4);
+            w.tile_base.ensure(ntile * 4);
+            for (DevBuf* b : {&w.cand_pos, &w.cand_bsize, &w.cpos, &w.clen, &w.isize, &w.uoff, &w.blk_start,
+                              &w.blk_end, &w.blk_nrec, &w.rec_base})
+                b->ensure((size_t)(cand_cap + 8) * 4);
+        }
+        ensure_U((size_t)W * 5);
+    }
+    ~Pipeline() {
+        cudaSetDevice(device);
+        cudaDeviceSynchronize();
+        for (auto& w : wb) {
+            if (w.ev_front) cudaEventDestroy(w.ev_front);
+            if (w.ev_main) cudaEventDestroy(w.ev_main);
+            for (auto& t : w.t) if (t) cudaEventDestroy(t);
+        }
+        if (ev_reuse) cudaEventDestroy(ev_reuse);
+        if (s_front) cudaStreamDestroy(s_front);
+        if (s_main) cudaStreamDestroy(s_main);
+    }
+
+    void launched(const char* what, cudaStream_t s) {
+        st.n_kernel_launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) throw Error(MBFBAM_ERR_CUDA, fmt("launch of %s failed: %s", what, cudaGetErrorString(e)));
+        if (sync_debug) {
+            e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) throw Error(MBFBAM_ERR_CUDA, fmt("kernel %s failed: %s", what, cudaGetErrorString(e)));
+        }
+    }
+
+    WinMeta* dmeta(int i) { return d_meta.as<WinMeta>() + i; }
+
+    // (re)allocate both U buffers; preserves the carry prefix of buffer `keep` if >= 0
+    void ensure_U(size_t data_bytes, int keep = -1) {
+        if (data_bytes <= U_cap) return;
+        size_t cap = std::max(data_bytes, U_cap * 2);
+        if ((uint64_t)cap + U_PREFIX + 65536 > 0xffff0000ull) throw Error(MBFBAM_ERR_UNSUPPORTED, "window inflates past 4 GiB; lower MBF_BAM_WINDOW_MB");
+        CK(cudaStreamSynchronize(s_main));
+        for (int i = 0; i < 2; i++) {
+            DevBuf nb;
+            nb.ensure(cap + U_PREFIX + 65536);
+            if (i == keep && U[i].p) CK(cudaMemcpy(nb.p, U[i].p, U_PREFIX, cudaMemcpyDeviceToDevice));
+            std::swap(U[i].p, nb.p);
+            std::swap(U[i].cap, nb.cap);
+        }
+        U_cap = cap;
+        for (auto& w : wb) w.rec_off.ensure((cap / 36 + 64) * 4);
+    }
+
+    // ---------------------------------------------------------------- front stage
+    void issue_front(int bi, uint64_t win_off, uint32_t scan_len, uint64_t src_end, int range_start,
+                     uint64_t range_off, uint32_t first_uoff) {
+        WinBufs& w = wb[bi];
+        uint64_t want = (uint64_t)scan_len + 65536 + 64;
+        uint64_t avail = std::min<uint64_t>(want, src_end - win_off);
+        w.win_off = win_off;
+        w.scan_len = scan_len;
+        w.avail = (uint32_t)avail;
+        w.range_start = range_start;
+        w.range_off = range_off;
+        w.first_uoff = first_uoff;
+        const uint8_t* res = src->resident(device);
+        if (res) {
+            w.c_ptr = res + win_off;
+        } else {
+            w.h_c.ensure((size_t)W + 65536 + 256);
+            w.d_c.ensure((size_t)W + 65536 + 256);
+            src->read(win_off, (size_t)avail, w.h_c.as<uint8_t>());
+            memset(w.h_c.as<uint8_t>() + avail, 0, 128);
+            CK(cudaMemcpyAsync(w.d_c.p, w.h_c.p, (size_t)avail + 128, cudaMemcpyHostToDevice, s_front));
+            st.h2d_bytes += avail;
+            w.c_ptr = w.d_c.as<uint8_t>();
+        }
+        st.compressed_bytes += scan_len;
+        CK(cudaEventRecord(w.t[0], s_front));
+        k_win_begin<<<1, 1, 0, s_front>>>(d_chain.as<ChainState>(), dmeta(bi), range_start, range_off, first_uoff);
+        launched("k_win_begin", s_front);
+        ScanArgs a{};
+        a.cbuf = w.c_ptr;
+        a.win_off = win_off;
+        a.scan_len = scan_len;
+        a.avail = (uint32_t)avail;
+        a.chain = d_chain.as<ChainState>();
+        a.meta = dmeta(bi);
+        a.tile_count = w.tile_count.as<uint32_t>();
+        a.tile_base = w.tile_base.as<uint32_t>();
+        a.cand_pos = w.cand_pos.as<uint32_t>();
+        a.cand_bsize = w.cand_bsize.as<uint32_t>();
+        a.cand_cap = cand_cap;
+        uint32_t ntile = (scan_len + SCAN_TILE - 1) / SCAN_TILE;
+        if (ntile) {
+            k_scan<false><<<ntile, SCAN_THREADS, 0, s_front>>>(a);
+            launched("k_scan<count>", s_front);
+        }
+        k_excl_scan<<<1, 1024, 0, s_front>>>(a.tile_count, a.tile_base, nullptr, ntile, 0, &dmeta(bi)->n_cand);
+        launched("k_excl_scan(tiles)", s_front);
+        if (ntile) {
+            k_scan<true><<<ntile, SCAN_THREADS, 0, s_front>>>(a);
+            launched("k_scan<emit>", s_front);
+        }
+        BlockArrays b{w.cpos.as<uint32_t>(), w.clen.as<uint32_t>(), w.isize.as<uint32_t>(), w.uoff.as<uint32_t>()};
+        k_blocks_finalize<<<std::max(1u, std::min(64u, cand_cap / 256)), 256, 0, s_front>>>(a, b);
+        launched("k_blocks_finalize", s_front);
+        k_excl_scan<<<1, 1024, 0, s_front>>>(b.isize, b.uoff, &dmeta(bi)->n_blocks, 0, U_PREFIX, &dmeta(bi)->u_total);
+        launched("k_excl_scan(isize)", s_front);
+        CK(cudaEventRecord(w.t[1], s_front));
+        CK(cudaMemcpyAsync(h_meta_front.as<WinMeta>() + bi, dmeta(bi), sizeof(WinMeta), cudaMemcpyDeviceToHost, s_front));
+        st.d2h_bytes += sizeof(WinMeta);
+        CK(cudaEventRecord(w.ev_front, s_front));
+        w.in_flight = true;
+    }
+
+    static std::string err_text(const WinMeta& m) {
+        const char* what = "unknown";
+        switch (m.err) {
+            case WERR_CHAIN: what = "BGZF block chain broken"; break;
+            case WERR_TRUNCATED: what = "truncated BGZF block"; break;
+            case WERR_ISIZE: what = "BGZF ISIZE > 64 KiB"; break;
+            case WERR_RECORD: what = "malformed BAM record"; break;
+            case WERR_CARRY: what = "BAM record larger than 4 MiB"; break;
+            case WERR_NH_TYPE: what = "NH tag is not an integer"; break;
+            case WERR_AUX: what = "malformed aux data"; break;
+            case WERR_CAPACITY: what = "too many BGZF blocks in one window (raise MBF_BAM_WINDOW_MB?)"; break;
+            default: if (m.err >= WERR_INFLATE) what = "corrupt DEFLATE stream in BGZF block"; break;
+        }
+        return fmt("Could not read bam: %s (code %u, info %u)", what, m.err, m.err_info);
+    }
+
+    // ---------------------------------------------------------------- main stage
+    void issue_main(int bi) {
+        WinBufs& w = wb[bi];
+        CK(cudaEventSynchronize(w.ev_front));
+        WinMeta m = h_meta_front.as<WinMeta>()[bi];
+        if (m.err) throw Error(MBFBAM_ERR_FORMAT, err_text(m));
+        ensure_U((size_t)m.u_total + 1024, bi);
+        st.n_bgzf_blocks += m.n_blocks;
+        st.uncompressed_bytes += m.u_total;
+        st.n_windows++;
+        CK(cudaStreamWaitEvent(s_main, w.ev_front, 0));
+        BlockArrays b{w.cpos.as<uint32_t>(), w.clen.as<uint32_t>(), w.isize.as<uint32_t>(), w.uoff.as<uint32_t>()};
+        CK(cudaEventRecord(w.t[2], s_main));
+        if (m.n_blocks) {
+            InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
+            k_inflate<<<m.n_blocks, 32, 0, s_main>>>(ia);
+            launched("k_inflate", s_main);
+        }
+        CK(cudaEventRecord(w.t[3], s_main));
+        if (kind == JOB_INFLATE) {
+            if (out_host) {
+                if (out_len + m.u_total > out_cap) throw Error(MBFBAM_ERR_ARG, "output buffer too small");
+                CK(cudaMemcpyAsync(out_host + out_len, U[bi].as<uint8_t>() + U_PREFIX, m.u_total, cudaMemcpyDeviceToHost, s_main));
+                st.d2h_bytes += m.u_total;
+            }
+            out_len += m.u_total;
+            CK(cudaEventRecord(w.t[4], s_main));
+            CK(cudaEventRecord(w.t[5], s_main));
+        } else {
+            FrameArgs fa{U[bi].as<uint8_t>(), b, nullptr, dmeta(bi), w.blk_start.as<uint32_t>(), w.blk_end.as<uint32_t>(),
+                         w.blk_nrec.as<uint32_t>(), w.rec_base.as<uint32_t>(), w.rec_off.as<uint32_t>(),
+                         (uint32_t)(w.rec_off.cap / 4)};
+            fa.carry = d_carry.as<uint32_t>();
+            uint32_t fgrid = std::max(1u, (m.n_blocks + 127) / 128);
+            k_frame_walk<false><<<fgrid, 128, 0, s_main>>>(fa);
+            launched("k_frame_walk<count>", s_main);
+            k_frame_fix<<<1, 32, 0, s_main>>>(fa);
+            launched("k_frame_fix", s_main);
+            k_excl_scan<<<1, 1024, 0, s_main>>>(fa.blk_nrec, fa.rec_base, &dmeta(bi)->n_blocks, 0, 0, &dmeta(bi)->n_records);
+            launched("k_excl_scan(records)", s_main);
+            k_frame_walk<true><<<fgrid, 128, 0, s_main>>>(fa);
+            launched("k_frame_walk<emit>", s_main);
+            k_carry_copy<<<1, 256, 0, s_main>>>(U[bi].as<uint8_t>(), U[bi ^ 1].as<uint8_t>(), d_carry.as<uint32_t>(), dmeta(bi));
+            launched("k_carry_copy", s_main);
+            CK(cudaEventRecord(w.t[4], s_main));
+            if (kind == JOB_COUNT) launch_count(bi, 0);
+            else launch_introns(bi, 1);
+            CK(cudaEventRecord(w.t[5], s_main));
+        }
+        CK(cudaMemcpyAsync(h_meta_main.as<WinMeta>() + bi, dmeta(bi), sizeof(WinMeta), cudaMemcpyDeviceToHost, s_main));
+        st.d2h_bytes += sizeof(WinMeta);
+        CK(cudaEventRecord(w.ev_main, s_main));
+        w.timed = true;
+    }
+
+    int count_grid() const { return sm_count * 8; }
+
+    void launch_count(int bi, int emit_only) {
+        WinBufs& w = wb[bi];
+        if (!w.mm_cap) {
+            w.mm_cap = std::max<uint32_t>(env_u32("MBF_BAM_MM_CAP", 1u << 20), 16);
+            w.mm_fp.ensure((size_t)w.mm_cap * 16);
+            w.mm_slot.ensure((size_t)w.mm_cap * 4);
+        }
+        CountCtx c = cc;
+        c.U = U[bi].as<uint8_t>();
+        c.rec_off = w.rec_off.as<uint32_t>();
+        c.meta = dmeta(bi);
+        c.mm_fp = w.mm_fp.as<ulonglong2>();
+        c.mm_slot = w.mm_slot.as<uint32_t>();
+        c.mm_cap = w.mm_cap;
+        c.emit_only = emit_only;
+        if (mode == MBFBAM_MODE_UNSTRANDED) k_count_reads<0><<<count_grid(), 256, 0, s_main>>>(c);
+        else if (mode == MBFBAM_MODE_STRANDED) k_count_reads<1><<<count_grid(), 256, 0, s_main>>>(c);
+        else k_count_reads<2><<<count_grid(), 256, 0, s_main>>>(c);
+        launched("k_count_reads", s_main);
+    }
+
+    void launch_introns(int bi, int count_only) {
+        WinBufs& w = wb[bi];
+        IntronCtx c = ic;
+        c.U = U[bi].as<uint8_t>();
+        c.rec_off = w.rec_off.as<uint32_t>();
+        c.meta = dmeta(bi);
+        c.map = d_map.as<ulonglong2>();
+        c.map_mask = (uint32_t)(map_cap - 1);
+        c.count_only = count_only;
+        k_count_introns<<<count_grid(), 256, 0, s_main>>>(c);
+        launched("k_count_introns", s_main);
+    }
+
+    // grow the multi-mapper set so that `extra` more keys keep the load factor <= 1/2
+    void ensure_set(uint64_t extra) {
+        if ((set_ub + extra) * 2 <= set_cap) { set_ub += extra; return; }
+        CK(cudaStreamSynchronize(s_main));
+        unsigned long long live = 0;
+        if (set_cap) CK(cudaMemcpy(&live, d_set_size.p, 8, cudaMemcpyDeviceToHost));
+        set_ub = live + extra;
+        if (set_ub * 2 <= set_cap) return;
+        uint64_t ncap = 1u << 16;
+        while (ncap < set_ub * 4) ncap <<= 1;
+        if (ncap > (1ull << 31)) throw Error(MBFBAM_ERR_UNSUPPORTED, "multi-mapper set exceeds 2^31 slots");
+        DevBuf nb;
+        nb.ensure(ncap * 16);
+        CK(cudaMemsetAsync(nb.p, 0, ncap * 16, s_main));
+        if (set_cap) {
+            k_set_rehash<<<sm_count * 8, 256, 0, s_main>>>(d_set.as<ulonglong2>(), (uint32_t)set_cap, nb.as<ulonglong2>(), (uint32_t)(ncap - 1));
+            launched("k_set_rehash", s_main);
+            CK(cudaStreamSynchronize(s_main));
+        }
+        std::swap(d_set.p, nb.p);
+        std::swap(d_set.cap, nb.cap);
+        set_cap = ncap;
+    }
+
+    void ensure_map(uint64_t extra) {
+        if ((map_ub + extra) * 2 <= map_cap) { map_ub += extra; return; }
+        CK(cudaStreamSynchronize(s_main));
+        unsigned long long live = 0;
+        if (map_cap) {
+            CK(cudaMemsetAsync(d_scalar.p, 0, 8, s_main));
+            k_map_count<<<sm_count * 8, 256, 0, s_main>>>(d_map.as<ulonglong2>(), (uint32_t)map_cap, d_scalar.as<unsigned long long>());
+            launched("k_map_count", s_main);
+            CK(cudaMemcpyAsync(&live, d_scalar.p, 8, cudaMemcpyDeviceToHost, s_main));
+            CK(cudaStreamSynchronize(s_main));
+        }
+        map_ub = live + extra;
+        if (map_ub * 2 <= map_cap) return;
+        uint64_t ncap = 1u << 16;
+        while (ncap < map_ub * 4) ncap <<= 1;
+        if (ncap > (1ull << 31)) throw Error(MBFBAM_ERR_UNSUPPORTED, "intron map exceeds 2^31 slots");
+        DevBuf nb;
+        nb.ensure(ncap * 16);
+        CK(cudaMemsetAsync(nb.p, 0xff, ncap * 16, s_main));
+        if (map_cap) {
+            k_map_rehash<<<sm_count * 8, 256, 0, s_main>>>(d_map.as<ulonglong2>(), (uint32_t)map_cap, nb.as<ulonglong2>(), (uint32_t)(ncap - 1));
+            launched("k_map_rehash", s_main);
+            CK(cudaStreamSynchronize(s_main));
+        }
+        std::swap(d_map.p, nb.p);
+        std::swap(d_map.cap, nb.cap);
+        map_cap = ncap;
+    }
+
+    // second half of a window's main stage: needs numbers from the first half
+    void finish_main(int bi) {
+        WinBufs& w = wb[bi];
+        if (!w.in_flight) return;
+        CK(cudaEventSynchronize(w.ev_main));
+        WinMeta m = h_meta_main.as<WinMeta>()[bi];
+        if (m.err) throw Error(MBFBAM_ERR_FORMAT, err_text(m));
+        st.n_records += m.n_records;
+        st.n_fixups += m.n_fixups;
+        if (kind == JOB_COUNT) {
+            st.n_records_owned += m.owned_records;
+            if (m.mm_count > w.mm_cap) {
+                // the key buffer overflowed: enlarge it and re-run the window in emit-only mode
+                CK(cudaStreamSynchronize(s_main));
+                w.mm_cap = m.mm_count + 1024;
+                w.mm_fp.ensure((size_t)w.mm_cap * 16);
+                w.mm_slot.ensure((size_t)w.mm_cap * 4);
+                CK(cudaMemsetAsync(&dmeta(bi)->mm_count, 0, 4, s_main));
+                launch_count(bi, 1);
+                CK(cudaMemcpyAsync(h_meta_main.as<WinMeta>() + bi, dmeta(bi), sizeof(WinMeta), cudaMemcpyDeviceToHost, s_main));
+                CK(cudaStreamSynchronize(s_main));
+                m = h_meta_main.as<WinMeta>()[bi];
+                if (m.mm_count > w.mm_cap) throw Error(MBFBAM_ERR_CUDA, "multi-mapper key buffer overflowed twice");
+            }
+            if (m.mm_count) {
+                st.n_mm_keys += m.mm_count;
+                ensure_set(m.mm_count);
+                k_mm_insert<<<sm_count * 4, 256, 0, s_main>>>(w.mm_fp.as<ulonglong2>(), w.mm_slot.as<uint32_t>(), dmeta(bi), w.mm_cap,
+                                                             d_set.as<ulonglong2>(), (uint32_t)(set_cap - 1),
+                                                             d_counts.as<unsigned long long>(), (uint32_t)n_genes,
+                                                             d_set_size.as<unsigned long long>());
+                launched("k_mm_insert", s_main);
+            }
+            outside_total += m.outside;
+        } else if (kind == JOB_INTRONS) {
+            st.n_records_owned += m.owned_records;
+            if (m.owned_records) {
+                ensure_map((uint64_t)m.cigar_ops + 64);
+                launch_introns(bi, 0);
+            }
+        }
+        if (w.timed) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, w.t[0], w.t[1]); st.ms_gpu_scan += ms;
+            cudaEventElapsedTime(&ms, w.t[2], w.t[3]); st.ms_gpu_inflate += ms;
+            cudaEventElapsedTime(&ms, w.t[3], w.t[4]); st.ms_gpu_frame += ms;
+            cudaEventElapsedTime(&ms, w.t[4], w.t[5]); st.ms_gpu_count += ms;
+            w.timed = false;
+        }
+        w.in_flight = false;
+    }
+    uint64_t outside_total = 0;
+
+    // ---------------------------------------------------------------- driver
+    void run(const std::vector<ByteRange>& ranges) {
+        struct Win { uint64_t off; uint32_t scan_len; uint64_t src_end; int range_start; uint64_t range_off; uint32_t first_uoff; };
+        std::vector<Win> wins;
+        for (const ByteRange& r : ranges) {
+            uint64_t pos = r.cbeg;
+            bool first = true;
+            while (pos < r.cend) {
+                uint64_t base = pos & ~(uint64_t)15;
+                uint64_t scan_end = std::min<uint64_t>(r.cend, base + W);
+                wins.push_back({base, (uint32_t)(scan_end - base), src->size(), first ? 1 : 0, r.cbeg, first ? r.first_uoff : 0u});
+                first = false;
+                pos = scan_end;
+            }
+        }
+        double t0 = now_ms();
+        if (!wins.empty()) {
+            const Win& w0 = wins[0];
+            issue_front(0, w0.off, w0.scan_len, w0.src_end, w0.range_start, w0.range_off, w0.first_uoff);
+        }
+        for (size_t k = 0; k < wins.size(); k++) {
+            int bi = (int)(k & 1);
+            finish_main(bi ^ 1);  // second half of window k-1 (must precede window k's carry copy)
+            issue_main(bi);
+            if (k + 1 < wins.size()) {
+                // buffers of parity bi^1 are reused: everything of window k-1 is queued on s_main by now
+                CK(cudaEventRecord(ev_reuse, s_main));
+                CK(cudaStreamWaitEvent(s_front, ev_reuse, 0));
+                const Win& wn = wins[k + 1];
+                issue_front(bi ^ 1, wn.off, wn.scan_len, wn.src_end, wn.range_start, wn.range_off, wn.first_uoff);
+            }
+        }
+        finish_main(0);
+        finish_main(1);
+        CK(cudaStreamSynchronize(s_main));
+        CK(cudaStreamSynchronize(s_front));
+        st.ms_gpu_all = now_ms() - t0;
+    }
+};
+
+// one pipeline call at a time per process keeps the pinned/device footprint bounded
+std::mutex g_mu;
+
+void copy_err(char* err, size_t errlen, const std::string& m) {
+    if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
+}
+
+template <class F>
+int guarded(char* err, size_t errlen, F&& f) {
+    try {
+        f();
+        return MBFBAM_OK;
+    } catch (const Error& e) {
+        copy_err(err, errlen, e.what());
+        return e.code;
+    } catch (const std::exception& e) {
+        copy_err(err, errlen, e.what());
+        return MBFBAM_ERR_CUDA;
+    }
+}
+
+struct ShardPlan {
+    std::vector<Chunk> chunks;       // all chunks, in contig order
+    size_t lo = 0, hi = 0;           // owned [lo, hi)
+    std::vector<ByteRange> ranges;
+};
+
+// contiguous chunk range of shard i of n, then the BGZF ranges that can hold its records
+void plan_shard(const Reader& r, ShardPlan& p, int shard, int nshards) {
+    if (nshards < 1 || shard < 0 || shard >= nshards) throw Error(MBFBAM_ERR_ARG, "bad shard index/count");
+    // balance by compressed bytes: weight of a chunk = span of its linear-index offsets
+    size_t n = p.chunks.size();
+    std::vector<double> w(n + 1, 0.0);
+    for (size_t i = 0; i < n; i++) {
+        const Chunk& c = p.chunks[i];
+        double wt = 1.0;
+        if (r.idx[(size_t)c.tid].has_reads) {
+            uint64_t a = r.voff_lower(c.tid, c.start) >> 16;
+            uint64_t b = c.stop >= r.lens[(size_t)c.tid] ? (r.idx[(size_t)c.tid].voff_end >> 16) : (r.voff_lower(c.tid, c.stop) >> 16);
+            if (b > a) wt += (double)(b - a);
+        }
+        w[i + 1] = w[i] + wt;
+    }
+    auto cut = [&](int s) -> size_t {
+        if (s <= 0) return 0;
+        if (s >= nshards) return n;
+        double target = w[n] * (double)s / (double)nshards;
+        return (size_t)(std::lower_bound(w.begin(), w.end(), target) - w.begin());
+    };
+    p.lo = std::min(cut(shard), n);
+    p.hi = std::min(std::max(cut(shard + 1), p.lo), n);
+    if (shard == nshards - 1) p.hi = n;
+    // byte ranges: per contiguous run of owned chunks on one tid
+    std::vector<std::pair<uint64_t, uint64_t>> vr;
+    size_t i = p.lo;
+    while (i < p.hi) {
+        size_t j = i;
+        while (j + 1 < p.hi && p.chunks[j + 1].tid == p.chunks[i].tid) j++;
+        const Chunk &a = p.chunks[i], &b = p.chunks[j];
+        const RefIndex& ri = r.idx[(size_t)a.tid];
+        if (ri.has_reads) {
+            uint64_t v0 = r.voff_lower(a.tid, a.start);
+            uint64_t v1 = r.voff_upper(a.tid, b.stop);
+            if (v1 > v0) vr.push_back({v0, v1});
+        }
+        i = j + 1;
+    }
+    std::sort(vr.begin(), vr.end());
+    for (auto& x : vr) add_range(p.ranges, x.first, x.second, r.file_size);
+}
+
+}  // namespace
+
+struct mbfbam_reader {
+    Reader r;
+    DevBuf preload;
+};
+
+extern "C" {
+
+const char* mbfbam_version(void) { return MBFBAM_VERSION; }
+
+int32_t mbfbam_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int mbfbam_open(const char* bam_path, const char* bai_path, mbfbam_reader** out, char* err, size_t errlen) {
+    *out = nullptr;
+    return guarded(err, errlen, [&] {
+        std::unique_ptr<mbfbam_reader> h(new mbfbam_reader());
+        h->r.open(bam_path, bai_path);
+        *out = h.release();
+    });
+}
+
+void mbfbam_close(mbfbam_reader* r) {
+    if (!r) return;
+    if (r->r.preload_device >= 0) cudaSetDevice(r->r.preload_device);
+    delete r;
+}
+
+int32_t mbfbam_n_targets(const mbfbam_reader* r) { return (int32_t)r->r.names.size(); }
+const char* mbfbam_target_name(const mbfbam_reader* r, int32_t tid) {
+    return tid >= 0 && (size_t)tid < r->r.names.size() ? r->r.names[(size_t)tid].c_str() : nullptr;
+}
+uint32_t mbfbam_target_len(const mbfbam_reader* r, int32_t tid) {
+    return tid >= 0 && (size_t)tid < r->r.lens.size() ? r->r.lens[(size_t)tid] : 0;
+}
+int32_t mbfbam_tid(const mbfbam_reader* r, const char* name) {
+    auto it = r->r.name2tid.find(name);
+    return it == r->r.name2tid.end() ? -1 : it->second;
+}
+
+int mbfbam_preload(mbfbam_reader* r, int32_t device, char* err, size_t errlen) {
+    return guarded(err, errlen, [&] {
+        std::lock_guard<std::mutex> lk(g_mu);
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) throw Error(MBFBAM_ERR_CUDA, "no such CUDA device");
+        CK(cudaSetDevice(device));
+        r->preload.ensure(r->r.file_size + 65536 + 4096);
+        CK(cudaMemset((uint8_t*)r->preload.p + r->r.file_size, 0, 65536 + 4096));
+        PinnedBuf stage;
+        const size_t CH = 64u << 20;
+        stage.ensure(CH);
+        for (uint64_t off = 0; off < r->r.file_size; off += CH) {
+            size_t n2 = (size_t)std::min<uint64_t>(CH, r->r.file_size - off);
+            r->r.pread_exact(stage.p, off, n2);
+            CK(cudaMemcpy((uint8_t*)r->preload.p + off, stage.p, n2, cudaMemcpyHostToDevice));
+        }
+        r->r.preload_device = device;
+        r->r.preload_ptr = (uint8_t*)r->preload.p;
+    });
+}
+
+void mbfbam_drop_preload(mbfbam_reader* r) {
+    if (r->r.preload_device >= 0) cudaSetDevice(r->r.preload_device);
+    r->r.preload_device = -1;
+    r->r.preload_ptr = nullptr;
+    DevBuf tmp;
+    std::swap(tmp.p, r->preload.p);
+    std::swap(tmp.cap, r->preload.cap);
+}
+
+int64_t mbfbam_chunks(const mbfbam_reader* r, const mbfbam_intervals* gene_intervals, int32_t* tid, uint32_t* start,
+                      uint32_t* stop, int64_t cap) {
+    try {
+        std::vector<Chunk> c = make_chunks(r->r, gene_intervals);
+        for (size_t i = 0; i < c.size() && (int64_t)i < cap; i++) {
+            tid[i] = c[i].tid;
+            start[i] = c[i].start;
+            stop[i] = c[i].stop;
+        }
+        return (int64_t)c.size();
+    } catch (...) {
+        return -1;
+    }
+}
+
+int mbfbam_count_reads(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_counts* out, mbfbam_stats* stats, char* err,
+                       size_t errlen) {
+    if (stats) memset(stats, 0, sizeof *stats);
+    return guarded(err, errlen, [&] {
+        std::lock_guard<std::mutex> lk(g_mu);
+        double t0 = now_ms();
+        const Reader& r = rd->r;
+        const mbfbam_intervals* iv = job->intervals;
+        const mbfbam_intervals* gv = job->gene_intervals;
+        if (!iv || !gv || !out) throw Error(MBFBAM_ERR_ARG, "null argument");
+        if (job->mode < 0 || job->mode > 2) throw Error(MBFBAM_ERR_ARG, "bad mode");
+        if (job->each_read_counts_once)
+            throw Error(MBFBAM_ERR_UNSUPPORTED, "each_read_counts_once=True is not supported (it depends on bio's interval-tree iteration order)");
+        // gene slots
+        std::vector<uint64_t> gene_base((size_t)iv->n_contigs + 1, 0);
+        for (int c = 0; c < iv->n_contigs; c++) gene_base[(size_t)c + 1] = gene_base[(size_t)c] + iv->n_genes[c];
+        const size_t G = (size_t)gene_base[(size_t)iv->n_contigs];
+        if (G >= (1ull << 31)) throw Error(MBFBAM_ERR_UNSUPPORTED, "too many genes");
+        std::map<std::string, int> iv_index;
+        for (int c = 0; c < iv->n_contigs; c++) iv_index.emplace(iv->contig_names[c], c);
+        // chunks over gene_intervals ∩ header (chunked_genome.rs:17-31); every such contig must be in `intervals`
+        ShardPlan plan;
+        plan.chunks = make_chunks(r, gv);
+        std::vector<int32_t> tid2slot(r.names.size(), -1);
+        std::vector<int> slot_iv;  // slot -> contig index in iv
+        for (const Chunk& c : plan.chunks) {
+            if (tid2slot[(size_t)c.tid] >= 0) continue;
+            auto it = iv_index.find(r.names[(size_t)c.tid]);
+            if (it == iv_index.end())
+                throw Error(MBFBAM_ERR_ARG, "contig " + r.names[(size_t)c.tid] + " is in gene_intervals but not in intervals");
+            tid2slot[(size_t)c.tid] = (int32_t)slot_iv.size();
+            slot_iv.push_back(it->second);
+        }
+        if (out->scanned) {
+            memset(out->scanned, 0, (size_t)iv->n_contigs);
+            for (int c : slot_iv) out->scanned[c] = 1;
+        }
+        // chunk_stop per slot, chunk ids global in plan.chunks order (slots are created in that order too)
+        std::vector<uint32_t> slot_chunk_off(slot_iv.size() + 1, 0), chunk_stop;
+        {
+            size_t i = 0;
+            for (size_t s = 0; s < slot_iv.size(); s++) {
+                slot_chunk_off[s] = (uint32_t)chunk_stop.size();
+                int32_t tid = plan.chunks[i].tid;
+                while (i < plan.chunks.size() && plan.chunks[i].tid == tid) chunk_stop.push_back(plan.chunks[i++].stop);
+            }
+            slot_chunk_off[slot_iv.size()] = (uint32_t)chunk_stop.size();
+        }
+        plan_shard(r, plan, job->shard_index, job->shard_count < 1 ? 1 : job->shard_count);
+        // flattened, start-sorted interval tables per slot
+        std::vector<uint32_t> slot_iv_off(slot_iv.size() + 1, 0), ivs, ive, ivp, ivg;
+        for (size_t s = 0; s < slot_iv.size(); s++) {
+            int c = slot_iv[s];
+            SortedIntervals si = sort_intervals(iv, c);
+            slot_iv_off[s] = (uint32_t)ivs.size();
+            for (size_t k = 0; k < si.start.size(); k++) {
+                if (si.gene[k] >= iv->n_genes[c]) throw Error(MBFBAM_ERR_ARG, "gene index out of range");
+                ivs.push_back(si.start[k]);
+                ive.push_back(si.end[k]);
+                ivp.push_back(si.pmax[k]);
+                ivg.push_back((uint32_t)(gene_base[(size_t)c] + si.gene[k]) | (si.strand[k] == 1 ? 0x80000000u : 0u));
+            }
+        }
+        slot_iv_off[slot_iv.size()] = (uint32_t)ivs.size();
+
+        FileSource src(&r);
+        Pipeline p(job->device, &src, JOB_COUNT);
+        p.mode = job->mode;
+        p.n_genes = G;
+        p.n_count_words = (job->mode == MBFBAM_MODE_WEIGHTED ? (size_t)NH_DENSE * 2 : 2) * std::max<size_t>(G, 1);
+        p.d_counts.ensure(p.n_count_words * 8);
+        CK(cudaMemsetAsync(p.d_counts.p, 0, p.n_count_words * 8, p.s_main));
+        p.d_wspill.ensure(std::max<size_t>(G, 1) * 16);
+        CK(cudaMemsetAsync(p.d_wspill.p, 0, std::max<size_t>(G, 1) * 16, p.s_main));
+        p.d_set_size.ensure(8);
+        CK(cudaMemsetAsync(p.d_set_size.p, 0, 8, p.s_main));
+        CountCtx& c = p.cc;
+        c.tid2slot = upload(p.d_tid2slot, tid2slot, p.s_main);
+        c.n_ref = (int32_t)tid2slot.size();
+        c.slot_iv_off = upload(p.d_slot_iv_off, slot_iv_off, p.s_main);
+        c.iv_start = upload(p.d_iv_start, ivs, p.s_main);
+        c.iv_end = upload(p.d_iv_end, ive, p.s_main);
+        c.iv_pmax = upload(p.d_iv_pmax, ivp, p.s_main);
+        c.iv_gene = upload(p.d_iv_gene, ivg, p.s_main);
+        c.slot_chunk_off = upload(p.d_slot_chunk_off, slot_chunk_off, p.s_main);
+        c.chunk_stop = upload(p.d_chunk_stop, chunk_stop, p.s_main);
+        c.chunk_lo = (uint32_t)plan.lo;
+        c.chunk_hi = (uint32_t)plan.hi;
+        c.counts = p.d_counts.as<unsigned long long>();
+        c.wspill = p.d_wspill.as<double>();
+        c.n_genes = (uint32_t)G;
+        CK(cudaStreamSynchronize(p.s_main));  // uploads come from stack vectors
+        p.st.n_chunks = plan.hi - plan.lo;
+        p.run(plan.ranges);
+        // results
+        std::vector<unsigned long long> h(p.n_count_words);
+        CK(cudaMemcpy(h.data(), p.d_counts.p, p.n_count_words * 8, cudaMemcpyDeviceToHost));
+        p.st.d2h_bytes += p.n_count_words * 8;
+        if (job->mode == MBFBAM_MODE_WEIGHTED) {
+            std::vector<double> sp(2 * std::max<size_t>(G, 1));
+            CK(cudaMemcpy(sp.data(), p.d_wspill.p, sp.size() * 8, cudaMemcpyDeviceToHost));
+            p.st.d2h_bytes += sp.size() * 8;
+            for (size_t g = 0; g < G; g++) {
+                for (int b = 0; b < 2; b++) {
+                    double acc = 0.0;
+                    for (int k = 0; k < NH_DENSE; k++) {
+                        unsigned long long n = h[((size_t)k * 2 + b) * G + g];
+                        if (n) acc += (double)n / (double)(k + 1);
+                    }
+                    acc += sp[(size_t)b * G + g];
+                    double* dst = b ? out->wrev : out->wfwd;
+                    if (dst) dst[g] = acc;
+                }
+                if (out->fwd) out->fwd[g] = 0;
+                if (out->rev) out->rev[g] = 0;
+            }
+        } else {
+            for (size_t g = 0; g < G; g++) {
+                if (out->fwd) out->fwd[g] = h[g];
+                if (out->rev) out->rev[g] = h[G + g];
+            }
+        }
+        out->outside = p.outside_total;
+        p.st.ms_total = now_ms() - t0;
+        if (stats) *stats = p.st;
+    });
+}
+
+int mbfbam_count_introns(mbfbam_reader* rd, int32_t device, int32_t shard_index, int32_t shard_count, mbfbam_introns* out,
+                         mbfbam_stats* stats, char* err, size_t errlen) {
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (out) memset(out, 0, sizeof *out);
+    return guarded(err, errlen, [&] {
+        std::lock_guard<std::mutex> lk(g_mu);
+        double t0 = now_ms();
+        const Reader& r = rd->r;
+        if (!out) throw Error(MBFBAM_ERR_ARG, "null argument");
+        ShardPlan plan;
+        plan.chunks = make_chunks(r, nullptr);
+        std::vector<uint32_t> ref_chunk_off(r.names.size() + 1, 0);
+        for (const Chunk& c : plan.chunks) ref_chunk_off[(size_t)c.tid + 1]++;
+        for (size_t i = 0; i < r.names.size(); i++) ref_chunk_off[i + 1] += ref_chunk_off[i];
+        plan_shard(r, plan, shard_index, shard_count < 1 ? 1 : shard_count);
+        FileSource src(&r);
+        Pipeline p(device, &src, JOB_INTRONS);
+        const size_t n_ref = r.names.size();
+        p.d_hist.ensure(std::max<size_t>(1, n_ref) * HIST_DENSE * 8);
+        CK(cudaMemsetAsync(p.d_hist.p, 0, std::max<size_t>(1, n_ref) * HIST_DENSE * 8, p.s_main));
+        p.d_scalar.ensure(16);
+        p.ic.n_ref = (int32_t)n_ref;
+        p.ic.ref_chunk_off = upload(p.d_ref_chunk_off, ref_chunk_off, p.s_main);
+        p.ic.chunk_lo = (uint32_t)plan.lo;
+        p.ic.chunk_hi = (uint32_t)plan.hi;
+        p.ic.hist = p.d_hist.as<unsigned long long>();
+        CK(cudaStreamSynchronize(p.s_main));
+        p.ensure_map(1024);
+        p.st.n_chunks = plan.hi - plan.lo;
+        p.run(plan.ranges);
+        // pull the map and the dense histogram
+        std::vector<ulonglong2> slots((size_t)p.map_cap);
+        CK(cudaMemcpy(slots.data(), p.d_map.p, (size_t)p.map_cap * 16, cudaMemcpyDeviceToHost));
+        std::vector<unsigned long long> hist(std::max<size_t>(1, n_ref) * HIST_DENSE);
+        CK(cudaMemcpy(hist.data(), p.d_hist.p, hist.size() * 8, cudaMemcpyDeviceToHost));
+        p.st.d2h_bytes += (size_t)p.map_cap * 16 + hist.size() * 8;
+        size_t n = 0;
+        for (const auto& s : slots) if (!(s.x == ~0ull && s.y == ~0ull)) n++;
+        for (auto v : hist) if (v) n++;
+        out->tid = (int32_t*)malloc((n + 1) * 4);
+        out->start = (uint32_t*)malloc((n + 1) * 4);
+        out->stop = (uint32_t*)malloc((n + 1) * 4);
+        out->count = (uint64_t*)malloc((n + 1) * 8);
+        out->n_targets = (int32_t)n_ref;
+        out->contig_seen = (uint8_t*)calloc(n_ref + 1, 1);
+        size_t k = 0;
+        for (const auto& s : slots) {
+            if (s.x == ~0ull && s.y == ~0ull) continue;
+            out->tid[k] = (int32_t)(uint32_t)s.y;
+            out->start[k] = (uint32_t)s.x;
+            out->stop[k] = (uint32_t)(s.x >> 32);
+            out->count[k] = s.y >> 32;
+            k++;
+        }
+        for (size_t t = 0; t < n_ref; t++)
+            for (int q = 0; q < HIST_DENSE; q++)
+                if (hist[t * HIST_DENSE + q]) {
+                    out->tid[k] = (int32_t)t;
+                    out->start[k] = 0xffffffffu;
+                    out->stop[k] = 0xffffffffu - (uint32_t)q;
+                    out->count[k] = hist[t * HIST_DENSE + q];
+                    k++;
+                }
+        out->n = k;
+        // introns.rs:75-79: every chunk that was scanned inserts its contig key (possibly empty dict)
+        for (size_t i = plan.lo; i < plan.hi; i++) out->contig_seen[(size_t)plan.chunks[i].tid] = 1;
+        p.st.ms_total = now_ms() - t0;
+        if (stats) *stats = p.st;
+    });
+}
+
+void mbfbam_free_introns(mbfbam_introns* x) {
+    if (!x) return;
+    free(x->tid);
+    free(x->start);
+    free(x->stop);
+    free(x->count);
+    free(x->contig_seen);
+    memset(x, 0, sizeof *x);
+}
+
+int mbfbam_inflate_buffer(const uint8_t* bgzf, uint64_t n, uint8_t* out, uint64_t out_cap, uint64_t* out_len, int32_t device,
+                          mbfbam_stats* stats, char* err, size_t errlen) {
+    if (stats) memset(stats, 0, sizeof *stats);
+    return guarded(err, errlen, [&] {
+        std::lock_guard<std::mutex> lk(g_mu);
+        double t0 = now_ms();
+        MemSource src(bgzf, n);
+        Pipeline p(device, &src, JOB_INFLATE);
+        p.out_host = out;
+        p.out_cap = out_cap;
+        std::vector<ByteRange> ranges;
+        if (n) ranges.push_back({0, n, 0});
+        p.run(ranges);
+        if (out_len) *out_len = p.out_len;
+        p.st.ms_total = now_ms() - t0;
+        if (stats) *stats = p.st;
+    });
+}
+
+int mbfbam_cigar_expand(const uint32_t* cigar, int32_t n_ops, int32_t pos, int32_t want_introns, uint32_t* out_pairs,
+                        int32_t cap_pairs, int32_t* n_pairs, int32_t device, char* err, size_t errlen) {
+    return guarded(err, errlen, [&] {
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
+        CK(cudaSetDevice(device));
+        DevBuf d_c, d_o, d_n;
+        d_c.ensure(((size_t)n_ops + 2) * 4);
+        d_o.ensure(((size_t)cap_pairs + 1) * 8);
+        d_n.ensure(4);
+        if (n_ops) CK(cudaMemcpy(d_c.p, cigar, (size_t)n_ops * 4, cudaMemcpyHostToDevice));
+        k_cigar_expand<<<1, 1>>>(d_c.as<uint32_t>(), n_ops, pos, want_introns, d_o.as<uint32_t>(), cap_pairs, d_n.as<int>());
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(n_pairs, d_n.p, 4, cudaMemcpyDeviceToHost));
+        int m = std::min(*n_pairs, cap_pairs);
+        if (m > 0) CK(cudaMemcpy(out_pairs, d_o.p, (size_t)m * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+}  // extern "C"

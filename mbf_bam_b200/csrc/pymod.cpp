@@ -1,0 +1,456 @@
+// CPython host extension `mbf_bam_b200.mbf_bam` -- the C++ stand-in for the reference's Rust/PyO3
+// cdylib `mbf_bam.mbf_bam` (reference src/lib.rs).  It only converts Python objects to the flat
+// arrays of include/mbfbam.h, calls the C ABI of libmbfbam_cuda.so, and assembles the result
+// dicts.  No alignment data is touched here and there is no CPU counting path: without the CUDA
+// library / a GPU every call raises.
+//
+//   count_reads_unstranded   src/lib.rs:138-157 + map assembly of counters.rs:236-254
+//   count_reads_stranded     src/lib.rs:161-181 + counters.rs:262-273,309-314
+//   count_introns            src/lib.rs:216-225
+//   count_reads_weighted     not in the reference
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mbfbam.h"
+
+namespace py = pybind11;
+
+namespace {
+
+struct Flat {
+    std::vector<std::string> names;
+    std::vector<const char*> name_ptrs;
+    std::vector<uint32_t> n_genes;
+    std::vector<uint64_t> offs{0};
+    std::vector<uint32_t> st, en, ge;
+    std::vector<int8_t> sd;
+    std::vector<std::vector<std::string>> gene_ids;
+    mbfbam_intervals c{};
+};
+
+[[noreturn]] void value_error(const std::string& m) {
+    PyErr_SetString(PyExc_ValueError, m.c_str());
+    throw py::error_already_set();
+}
+
+// src/lib.rs:118-134 py_intervals_to_trees + src/count_reads/mod.rs:27-45 build_tree
+void flatten(const py::dict& d, Flat& f) {
+    try {
+        for (auto item : d) {
+            f.names.push_back(py::cast<std::string>(item.first));
+            if (!py::isinstance<py::list>(item.second)) value_error("Python error: interval value is not a list");
+            py::list lst = py::reinterpret_borrow<py::list>(item.second);
+            f.n_genes.push_back((uint32_t)lst.size());
+            f.gene_ids.emplace_back();
+            uint32_t gene_no = 0;
+            for (auto e : lst) {
+                if (!py::isinstance<py::tuple>(e)) value_error("Python error: interval entry is not a tuple");
+                py::tuple t = py::reinterpret_borrow<py::tuple>(e);
+                if (t.size() < 4) value_error("Python error: interval entry needs (gene_id, strand, starts, stops)");
+                f.gene_ids.back().push_back(py::cast<std::string>(t[0]));
+                long strand = py::cast<long>(t[1]);
+                if (strand < -128 || strand > 127) value_error("Python error: strand does not fit i8");
+                if (!py::isinstance<py::list>(t[2]) || !py::isinstance<py::list>(t[3]))
+                    value_error("Python error: starts/stops must be lists");
+                py::list s = py::reinterpret_borrow<py::list>(t[2]), e2 = py::reinterpret_borrow<py::list>(t[3]);
+                size_t n = std::min(s.size(), e2.size());  // zip() truncates (mod.rs:38)
+                for (size_t i = 0; i < n; i++) {
+                    long long a = py::cast<long long>(s[i]), b = py::cast<long long>(e2[i]);
+                    if (a < 0 || b < 0 || a > 0xffffffffLL || b > 0xffffffffLL) value_error("Python error: coordinate does not fit u32");
+                    f.st.push_back((uint32_t)a);
+                    f.en.push_back((uint32_t)b);
+                    f.ge.push_back(gene_no);
+                    f.sd.push_back((int8_t)strand);
+                }
+                gene_no++;
+            }
+            f.offs.push_back(f.st.size());
+        }
+    } catch (py::cast_error& e) {
+        value_error(std::string("Python error: ") + e.what());
+    }
+    for (auto& n : f.names) f.name_ptrs.push_back(n.c_str());
+    f.c.n_contigs = (int32_t)f.names.size();
+    f.c.contig_names = f.name_ptrs.data();
+    f.c.n_genes = f.n_genes.data();
+    f.c.iv_offsets = f.offs.data();
+    f.c.iv_start = f.st.data();
+    f.c.iv_end = f.en.data();
+    f.c.iv_gene = f.ge.data();
+    f.c.iv_strand = f.sd.data();
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+py::dict stats_dict(const mbfbam_stats& s) {
+    py::dict d;
+    d["n_records"] = s.n_records;
+    d["n_records_owned"] = s.n_records_owned;
+    d["n_bgzf_blocks"] = s.n_bgzf_blocks;
+    d["compressed_bytes"] = s.compressed_bytes;
+    d["uncompressed_bytes"] = s.uncompressed_bytes;
+    d["h2d_bytes"] = s.h2d_bytes;
+    d["d2h_bytes"] = s.d2h_bytes;
+    d["n_chunks"] = s.n_chunks;
+    d["n_kernel_launches"] = s.n_kernel_launches;
+    d["n_windows"] = s.n_windows;
+    d["n_mm_keys"] = s.n_mm_keys;
+    d["n_fixups"] = s.n_fixups;
+    d["ms_total"] = s.ms_total;
+    d["ms_gpu_scan"] = s.ms_gpu_scan;
+    d["ms_gpu_inflate"] = s.ms_gpu_inflate;
+    d["ms_gpu_frame"] = s.ms_gpu_frame;
+    d["ms_gpu_count"] = s.ms_gpu_count;
+    d["ms_gpu_other"] = s.ms_gpu_other;
+    d["ms_gpu_all"] = s.ms_gpu_all;
+    return d;
+}
+
+struct PyReader {
+    mbfbam_reader* r = nullptr;
+    mbfbam_stats last{};
+    int device = 0, shard_index = 0, shard_count = 1;
+
+    PyReader(const std::string& filename, py::object index_filename) {
+        char err[512] = {0};
+        std::string idx;
+        const char* ip = nullptr;
+        if (!index_filename.is_none()) {
+            idx = py::cast<std::string>(index_filename);
+            ip = idx.c_str();
+        }
+        if (mbfbam_open(filename.c_str(), ip, &r, err, sizeof err)) value_error(err);
+        device = env_int("MBF_BAM_DEVICE", 0);
+        const char* sh = getenv("MBF_BAM_SHARD");  // "i/n"
+        if (sh && strchr(sh, '/')) {
+            shard_index = atoi(sh);
+            shard_count = atoi(strchr(sh, '/') + 1);
+        }
+    }
+    ~PyReader() { mbfbam_close(r); }
+
+    void set_device(int d) { device = d; }
+    void set_shard(int i, int n) { shard_index = i; shard_count = n; }
+
+    void preload() {
+        char err[512] = {0};
+        int rc;
+        {
+            py::gil_scoped_release rel;
+            rc = mbfbam_preload(r, device, err, sizeof err);
+        }
+        if (rc) value_error(err);
+    }
+    void drop_preload() { mbfbam_drop_preload(r); }
+
+    std::vector<std::pair<std::string, uint32_t>> targets() const {
+        std::vector<std::pair<std::string, uint32_t>> v;
+        for (int32_t i = 0; i < mbfbam_n_targets(r); i++) v.push_back({mbfbam_target_name(r, i), mbfbam_target_len(r, i)});
+        return v;
+    }
+
+    py::list chunks(py::object gene_intervals) {
+        Flat g;
+        const mbfbam_intervals* gp = nullptr;
+        if (!gene_intervals.is_none()) {
+            flatten(py::cast<py::dict>(gene_intervals), g);
+            gp = &g.c;
+        }
+        int64_t n = mbfbam_chunks(r, gp, nullptr, nullptr, nullptr, 0);
+        if (n < 0) value_error("could not build the chunk table");
+        std::vector<int32_t> tid((size_t)n + 1);
+        std::vector<uint32_t> st((size_t)n + 1), en((size_t)n + 1);
+        mbfbam_chunks(r, gp, tid.data(), st.data(), en.data(), n);
+        py::list out;
+        for (int64_t i = 0; i < n; i++) out.append(py::make_tuple(tid[(size_t)i], st[(size_t)i], en[(size_t)i]));
+        return out;
+    }
+
+    // dense results: used by the dict assembly below and by the multi-process (one rank per GPU) merge
+    struct Raw {
+        Flat iv;
+        std::vector<uint64_t> fwd, rev;
+        std::vector<double> wfwd, wrev;
+        std::vector<uint8_t> scanned;
+        uint64_t outside = 0;
+    };
+
+    void run(int mode, const py::dict& intervals, const py::dict& gene_intervals, bool once, Raw& raw) {
+        Flat gv;
+        flatten(intervals, raw.iv);
+        flatten(gene_intervals, gv);
+        size_t G = 0;
+        for (uint32_t n : raw.iv.n_genes) G += n;
+        raw.fwd.assign(G + 1, 0);
+        raw.rev.assign(G + 1, 0);
+        raw.wfwd.assign(G + 1, 0.0);
+        raw.wrev.assign(G + 1, 0.0);
+        raw.scanned.assign(raw.iv.names.size() + 1, 0);
+        mbfbam_count_job job{};
+        job.intervals = &raw.iv.c;
+        job.gene_intervals = &gv.c;
+        job.mode = mode;
+        job.each_read_counts_once = once ? 1 : 0;
+        job.device = device;
+        job.shard_index = shard_index;
+        job.shard_count = shard_count;
+        mbfbam_counts out{};
+        out.fwd = raw.fwd.data();
+        out.rev = raw.rev.data();
+        out.wfwd = raw.wfwd.data();
+        out.wrev = raw.wrev.data();
+        out.scanned = raw.scanned.data();
+        char err[512] = {0};
+        int rc;
+        {
+            py::gil_scoped_release rel;  // superset of the reference, which keeps the GIL
+            rc = mbfbam_count_reads(r, &job, &out, &last, err, sizeof err);
+        }
+        if (rc) value_error(err);
+        raw.outside = out.outside;
+    }
+
+    // counters.rs:236-254 summed over chunks: per contig, `insert` keeps the LAST gene_no of a duplicated id
+    static py::dict assemble_unstranded(const Raw& raw) {
+        py::dict out;
+        std::map<std::string, uint64_t> acc;
+        size_t base = 0;
+        uint64_t total_all = 0;
+        bool any = false;
+        for (size_t c = 0; c < raw.iv.names.size(); c++) {
+            const auto& ids = raw.iv.gene_ids[c];
+            if (raw.scanned[c]) {
+                any = true;
+                std::map<std::string, uint64_t> last;
+                uint64_t tot = 0;
+                for (size_t g = 0; g < ids.size(); g++) {
+                    last[ids[g]] = raw.fwd[base + g];
+                    tot += raw.fwd[base + g];
+                }
+                for (auto& kv : last) acc[kv.first] += kv.second;
+                acc["_" + raw.iv.names[c]] += tot;
+                total_all += tot;
+            }
+            base += ids.size();
+        }
+        if (any) {
+            acc["_total"] += total_all;
+            acc["_outside"] += raw.outside;
+        }
+        for (auto& kv : acc) out[py::str(kv.first)] = py::int_(kv.second);
+        return out;
+    }
+
+    // counters.rs:262-273 (+= per gene id), :309-314 (_outside only in the forward dict)
+    template <class T>
+    static py::tuple assemble_dual(const Raw& raw, const std::vector<T>& f, const std::vector<T>& v) {
+        std::map<std::string, T> a, b;
+        size_t base = 0;
+        bool any = false;
+        for (size_t c = 0; c < raw.iv.names.size(); c++) {
+            const auto& ids = raw.iv.gene_ids[c];
+            if (raw.scanned[c]) {
+                any = true;
+                T ta = 0, tb = 0;
+                for (size_t g = 0; g < ids.size(); g++) {
+                    a[ids[g]] += f[base + g];
+                    b[ids[g]] += v[base + g];
+                    ta += f[base + g];
+                    tb += v[base + g];
+                }
+                a["_" + raw.iv.names[c]] += ta;
+                b["_" + raw.iv.names[c]] += tb;
+                a["_total"] += ta;
+                b["_total"] += tb;
+            }
+            base += ids.size();
+        }
+        py::dict da, db;
+        for (auto& kv : a) da[py::str(kv.first)] = py::cast(kv.second);
+        for (auto& kv : b) db[py::str(kv.first)] = py::cast(kv.second);
+        if (any) da["_outside"] = py::int_(raw.outside);
+        return py::make_tuple(da, db);
+    }
+
+    py::object count_reads(int mode, const py::dict& intervals, const py::dict& gene_intervals, py::object once) {
+        Raw raw;
+        run(mode, intervals, gene_intervals, !once.is_none() && py::cast<bool>(once), raw);
+        if (mode == MBFBAM_MODE_UNSTRANDED) return assemble_unstranded(raw);
+        if (mode == MBFBAM_MODE_STRANDED) return assemble_dual<uint64_t>(raw, raw.fwd, raw.rev);
+        return assemble_dual<double>(raw, raw.wfwd, raw.wrev);
+    }
+
+    // dense vectors (bytes of u64 / f64) for the one-process-per-GPU merge: the caller all-reduces them
+    // and calls assemble()
+    py::tuple count_reads_raw(int mode, const py::dict& intervals, const py::dict& gene_intervals) {
+        Raw raw;
+        run(mode, intervals, gene_intervals, false, raw);
+        size_t G = raw.fwd.size() - 1;
+        auto b = [](const void* p, size_t n) { return py::bytes((const char*)p, n); };
+        return py::make_tuple(b(raw.fwd.data(), G * 8), b(raw.rev.data(), G * 8), b(raw.wfwd.data(), G * 8),
+                              b(raw.wrev.data(), G * 8), b(raw.scanned.data(), raw.iv.names.size()), raw.outside);
+    }
+
+    py::object assemble(int mode, const py::dict& intervals, py::bytes fwd, py::bytes rev, py::bytes wfwd, py::bytes wrev,
+                        py::bytes scanned, uint64_t outside) {
+        Raw raw;
+        flatten(intervals, raw.iv);
+        size_t G = 0;
+        for (uint32_t n : raw.iv.n_genes) G += n;
+        auto load = [&](py::bytes& src, void* dst, size_t n) {
+            std::string s = src;
+            if (s.size() != n) value_error("assemble: wrong buffer size");
+            memcpy(dst, s.data(), n);
+        };
+        raw.fwd.assign(G + 1, 0); raw.rev.assign(G + 1, 0); raw.wfwd.assign(G + 1, 0); raw.wrev.assign(G + 1, 0);
+        raw.scanned.assign(raw.iv.names.size() + 1, 0);
+        load(fwd, raw.fwd.data(), G * 8); load(rev, raw.rev.data(), G * 8);
+        load(wfwd, raw.wfwd.data(), G * 8); load(wrev, raw.wrev.data(), G * 8);
+        load(scanned, raw.scanned.data(), raw.iv.names.size());
+        raw.outside = outside;
+        if (mode == MBFBAM_MODE_UNSTRANDED) return assemble_unstranded(raw);
+        if (mode == MBFBAM_MODE_STRANDED) return assemble_dual<uint64_t>(raw, raw.fwd, raw.rev);
+        return assemble_dual<double>(raw, raw.wfwd, raw.wrev);
+    }
+
+    py::dict count_introns() {
+        mbfbam_introns res{};
+        char err[512] = {0};
+        int rc;
+        {
+            py::gil_scoped_release rel;
+            rc = mbfbam_count_introns(r, device, shard_index, shard_count, &res, &last, err, sizeof err);
+        }
+        if (rc) {
+            mbfbam_free_introns(&res);
+            value_error(err);
+        }
+        py::dict out;
+        std::vector<py::dict> per(res.n_targets > 0 ? (size_t)res.n_targets : 0);
+        for (int32_t t = 0; t < res.n_targets; t++)
+            if (res.contig_seen[t]) out[py::str(mbfbam_target_name(r, t))] = per[(size_t)t];
+        for (uint64_t i = 0; i < res.n; i++) {
+            py::dict& d = per[(size_t)res.tid[i]];
+            py::tuple key = py::make_tuple(res.start[i], res.stop[i]);
+            if (d.contains(key)) d[key] = py::int_(py::cast<uint64_t>(d[key]) + res.count[i]);
+            else d[key] = py::int_(res.count[i]);
+            if (!res.contig_seen[res.tid[i]]) out[py::str(mbfbam_target_name(r, res.tid[i]))] = d;
+        }
+        mbfbam_free_introns(&res);
+        return out;
+    }
+
+    py::dict stats() const { return stats_dict(last); }
+};
+
+mbfbam_stats g_last_stats{};  // POD: a global py::object would be destroyed after the interpreter
+
+py::object module_count(int mode, const std::string& filename, py::object index_filename, const py::dict& intervals,
+                        const py::dict& gene_intervals, py::object once) {
+    PyReader rd(filename, index_filename);
+    py::object res = rd.count_reads(mode, intervals, gene_intervals, once);
+    g_last_stats = rd.last;
+    return res;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(mbf_bam, m) {
+    m.doc() = "B200-native drop-in for the read counters of mbf_bam.mbf_bam (reference src/lib.rs:286-299)";
+    m.attr("__version__") = mbfbam_version();
+
+    m.def("count_reads_unstranded",
+          [](const std::string& filename, py::object index_filename, const py::dict& intervals, const py::dict& gene_intervals,
+             py::object each_read_counts_once) {
+              return module_count(MBFBAM_MODE_UNSTRANDED, filename, index_filename, intervals, gene_intervals, each_read_counts_once);
+          },
+          py::arg("filename"), py::arg("index_filename"), py::arg("intervals"), py::arg("gene_intervals"),
+          py::arg("each_read_counts_once") = py::none(), "python wrapper for py_count_reads_unstranded (reference src/lib.rs:138)");
+    m.def("count_reads_stranded",
+          [](const std::string& filename, py::object index_filename, const py::dict& intervals, const py::dict& gene_intervals,
+             py::object each_read_counts_once) {
+              return module_count(MBFBAM_MODE_STRANDED, filename, index_filename, intervals, gene_intervals, each_read_counts_once);
+          },
+          py::arg("filename"), py::arg("index_filename"), py::arg("intervals"), py::arg("gene_intervals"),
+          py::arg("each_read_counts_once") = py::none(), "python wrapper for py_count_reads_stranded (reference src/lib.rs:161)");
+    m.def("count_reads_weighted",
+          [](const std::string& filename, py::object index_filename, const py::dict& intervals, const py::dict& gene_intervals,
+             py::object each_read_counts_once) {
+              return module_count(MBFBAM_MODE_WEIGHTED, filename, index_filename, intervals, gene_intervals, each_read_counts_once);
+          },
+          py::arg("filename"), py::arg("index_filename"), py::arg("intervals"), py::arg("gene_intervals"),
+          py::arg("each_read_counts_once") = py::none(), "1/NH weighted stranded counts (not in the reference; DESIGN.md)");
+    m.def("count_introns",
+          [](const std::string& filename, py::object index_filename) {
+              PyReader rd(filename, index_filename);
+              py::dict res = rd.count_introns();
+              g_last_stats = rd.last;
+              return res;
+          },
+          py::arg("filename"), py::arg("index_filename") = py::none(), "python wrapper for py_count_introns (reference src/lib.rs:216)");
+    m.def("last_stats", []() { return stats_dict(g_last_stats); }, "measurements of the most recent module-level call");
+    m.def("device_count", []() { return mbfbam_device_count(); });
+
+    m.def("inflate_buffer", [](py::bytes data, int device) {
+        std::string s = data;
+        uint64_t need = 0;
+        // sum of ISIZE by walking the BSIZE chain (host, headers only)
+        for (size_t off = 0; off + 28 <= s.size();) {
+            uint32_t bs = ((uint8_t)s[off + 16] | ((uint8_t)s[off + 17] << 8)) + 1u;
+            if (off + bs > s.size()) break;
+            uint32_t isz;
+            memcpy(&isz, s.data() + off + bs - 4, 4);
+            need += isz;
+            off += bs;
+        }
+        std::string out(need, '\0');
+        uint64_t got = 0;
+        char err[512] = {0};
+        mbfbam_stats st{};
+        int rc;
+        {
+            py::gil_scoped_release rel;
+            rc = mbfbam_inflate_buffer((const uint8_t*)s.data(), s.size(), (uint8_t*)&out[0], need, &got, device, &st, err, sizeof err);
+        }
+        if (rc) value_error(err);
+        out.resize(got);
+        g_last_stats = st;
+        return py::bytes(out);
+    }, py::arg("data"), py::arg("device") = 0, "inflate every BGZF member of `data` on the GPU (stage-level parity entry)");
+
+    m.def("cigar_expand", [](std::vector<uint32_t> cigar, int pos, bool introns, int device) {
+        std::vector<uint32_t> out(2 * (cigar.size() + 1));
+        int32_t n = 0;
+        char err[512] = {0};
+        if (mbfbam_cigar_expand(cigar.data(), (int32_t)cigar.size(), pos, introns ? 1 : 0, out.data(), (int32_t)cigar.size() + 1, &n,
+                                device, err, sizeof err))
+            value_error(err);
+        py::list l;
+        for (int i = 0; i < n; i++) l.append(py::make_tuple(out[2 * i], out[2 * i + 1]));
+        return l;
+    }, py::arg("cigar"), py::arg("pos"), py::arg("introns") = false, py::arg("device") = 0);
+
+    py::class_<PyReader>(m, "Reader", "open BAM + BAI once (reference src/bam_ext.rs:6 open_bam), run several jobs")
+        .def(py::init<const std::string&, py::object>(), py::arg("filename"), py::arg("index_filename") = py::none())
+        .def("set_device", &PyReader::set_device)
+        .def("set_shard", &PyReader::set_shard)
+        .def("preload", &PyReader::preload)
+        .def("drop_preload", &PyReader::drop_preload)
+        .def("targets", &PyReader::targets)
+        .def("chunks", &PyReader::chunks, py::arg("gene_intervals") = py::none())
+        .def("count_reads", &PyReader::count_reads, py::arg("mode"), py::arg("intervals"), py::arg("gene_intervals"),
+             py::arg("each_read_counts_once") = py::none())
+        .def("count_reads_raw", &PyReader::count_reads_raw)
+        .def("assemble", &PyReader::assemble)
+        .def("count_introns", &PyReader::count_introns)
+        .def("stats", &PyReader::stats);
+}

@@ -1,0 +1,344 @@
+// Host-side control plane: BAM header + BAI parsing, the ChunkedGenome table, flattened interval
+// tables and the BGZF byte ranges a job has to feed to the GPU.  No alignment record is ever parsed
+// here; that is the kernels' job.
+//
+// Reference behaviour replaced:
+//   open_bam                       src/bam_ext.rs:6-21 (IndexedReader::from_path[_and_index])
+//   header tid/target_len/names    src/count_reads/chunked_genome.rs:24,36-40,81-82
+//   ChunkedGenome                  src/count_reads/chunked_genome.rs:17-43,72-119
+//   build_tree                     src/count_reads/mod.rs:27-45 (flattened instead of an AVL tree)
+#pragma once
+#include <fcntl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/mbfbam.h"
+#include "inflate_host.hpp"
+
+namespace mbf {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+constexpr uint32_t CHUNK_SIZE = 1000000u;  // chunked_genome.rs:75
+
+struct RefIndex {
+    bool has_reads = false;
+    uint64_t voff_beg = 0, voff_end = 0;           // over all real bins
+    std::vector<uint64_t> ioffset;                 // 16 kb linear index
+    std::vector<std::pair<uint32_t, std::pair<uint64_t, uint64_t>>> bins;  // bin -> (min beg, max end)
+};
+
+struct Reader {
+    std::string path;
+    int fd = -1;
+    uint64_t file_size = 0;
+    std::vector<std::string> names;
+    std::vector<uint32_t> lens;
+    std::map<std::string, int32_t> name2tid;
+    uint64_t first_rec_voff = 0;  // virtual offset of the first alignment record
+    std::vector<RefIndex> idx;
+    // optional device-resident copy of the whole file (mbfbam_preload)
+    int preload_device = -1;
+    uint8_t* preload_ptr = nullptr;
+
+    ~Reader() {
+        if (fd >= 0) ::close(fd);
+    }
+
+    void pread_exact(void* dst, uint64_t off, size_t n) const {
+        size_t got = 0;
+        while (got < n) {
+            ssize_t r = ::pread(fd, (char*)dst + got, n - got, (off_t)(off + got));
+            if (r <= 0) throw Error(MBFBAM_ERR_IO, "Could not read bam: short read on " + path);
+            got += (size_t)r;
+        }
+    }
+
+    void open(const char* bam, const char* bai) {
+        path = bam;
+        fd = ::open(bam, O_RDONLY);
+        if (fd < 0) throw Error(MBFBAM_ERR_IO, std::string("Could not read bam: cannot open ") + bam);
+        struct stat st;
+        fstat(fd, &st);
+        file_size = (uint64_t)st.st_size;
+        parse_header();
+        std::string bp;
+        if (bai) {
+            bp = bai;
+        } else {
+            bp = path + ".bai";
+            if (access(bp.c_str(), R_OK) != 0) {
+                size_t n = path.size();
+                if (n > 4 && path.compare(n - 4, 4, ".bam") == 0) bp = path.substr(0, n - 4) + ".bai";
+            }
+        }
+        parse_bai(bp);
+    }
+
+    // BAM header: inflated on the host with the shared DEFLATE core (a few KB, once per open)
+    void parse_header() {
+        std::vector<uint8_t> u;
+        std::vector<std::pair<uint64_t, uint32_t>> blocks;  // (coffset, uncompressed start)
+        uint64_t coff = 0;
+        std::vector<uint8_t> cb(65536 + 64), ob(65536 + 512);
+        DecoderTables T;
+        auto need = [&](size_t n) {
+            while (u.size() < n) {
+                if (coff + 28 > file_size) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: truncated header in " + path);
+                uint8_t h[18];
+                pread_exact(h, coff, 18);
+                if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4))
+                    throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: not a BGZF file: " + path);
+                uint32_t xlen = h[10] | (h[11] << 8);
+                std::vector<uint8_t> extra(xlen);
+                pread_exact(extra.data(), coff + 12, xlen);
+                int32_t bsize = -1;
+                for (uint32_t p = 0; p + 4 <= xlen;) {
+                    uint32_t slen = extra[p + 2] | (extra[p + 3] << 8);
+                    if (extra[p] == 66 && extra[p + 1] == 67 && slen == 2 && p + 6 <= xlen) bsize = extra[p + 4] | (extra[p + 5] << 8);
+                    p += 4 + slen;
+                }
+                if (bsize < 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: BGZF block without BC field: " + path);
+                uint32_t csize = (uint32_t)bsize + 1, hdr = 12 + xlen;
+                if (csize < hdr + 8 || coff + csize > file_size) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: truncated BGZF block: " + path);
+                std::fill(cb.begin(), cb.end(), 0);
+                pread_exact(cb.data(), coff + hdr, csize - hdr);
+                uint32_t clen = csize - hdr - 8, isize;
+                memcpy(&isize, cb.data() + clen + 4, 4);
+                if (isize > 65536) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: bad ISIZE: " + path);
+                int rc = inflate_member_host(cb.data(), clen, ob.data(), isize, &T);
+                if (rc) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: corrupt BGZF block in header of " + path);
+                blocks.push_back({coff, (uint32_t)u.size()});
+                u.insert(u.end(), ob.begin(), ob.begin() + isize);
+                coff += csize;
+            }
+        };
+        auto rd32 = [&](size_t p) { need(p + 4); int32_t v; memcpy(&v, u.data() + p, 4); return v; };
+        need(4);
+        if (memcmp(u.data(), "BAM\1", 4) != 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: bad magic in " + path);
+        int32_t l_text = rd32(4);
+        if (l_text < 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: bad header");
+        size_t p = 8 + (size_t)l_text;
+        int32_t n_ref = rd32(p);
+        p += 4;
+        if (n_ref < 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: bad header");
+        for (int32_t i = 0; i < n_ref; i++) {
+            int32_t ln = rd32(p);
+            if (ln < 1) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: bad reference name");
+            need(p + 4 + (size_t)ln + 4);
+            names.emplace_back((const char*)u.data() + p + 4, (size_t)ln - 1);
+            p += 4 + (size_t)ln;
+            lens.push_back((uint32_t)rd32(p));
+            p += 4;
+            name2tid.emplace(names.back(), i);  // first wins, like htslib's name hash
+        }
+        // p = uncompressed offset of the first record -> virtual offset
+        size_t bi = blocks.size() - 1;
+        while (blocks[bi].second > p) bi--;
+        if (p == u.size()) {
+            first_rec_voff = coff << 16;  // header ends exactly at a block end
+        } else {
+            first_rec_voff = (blocks[bi].first << 16) | (uint64_t)(p - blocks[bi].second);
+        }
+    }
+
+    void parse_bai(const std::string& bp) {
+        FILE* f = fopen(bp.c_str(), "rb");
+        if (!f) throw Error(MBFBAM_ERR_IO, "Could not read bam: no index " + bp);
+        std::vector<uint8_t> d;
+        {
+            fseek(f, 0, SEEK_END);
+            long n = ftell(f);
+            fseek(f, 0, SEEK_SET);
+            d.resize((size_t)n);
+            if (n && fread(d.data(), 1, (size_t)n, f) != (size_t)n) { fclose(f); throw Error(MBFBAM_ERR_IO, "Could not read bam: short index read"); }
+            fclose(f);
+        }
+        size_t p = 0;
+        auto take = [&](void* dst, size_t n) {
+            if (p + n > d.size()) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: truncated index " + bp);
+            memcpy(dst, d.data() + p, n);
+            p += n;
+        };
+        char magic[4];
+        take(magic, 4);
+        if (memcmp(magic, "BAI\1", 4) != 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: not a BAI index: " + bp);
+        int32_t n_ref;
+        take(&n_ref, 4);
+        idx.assign(names.size(), RefIndex());
+        for (int32_t r = 0; r < n_ref; r++) {
+            RefIndex ri;
+            int32_t n_bin;
+            take(&n_bin, 4);
+            uint64_t mn = UINT64_MAX, mx = 0;
+            for (int32_t i = 0; i < n_bin; i++) {
+                uint32_t bin;
+                int32_t n_chunk;
+                take(&bin, 4);
+                take(&n_chunk, 4);
+                uint64_t bmn = UINT64_MAX, bmx = 0;
+                for (int32_t c = 0; c < n_chunk; c++) {
+                    uint64_t be[2];
+                    take(be, 16);
+                    if (bin == 37450) continue;
+                    bmn = std::min(bmn, be[0]);
+                    bmx = std::max(bmx, be[1]);
+                }
+                if (bin != 37450 && n_chunk > 0) {
+                    ri.bins.push_back({bin, {bmn, bmx}});
+                    mn = std::min(mn, bmn);
+                    mx = std::max(mx, bmx);
+                }
+            }
+            int32_t n_intv;
+            take(&n_intv, 4);
+            ri.ioffset.resize((size_t)std::max(0, n_intv));
+            if (n_intv > 0) take(ri.ioffset.data(), 8 * (size_t)n_intv);
+            ri.has_reads = mn != UINT64_MAX;
+            ri.voff_beg = ri.has_reads ? mn : 0;
+            ri.voff_end = mx;
+            std::sort(ri.bins.begin(), ri.bins.end());
+            if ((size_t)r < idx.size()) idx[(size_t)r] = std::move(ri);
+        }
+    }
+
+    // Lower bound of the virtual offset of any record on `tid` with pos >= start (linear index).
+    uint64_t voff_lower(int32_t tid, uint32_t start) const {
+        const RefIndex& ri = idx[(size_t)tid];
+        uint64_t v = ri.voff_beg;
+        size_t w = start >> 14;
+        if (w < ri.ioffset.size() && ri.ioffset[w] > v) v = ri.ioffset[w];
+        return v;
+    }
+    // Upper bound of the virtual END offset of any record on `tid` with pos < stop: max chunk end over
+    // all bins that overlap [0, stop) -- i.e. the standard reg2bins walk.
+    uint64_t voff_upper(int32_t tid, uint32_t stop) const {
+        const RefIndex& ri = idx[(size_t)tid];
+        if (stop >= lens[(size_t)tid] || stop == 0) return ri.voff_end;
+        uint32_t end = stop - 1;
+        uint64_t mx = 0;
+        static const uint32_t lvl_off[6] = {0, 1, 9, 73, 585, 4681};
+        static const int lvl_shift[6] = {29, 26, 23, 20, 17, 14};
+        for (const auto& b : ri.bins) {
+            int l = 5;
+            while (l > 0 && b.first < lvl_off[l]) l--;
+            uint32_t first_pos_bin = b.first - lvl_off[l];
+            if (first_pos_bin <= (end >> lvl_shift[l])) mx = std::max(mx, b.second.second);
+        }
+        return mx ? mx : ri.voff_end;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct Chunk {
+    int32_t tid;
+    uint32_t start, stop;
+};
+
+struct SortedIntervals {
+    std::vector<uint32_t> start, end, pmax, gene;  // gene = local gene_no
+    std::vector<int8_t> strand;
+};
+
+inline SortedIntervals sort_intervals(const mbfbam_intervals* iv, int c) {
+    uint64_t a = iv->iv_offsets[c], b = iv->iv_offsets[c + 1];
+    std::vector<uint32_t> order((size_t)(b - a));
+    for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        if (iv->iv_start[a + x] != iv->iv_start[a + y]) return iv->iv_start[a + x] < iv->iv_start[a + y];
+        if (iv->iv_end[a + x] != iv->iv_end[a + y]) return iv->iv_end[a + x] < iv->iv_end[a + y];
+        return x < y;
+    });
+    SortedIntervals s;
+    uint32_t m = 0;
+    for (uint32_t o : order) {
+        uint32_t st = iv->iv_start[a + o], en = iv->iv_end[a + o];
+        if (st > en) throw Error(MBFBAM_ERR_ARG, "interval start > end");  // bio panics here
+        s.start.push_back(st);
+        s.end.push_back(en);
+        s.gene.push_back(iv->iv_gene[a + o]);
+        s.strand.push_back(iv->iv_strand[a + o]);
+        m = std::max(m, en);
+        s.pmax.push_back(m);
+    }
+    return s;
+}
+
+// chunked_genome.rs:93-109: push the chunk's right edge past any gene interval covering it.  When
+// several cover it the reference takes whatever bio's tree yields first; every choice reaches the
+// same fixed point except in 1-bp-abutting corner layouts.  We take the largest end.
+inline uint32_t extend_stop(const SortedIntervals& g, uint32_t stop) {
+    for (;;) {
+        size_t hi = (size_t)(std::upper_bound(g.start.begin(), g.start.end(), stop) - g.start.begin());
+        uint32_t best = 0;
+        bool found = false;
+        for (size_t i = hi; i-- > 0;) {
+            if (g.pmax[i] <= stop) break;
+            if (g.end[i] > stop) {
+                best = found ? std::max(best, g.end[i]) : g.end[i];
+                found = true;
+            }
+        }
+        if (!found) return stop;
+        stop = best + 1;
+    }
+}
+
+// gene_intervals == nullptr: new_without_tree (all header contigs, fixed 1 Mb chunks).
+inline std::vector<Chunk> make_chunks(const Reader& r, const mbfbam_intervals* genes) {
+    std::vector<Chunk> out;
+    int n = genes ? genes->n_contigs : (int)r.names.size();
+    for (int c = 0; c < n; c++) {
+        int32_t tid = c;
+        SortedIntervals g;
+        if (genes) {
+            auto it = r.name2tid.find(genes->contig_names[c]);
+            if (it == r.name2tid.end()) continue;  // chunked_genome.rs:21-25
+            tid = it->second;
+            g = sort_intervals(genes, c);
+        }
+        uint32_t len = r.lens[(size_t)tid], start = 0;
+        do {
+            uint32_t stop = start + CHUNK_SIZE;
+            if (genes) stop = extend_stop(g, stop);
+            out.push_back({tid, start, stop});
+            start = stop;
+        } while (start < len);
+    }
+    return out;
+}
+
+// A contiguous run of BGZF blocks to scan: file bytes [cbeg, cend), first record at first_uoff
+// inside the block at cbeg.
+struct ByteRange {
+    uint64_t cbeg, cend;
+    uint32_t first_uoff;
+};
+
+inline void add_range(std::vector<ByteRange>& v, uint64_t voff_beg, uint64_t voff_end, uint64_t file_size) {
+    uint64_t cbeg = voff_beg >> 16, cend = voff_end >> 16;
+    if (voff_end & 0xffff) cend += 1;  // the block holding the end offset is needed as well; its true
+                                       // end is found by the scanner (scan_len reaches one byte into it)
+    if (cend > file_size) cend = file_size;
+    if (cbeg >= cend) return;
+    if (!v.empty() && cbeg <= v.back().cend) {
+        // overlapping / adjacent in the file: extend (records in the shared block are walked once)
+        v.back().cend = std::max(v.back().cend, cend);
+        return;
+    }
+    v.push_back({cbeg, cend, (uint32_t)(voff_beg & 0xffff)});
+}
+
+}  // namespace mbf

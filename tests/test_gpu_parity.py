@@ -1,0 +1,221 @@
+"""GPU suite: every stage and every entry point against the oracle, through the C ABI (the host
+extension only converts arguments).  Integer results bit-exact; weighted within 1e-9 relative."""
+import json
+import os
+import random
+import zlib
+
+import pytest
+
+from conftest import ROOT, make_case
+from mbf_bam_b200.synth import bamio
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "cigar_golden.json")))
+
+
+@pytest.fixture()
+def mb(built, has_gpu):
+    assert has_gpu, "GPU tests need a CUDA device (no CPU fallback exists)"
+    return built
+
+
+def assert_weighted_close(a, b):
+    for x, y in zip(a, b):
+        assert set(x) == set(y)
+        for k in x:
+            assert abs(x[k] - y[k]) <= 1e-9 * max(1.0, abs(y[k])), (k, x[k], y[k])
+
+
+def check_all(mb, path, iv, giv):
+    assert mb.count_reads_unstranded(path, None, iv, giv) == c_oracle.count_reads_unstranded(path, None, iv, giv, nthreads=4)
+    st = mb.last_stats()
+    assert mb.count_reads_stranded(path, None, iv, giv) == c_oracle.count_reads_stranded(path, None, iv, giv, nthreads=4)
+    assert_weighted_close(mb.count_reads_weighted(path, None, iv, giv), c_oracle.count_reads_weighted(path, None, iv, giv, nthreads=4))
+    assert mb.count_introns(path) == c_oracle.count_introns(path, nthreads=4)
+    return st
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("kw", [dict(), dict(level=1), dict(level=9, split_records=True), dict(sync_every=500),
+                                dict(strategy=zlib.Z_FIXED), dict(level=0), dict(strategy=zlib.Z_HUFFMAN_ONLY),
+                                dict(strategy=zlib.Z_RLE, payload_limit=3000)],
+                         ids=["default", "l1", "l9split", "syncflush", "fixed", "stored", "huffonly", "rle_small"])
+def test_inflate_matches_zlib(mb, tmp_path, kw):
+    path, *_ = make_case(tmp_path, 12, n_reads=6000, **kw)
+    data = open(path, "rb").read()
+    want = b"".join(p for _, _, p in bamio.iter_bgzf_blocks(data))
+    got = mb.inflate_buffer(data)
+    assert len(got) == len(want)
+    assert got == want
+    assert mb.last_stats()["n_bgzf_blocks"] == len(list(bamio.iter_bgzf_blocks(data)))
+
+
+def test_inflate_random_and_text(mb, tmp_path):
+    rng = random.Random(5)
+    p = tmp_path / "r.bgzf"
+    payload = bytes(rng.getrandbits(8) for _ in range(300_000)) + b"abc" * 50_000 + b"\0" * 200_000 + \
+        b"".join(b"%d," % rng.randrange(10 ** 6) for _ in range(100_000))
+    with open(p, "wb") as fh:
+        w = bamio.BgzfWriter(fh)
+        w.write(payload, atomic=False)
+        w.close()
+    assert mb.inflate_buffer(p.read_bytes()) == payload
+
+
+def test_inflate_many_windows(mb, tmp_path, monkeypatch):
+    monkeypatch.setenv("MBF_BAM_WINDOW_MB", "1")
+    rng = random.Random(6)
+    payload = b"".join(b"%x\t" % rng.getrandbits(40) for _ in range(700_000))
+    p = tmp_path / "w.bgzf"
+    with open(p, "wb") as fh:
+        w = bamio.BgzfWriter(fh, level=1)
+        w.write(payload, atomic=False)
+        w.close()
+    data = p.read_bytes()
+    assert len(data) > 3 * (1 << 20)
+    assert mb.inflate_buffer(data) == payload
+    assert mb.last_stats()["n_windows"] >= 3
+
+
+def test_inflate_rejects_corruption(mb, tmp_path):
+    path, *_ = make_case(tmp_path, 13, n_reads=3000)
+    data = bytearray(open(path, "rb").read())
+    blocks = list(bamio.iter_bgzf_blocks(bytes(data)))
+    off, csize, _ = blocks[1]
+    for k in range(40, 60):
+        data[off + k] ^= 0x5A
+    with pytest.raises(ValueError, match="Could not read bam"):
+        mb.inflate_buffer(bytes(data))
+
+
+# ------------------------------------------------------------------------------------------------ K3
+@pytest.mark.parametrize("g", GOLDEN, ids=lambda g: "%d_%s" % (g["index"], g["cigar"]))
+def test_cigar_golden_on_device(mb, g):
+    """reference src/bam_ext.rs:50-604 golden records through the device CIGAR expander."""
+    words = [(l << 4) | op for op, l in bamio.parse_cigar(g["cigar"])]
+    assert [tuple(x) for x in mb.cigar_expand(words, g["pos"], False)] == [tuple(b) for b in g["blocks"]]
+    got = [tuple(x) for x in mb.cigar_expand(words, g["pos"], True)]
+    assert len(got) == g["n_introns"]
+    assert got[:len(g["introns"])] == [tuple(b) for b in g["introns"]]
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+@pytest.mark.parametrize("seed,kw", [
+    (1, {}), (2, dict(paired=True)), (3, dict(split_records=True, level=9)),
+    (4, dict(sync_every=700)), (5, dict(exon_mode=False)), (6, dict(n_contigs=4, contig_len=900_000)),
+    (7, dict(n_reads=60_000)), (8, dict(n_reads=20_000, split_records=True, payload_limit=2000)),
+])
+def test_counts_match_oracle(mb, tmp_path, seed, kw):
+    path, contigs, recs, iv, giv = make_case(tmp_path, seed, **kw)
+    st = check_all(mb, path, iv, giv)
+    assert st["n_kernel_launches"] > 0
+
+
+def test_counts_many_windows_and_key_overflow(mb, tmp_path, monkeypatch):
+    """Small windows (carry between windows, multi-mapper sets spanning windows) and a multi-mapper key
+    buffer that overflows (emit-only re-run)."""
+    monkeypatch.setenv("MBF_BAM_WINDOW_MB", "1")
+    monkeypatch.setenv("MBF_BAM_MM_CAP", "64")
+    path, contigs, recs, iv, giv = make_case(tmp_path, 9, n_reads=150_000, level=1)
+    assert os.path.getsize(path) > 3 * (1 << 20)
+    st = check_all(mb, path, iv, giv)
+    assert st["n_windows"] >= 3
+
+
+def test_split_records_across_windows(mb, tmp_path, monkeypatch):
+    monkeypatch.setenv("MBF_BAM_WINDOW_MB", "1")
+    path, contigs, recs, iv, giv = make_case(tmp_path, 10, n_reads=120_000, level=1, split_records=True)
+    check_all(mb, path, iv, giv)
+
+
+def test_read_hitting_many_genes(mb, tmp_path):
+    """More distinct genes under one read than the per-thread register set holds (SEEN_K)."""
+    R = bamio.Rec
+    refs = [("c1", 2_000_000), ("c2", 1_500_000)]
+    genes = [("g%02d" % i, 1 if i % 2 else -1, [1000 + i, 1200 + i], [1100 + i, 1300 + i]) for i in range(25)]
+    iv = {"c1": genes, "c2": [("h", 1, [10], [20])]}
+    giv = {"c1": [(g[0], g[1], [g[2][0]], [g[3][-1]]) for g in genes], "c2": [("h", 1, [10], [20])]}
+    nh3 = bamio.aux_int(b"NH", 3, "s")
+    recs = [R(0, 1005 + i, b"x%d" % (i % 7), 16 * (i % 2), 255, [(0, 60), (3, 150), (0, 40)], 100,
+              nh3 if i % 3 == 0 else b"") for i in range(400)]
+    recs += [R(1, 12, b"y", 0, 255, [(0, 5)], 5)]
+    path = str(tmp_path / "many.bam")
+    bamio.write_bam(path, refs, recs)
+    check_all(mb, path, iv, giv)
+
+
+def test_contig_subsets_and_empty(mb, tmp_path):
+    path, contigs, recs, iv, giv = make_case(tmp_path, 14, n_contigs=3)
+    sub_g = {k: giv[k] for k in list(giv)[1:]}
+    sub_g["not_in_header"] = giv[list(giv)[0]]
+    sub_i = dict(iv)
+    sub_i["not_in_header"] = iv[list(iv)[0]]
+    assert mb.count_reads_unstranded(path, None, sub_i, sub_g) == c_oracle.count_reads_unstranded(path, None, sub_i, sub_g)
+    assert mb.count_reads_stranded(path, None, sub_i, sub_g) == c_oracle.count_reads_stranded(path, None, sub_i, sub_g)
+    assert mb.count_reads_unstranded(path, None, {}, {}) == {}
+    assert mb.count_reads_stranded(path, None, {}, {}) == ({}, {})
+    with pytest.raises(ValueError, match="gene_intervals but not in intervals"):
+        mb.count_reads_unstranded(path, None, {}, sub_g)
+    # a BAM without any record
+    p2 = str(tmp_path / "empty.bam")
+    bamio.write_bam(p2, contigs, [])
+    assert mb.count_reads_unstranded(p2, None, iv, giv) == c_oracle.count_reads_unstranded(p2, None, iv, giv)
+    assert mb.count_introns(p2) == c_oracle.count_introns(p2)
+
+
+def test_nh_type_error(mb, tmp_path):
+    R = bamio.Rec
+    refs = [("c1", 100_000)]
+    iv = {"c1": [("g", 1, [10], [90])]}
+    path = str(tmp_path / "nhz.bam")
+    bamio.write_bam(path, refs, [R(0, 20, b"a", 0, 255, [(0, 10)], 10, bamio.aux_str(b"NH", b"2"))])
+    with pytest.raises(ValueError, match="NH tag is not an integer"):
+        mb.count_reads_unstranded(path, None, iv, iv)
+
+
+def test_shards_sum_to_whole(mb, tmp_path):
+    """Chunk-range sharding: per-shard dense results add up to the single-shard result."""
+    import numpy as np
+
+    path, contigs, recs, iv, giv = make_case(tmp_path, 15, n_reads=40_000, n_contigs=3)
+    for mode in (0, 1, 2):
+        rd = mb.Reader(path)
+        whole = rd.count_reads_raw(mode, iv, giv)
+        for n in (2, 3, 5):
+            acc = None
+            for i in range(n):
+                rd.set_shard(i, n)
+                part = rd.count_reads_raw(mode, iv, giv)
+                arrs = [np.frombuffer(part[0], dtype=np.uint64), np.frombuffer(part[1], dtype=np.uint64),
+                        np.frombuffer(part[2], dtype=np.float64), np.frombuffer(part[3], dtype=np.float64),
+                        np.frombuffer(part[4], dtype=np.uint8), np.uint64(part[5])]
+                acc = arrs if acc is None else [a + b if k != 4 else np.maximum(a, b) for k, (a, b) in enumerate(zip(acc, arrs))]
+            rd.set_shard(0, 1)
+            assert acc[0].tobytes() == whole[0] and acc[1].tobytes() == whole[1]
+            assert np.allclose(acc[2], np.frombuffer(whole[2], dtype=np.float64), rtol=1e-12, atol=0)
+            assert np.allclose(acc[3], np.frombuffer(whole[3], dtype=np.float64), rtol=1e-12, atol=0)
+            assert acc[4].tobytes() == whole[4] and int(acc[5]) == whole[5]
+    # introns: shard dicts merge to the whole
+    rd = mb.Reader(path)
+    whole = rd.count_introns()
+    merged = {}
+    for i in range(3):
+        rd.set_shard(i, 3)
+        for c, d in rd.count_introns().items():
+            tgt = merged.setdefault(c, {})
+            for k, v in d.items():
+                tgt[k] = tgt.get(k, 0) + v
+    assert merged == whole == c_oracle.count_introns(path)
+
+
+def test_preloaded_file_gives_same_result(mb, tmp_path):
+    path, contigs, recs, iv, giv = make_case(tmp_path, 16, n_reads=30_000)
+    rd = mb.Reader(path)
+    a = rd.count_reads(1, iv, giv)
+    rd.preload()
+    b = rd.count_reads(1, iv, giv)
+    assert rd.stats()["h2d_bytes"] == 0
+    rd.drop_preload()
+    assert a == b == c_oracle.count_reads_stranded(path, None, iv, giv)

@@ -1,0 +1,90 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every declared symbol, the host-side control
+plane (header/BAI parsing, ChunkedGenome table, argument handling, error convention) behaves like the
+reference's -- no compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, make_case
+from oracle import c_oracle
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "mbfbam.h")).read()
+    names = set(re.findall(r"\b(mbfbam_[a-z_0-9]+)\s*\(", hdr))
+    assert len(names) >= 15
+    lib = ctypes.CDLL(os.path.join(ROOT, "mbf_bam_b200", "libmbfbam_cuda.so"))
+    for n in sorted(names):
+        assert hasattr(lib, n), "missing export " + n
+    lib.mbfbam_version.restype = ctypes.c_char_p
+    assert lib.mbfbam_version().decode() == built.__version__
+
+
+def test_module_surface_matches_reference(built):
+    """reference src/lib.rs:286-299 (+ count_reads_weighted named by the north star)."""
+    import inspect
+
+    import mbf_bam
+
+    for fn in ("count_reads_unstranded", "count_reads_stranded", "count_reads_weighted", "count_introns"):
+        assert callable(getattr(mbf_bam, fn))
+    assert isinstance(mbf_bam.__version__, str)
+    doc = built.count_reads_unstranded.__doc__
+    for arg in ("filename", "index_filename", "intervals", "gene_intervals", "each_read_counts_once"):
+        assert arg in doc
+    assert "index_filename" in built.count_introns.__doc__
+    assert inspect.isbuiltin(built.count_reads_stranded) or callable(built.count_reads_stranded)
+
+
+def test_open_errors_are_value_errors(built, tmp_path):
+    """BamError -> ValueError (reference src/lib.rs:26-32), message of src/bam_ext.rs:16-18."""
+    with pytest.raises(ValueError, match="Could not read bam"):
+        built.count_introns(str(tmp_path / "missing.bam"))
+    path, contigs, recs, iv, giv = make_case(tmp_path, 21, n_reads=200)
+    os.rename(path + ".bai", path + ".bai.moved")
+    with pytest.raises(ValueError, match="Could not read bam"):
+        built.count_reads_unstranded(path, None, iv, giv)
+    # explicit index path (IndexedReader::from_path_and_index)
+    rd = built.Reader(path, path + ".bai.moved")
+    assert [n for n, _ in rd.targets()] == [c for c, _ in contigs]
+    junk = tmp_path / "junk.bam"
+    junk.write_bytes(b"this is not a bam file at all" * 10)
+    with pytest.raises(ValueError, match="Could not read bam"):
+        built.Reader(str(junk), path + ".bai.moved")
+
+
+def test_argument_errors(built, tmp_path):
+    path, contigs, recs, iv, giv = make_case(tmp_path, 22, n_reads=200)
+    with pytest.raises(TypeError):
+        built.count_reads_unstranded(path, None, [1, 2], giv)          # &PyDict argument
+    with pytest.raises(ValueError, match="Python error"):
+        built.count_reads_unstranded(path, None, {"chrA": "nope"}, giv)
+    with pytest.raises(ValueError, match="Python error"):
+        built.count_reads_unstranded(path, None, {"chrA": [("g", 1000, [1], [2])]}, giv)  # strand > i8
+
+
+def test_chunk_table_matches_oracle(built, tmp_path):
+    """ChunkedGenome (reference src/count_reads/chunked_genome.rs:72-119): host planner vs oracle."""
+    for seed in (31, 32, 33):
+        path, contigs, recs, iv, giv = make_case(tmp_path, seed, n_reads=300, n_contigs=3, genes_per_contig=60)
+        rd = built.Reader(path)
+        assert [tuple(c) for c in rd.chunks(giv)] == c_oracle.chunks(path, None, giv)
+        assert [tuple(c) for c in rd.chunks(None)] == c_oracle.chunks(path, None, None)
+        sub = {k: giv[k] for k in list(giv)[:1]}
+        sub["not_in_header"] = giv[list(giv)[0]]
+        assert [tuple(c) for c in rd.chunks(sub)] == c_oracle.chunks(path, None, sub)
+
+
+def test_no_cpu_fallback(built, has_gpu, tmp_path):
+    """Without a CUDA device every compute entry point must fail loudly."""
+    if has_gpu:
+        pytest.skip("GPU present")
+    path, contigs, recs, iv, giv = make_case(tmp_path, 23, n_reads=200)
+    for call in (lambda: built.count_reads_stranded(path, None, iv, giv),
+                 lambda: built.count_introns(path),
+                 lambda: built.inflate_buffer(open(path, "rb").read()),
+                 lambda: built.cigar_expand([16], 5)):
+        with pytest.raises(ValueError, match="no CUDA device"):
+            call()
