@@ -44,7 +44,7 @@ _EDGE_CIGARS = ["10S40M", "20M5I25M", "20M5D30M", "25=25X", "5H45M5H", "10M0N40M
 
 def reads(rng: random.Random, contigs: List[Tuple[str, int]], n: int, read_len: int = 50,
           nh_frac: float = 0.2, spliced_frac: float = 0.2, edge_frac: float = 0.1,
-          paired: bool = False, hot: List[Tuple[int, int, int]] = ()) -> List[Rec]:
+          paired: bool = False, hot: List[Tuple[int, int, int]] = (), random_seq: bool = False) -> List[Rec]:
     """n coordinate-sorted records.  `hot`: (tid, lo, hi) windows that get half of the reads."""
     recs: List[Rec] = []
     qn = 0
@@ -96,6 +96,10 @@ def reads(rng: random.Random, contigs: List[Tuple[str, int]], n: int, read_len: 
             mate_pos = pos + rng.randrange(100, 400)
             recs.append(Rec(tid, mate_pos, name, flag ^ 16 | 0x80 | 1, 255, [(0, read_len)], read_len, aux))
             i += 1
+    if random_seq:  # incompressible SEQ/QUAL like real data (keeps BGZF members large)
+        for r in recs:
+            r.seq = rng.randbytes((r.l_seq + 1) // 2)
+            r.qual = bytes(rng.choice((37, 37, 37, 25, 11, 2)) for _ in range(r.l_seq))
     # a few structural edge cases
     if n >= 20:
         t0 = 0
@@ -109,7 +113,7 @@ def reads(rng: random.Random, contigs: List[Tuple[str, int]], n: int, read_len: 
 
 
 def simple_case(seed: int, n_reads: int = 2000, n_contigs: int = 2, contig_len: int = 2_500_000,
-                genes_per_contig: int = 30, exon_mode: bool = True, paired: bool = False):
+                genes_per_contig: int = 30, exon_mode: bool = True, paired: bool = False, random_seq: bool = False):
     rng = random.Random(seed)
     contigs = [("chr%s" % "ABCDEFGH"[i], contig_len + 137 * i) for i in range(n_contigs)]
     intervals, gene_intervals = gene_model(rng, contigs, genes_per_contig, exon_mode)
@@ -117,5 +121,5 @@ def simple_case(seed: int, n_reads: int = 2000, n_contigs: int = 2, contig_len: 
     for ci, (name, _) in enumerate(contigs):
         for g in gene_intervals[name][:10]:
             hot.append((ci, g[2][0], g[3][0]))
-    recs = reads(rng, contigs, n_reads, paired=paired, hot=hot)
+    recs = reads(rng, contigs, n_reads, paired=paired, hot=hot, random_seq=random_seq)
     return contigs, recs, intervals, gene_intervals

@@ -118,7 +118,7 @@ def test_counts_many_windows_and_key_overflow(mb, tmp_path, monkeypatch):
     buffer that overflows (emit-only re-run)."""
     monkeypatch.setenv("MBF_BAM_WINDOW_MB", "1")
     monkeypatch.setenv("MBF_BAM_MM_CAP", "64")
-    path, contigs, recs, iv, giv = make_case(tmp_path, 9, n_reads=150_000, level=1)
+    path, contigs, recs, iv, giv = make_case(tmp_path, 9, n_reads=100_000, level=1, random_seq=True)
     assert os.path.getsize(path) > 3 * (1 << 20)
     st = check_all(mb, path, iv, giv)
     assert st["n_windows"] >= 3
@@ -126,7 +126,7 @@ def test_counts_many_windows_and_key_overflow(mb, tmp_path, monkeypatch):
 
 def test_split_records_across_windows(mb, tmp_path, monkeypatch):
     monkeypatch.setenv("MBF_BAM_WINDOW_MB", "1")
-    path, contigs, recs, iv, giv = make_case(tmp_path, 10, n_reads=120_000, level=1, split_records=True)
+    path, contigs, recs, iv, giv = make_case(tmp_path, 10, n_reads=80_000, level=1, split_records=True, random_seq=True)
     check_all(mb, path, iv, giv)
 
 
