@@ -1,0 +1,17 @@
+"""One count_reads_stranded job over a cfg2-shaped BAM (size from MBF_BENCH_READS): the command ncu wraps."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import mbf_bam_b200 as mb  # noqa: E402
+
+reads = int(os.environ.get("MBF_BENCH_READS", "4000000"))
+path, iv, giv, info, _ = bench.ensure_bam(os.environ.get("MBF_BENCH_DIR", "/tmp/mbf_bench"), reads, 0, 1, lambda: None)
+rd = mb.Reader(path)
+rd.preload()
+f, r = rd.count_reads(1, iv, giv)
+st = rd.stats()
+print("records", st["n_records"], "launches", st["n_kernel_launches"], "fwd", f["_total"], "rev", r["_total"],
+      {k: round(v, 2) for k, v in st.items() if k.startswith("ms_")})
