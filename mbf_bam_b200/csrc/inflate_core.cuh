@@ -6,7 +6,7 @@
 // `bam.read(&mut read)` (reference src/count_reads/counters.rs:41,132; introns.rs:33).
 //
 // Layout of one decoder's tables (shared memory on the device, ~3.4 KB):
-//   ll_lut[1<<LL_ROOT]  u16  (symbol<<4 | code length); 0 = invalid, 0x10 = "longer than root"
+//   ll_lut[1<<LL_ROOT]  u16  (symbol<<4 | code length); 0xFFFF = invalid, 0x8000 = "longer than root"
 //   d_lut [1<<D_ROOT]   u16
 //   ll_sym[288], d_sym[32]   canonical (length, symbol) ordered symbol lists for long codes
 //   HuffDec              first code / offset / count per code length
@@ -26,7 +26,9 @@ namespace mbf {
 constexpr int LL_ROOT = 10;
 constexpr int D_ROOT = 8;
 constexpr int CL_ROOT = 7;
-constexpr uint16_t LUT_SLOW = 0x10;
+constexpr uint16_t LUT_SLOW = 0x8000;     // code longer than the LUT root: canonical search
+constexpr uint16_t LUT_INVALID = 0xFFFF;  // no code has this prefix
+// valid entries are (symbol << 4 | code length) <= 0x11FF, so `entry < 0x1000` <=> literal
 
 enum InflateError : int {
     INF_OK = 0,
@@ -93,20 +95,21 @@ MBF_HD uint32_t bitrev32(uint32_t v) {
 #endif
 }
 
-// LSB-first bit reader over 32-bit aligned words (global memory on the device).
+// LSB-first bit reader over 32-bit aligned words (global memory on the device).  One word is
+// always prefetched (`nextw`) so that the load latency is off the decode chain.
 struct BitReader {
     const uint32_t* words;
-    uint32_t wpos;    // next word to load
+    uint32_t wpos;    // next word to prefetch
     uint32_t wlimit;  // words [0, wlimit) may be loaded
     uint64_t buf;
     uint32_t cnt;
-    uint32_t overrun;
+    uint32_t nextw;
 
     MBF_HD uint32_t load(uint32_t i) const {
 #ifdef __CUDA_ARCH__
-        return __ldg(words + i);
+        return i < wlimit ? __ldg(words + i) : 0u;
 #else
-        return words[i];
+        return i < wlimit ? words[i] : 0u;
 #endif
     }
     // byte pointer `p` (any alignment), `nbytes` of payload
@@ -115,25 +118,18 @@ struct BitReader {
         uint32_t mis = (uint32_t)(a & 3);
         words = (const uint32_t*)(a - mis);
         wlimit = (mis + nbytes + 3) >> 2;
-        wpos = 0;
-        buf = 0;
-        cnt = 0;
-        overrun = 0;
-        if (wlimit) {
-            buf = (uint64_t)load(0) >> (8 * mis);
-            cnt = 32 - 8 * mis;
-            wpos = 1;
-        }
+        buf = (uint64_t)load(0) >> (8 * mis);
+        cnt = 32 - 8 * mis;
+        nextw = load(1);
+        wpos = 2;
     }
     // guarantees cnt >= 32 afterwards
     MBF_HD void refill() {
         if (cnt < 32) {
-            uint32_t w = 0;
-            if (wpos < wlimit) w = load(wpos);
-            else overrun++;
-            wpos++;
-            buf |= (uint64_t)w << cnt;
+            buf |= (uint64_t)nextw << cnt;
             cnt += 32;
+            nextw = load(wpos);
+            wpos++;
         }
     }
     MBF_HD uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1); }
@@ -141,7 +137,7 @@ struct BitReader {
     MBF_HD uint32_t take(int n) { uint32_t v = peek(n); consume(n); return v; }
     // bytes of payload consumed so far (rounded up to whole bytes), given the initial misalignment
     MBF_HD uint32_t bytes_consumed(uint32_t mis) const {
-        uint64_t bits = (uint64_t)wpos * 32 - cnt - 8ull * mis;
+        uint64_t bits = (uint64_t)(wpos - 1) * 32 - cnt - 8ull * mis;
         return (uint32_t)((bits + 7) >> 3);
     }
 };
@@ -154,7 +150,7 @@ MBF_HD int build_table(const uint8_t* lens, int n, int root, uint16_t* lut, uint
     for (int i = 0; i < n; i++) hd->cnt[lens[i]]++;
     int max = 15;
     while (max > 0 && hd->cnt[max] == 0) max--;
-    for (int i = 0; i < (1 << root); i++) lut[i] = 0;
+    for (int i = 0; i < (1 << root); i++) lut[i] = LUT_INVALID;
     if (max == 0) return 0;  // no codes at all: every lookup is invalid (zlib allows this)
     int left = 1;
     for (int len = 1; len <= 15; len++) {
@@ -238,8 +234,8 @@ MBF_HD int build_dynamic(DecoderTables* T, BitReader& br) {
     while (i < n) {
         br.refill();
         uint32_t e = T->d_lut[br.peek(CL_ROOT)];
+        if (e >= LUT_SLOW) return INF_BAD_HEADER;  // code-length codes are <= 7 bits = CL_ROOT
         uint32_t l = e & 15;
-        if (!l) return INF_BAD_HEADER;
         br.consume(l);
         uint32_t s = e >> 4;
         if (s < 16) {
@@ -280,7 +276,7 @@ MBF_HD int decode_symbols(const DecoderTables* T, BitReader& br, Out& out) {
         if (out.want_flush()) return DEC_NEED_FLUSH;
         br.refill();
         uint32_t e = T->ll_lut[br.peek(LL_ROOT)];
-        if ((e & 15) == 0) {
+        if (e >= LUT_SLOW) {
             if (e != LUT_SLOW) return -INF_BAD_SYMBOL;
             e = slow_decode(&T->ll_hd, T->ll_sym, br.peek(15), LL_ROOT);
             if (!e) return -INF_BAD_SYMBOL;
@@ -297,7 +293,7 @@ MBF_HD int decode_symbols(const DecoderTables* T, BitReader& br, Out& out) {
         uint32_t len = MBF_TBL(LEN_BASE, sym) + br.take(MBF_TBL(LEN_EXTRA, sym));
         br.refill();
         e = T->d_lut[br.peek(D_ROOT)];
-        if ((e & 15) == 0) {
+        if (e >= LUT_SLOW) {
             if (e != LUT_SLOW) return -INF_BAD_DISTANCE;
             e = slow_decode(&T->d_hd, T->d_sym, br.peek(15), D_ROOT);
             if (!e) return -INF_BAD_DISTANCE;

@@ -255,33 +255,126 @@ __global__ void __launch_bounds__(256) k_blocks_finalize(ScanArgs a, BlockArrays
 // against LUTs in shared memory; the warp cooperates on flushing the shared-memory output ring to
 // HBM with 16-byte stores.  Back-references within RING bytes are served from shared memory, older
 // ones from L2/HBM (already flushed by this warp).
+// explicit 32-bit shared-memory addressing for the hot loop (generic-pointer accesses make ptxas
+// re-derive the shared window base, SR_CgaCtaId, on the decode chain)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// shared-window address of a __shared__ object; volatile so that ptxas keeps the value in a register
+// instead of re-deriving it (S2R SR_CgaCtaId + LEA) inside the decode loop
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    uint32_t a;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+    return a;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 struct RingOut {
-    uint8_t* ring;
+    uint32_t s_ring;  // shared address of the ring
     const uint8_t* U;
     uint32_t opos, ostart, soft_lim;
-    MBF_HD bool want_flush() const { return opos > soft_lim; }
-    MBF_HD void put(uint8_t b) {
-        ring[opos & RING_MASK] = b;
+    __device__ __forceinline__ bool want_flush() const { return opos > soft_lim; }
+    __device__ __forceinline__ void put(uint32_t b) {
+        sts_u8(s_ring + (opos & RING_MASK), b);
         opos++;
     }
-    MBF_HD bool copy(uint32_t dist, uint32_t len) {
+    __device__ __forceinline__ bool copy(uint32_t dist, uint32_t len) {
         if (dist > opos - ostart) return false;
-        uint32_t o = opos;
+        const uint32_t o = opos;
         if (dist <= (uint32_t)RING) {
-            uint32_t s = o - dist;
-            for (uint32_t i = 0; i < len; i++) ring[(o + i) & RING_MASK] = ring[(s + i) & RING_MASK];
+            const uint32_t src = o - dist;
+            uint32_t i = 0;
+            if (dist == 1) {  // run of one byte
+                const uint32_t b = lds_u8(s_ring + (src & RING_MASK));
+                for (; i < len; i++) sts_u8(s_ring + ((o + i) & RING_MASK), b);
+            } else if (dist >= 4) {  // source and destination do not overlap within 4 bytes
+                for (; i + 4 <= len; i += 4) {
+                    const uint32_t b0 = lds_u8(s_ring + ((src + i) & RING_MASK));
+                    const uint32_t b1 = lds_u8(s_ring + ((src + i + 1) & RING_MASK));
+                    const uint32_t b2 = lds_u8(s_ring + ((src + i + 2) & RING_MASK));
+                    const uint32_t b3 = lds_u8(s_ring + ((src + i + 3) & RING_MASK));
+                    sts_u8(s_ring + ((o + i) & RING_MASK), b0);
+                    sts_u8(s_ring + ((o + i + 1) & RING_MASK), b1);
+                    sts_u8(s_ring + ((o + i + 2) & RING_MASK), b2);
+                    sts_u8(s_ring + ((o + i + 3) & RING_MASK), b3);
+                }
+            }
+            for (; i < len; i++) sts_u8(s_ring + ((o + i) & RING_MASK), lds_u8(s_ring + ((src + i) & RING_MASK)));
         } else {
-            const uint8_t* s = U + (o - dist);
-#ifdef __CUDA_ARCH__
-            for (uint32_t i = 0; i < len; i++) ring[(o + i) & RING_MASK] = __ldcg(s + i);
-#else
-            for (uint32_t i = 0; i < len; i++) ring[(o + i) & RING_MASK] = s[i];
-#endif
+            const uint8_t* sp = U + (o - dist);  // flushed long ago by this warp; read through L2
+            uint32_t i = 0;
+            for (; i + 4 <= len; i += 4) {
+                const uint32_t b0 = __ldcg(sp + i), b1 = __ldcg(sp + i + 1), b2 = __ldcg(sp + i + 2), b3 = __ldcg(sp + i + 3);
+                sts_u8(s_ring + ((o + i) & RING_MASK), b0);
+                sts_u8(s_ring + ((o + i + 1) & RING_MASK), b1);
+                sts_u8(s_ring + ((o + i + 2) & RING_MASK), b2);
+                sts_u8(s_ring + ((o + i + 3) & RING_MASK), b3);
+            }
+            for (; i < len; i++) sts_u8(s_ring + ((o + i) & RING_MASK), __ldcg(sp + i));
         }
         opos = o + len;
         return true;
     }
 };
+
+// Hot loop of the inflate kernel: same contract as mbf::decode_symbols (inflate_core.cuh), with the
+// two LUTs and the ring addressed through 32-bit shared addresses.
+__device__ __forceinline__ int decode_symbols_fast(const DecoderTables* T, uint32_t s_ll, uint32_t s_d, BitReader& br, RingOut& out) {
+    for (;;) {
+        if (out.want_flush()) return DEC_NEED_FLUSH;
+        br.refill();
+        uint32_t e = lds_u16(s_ll + (br.peek(LL_ROOT) << 1));
+        if (e < 0x1000u) {  // literal
+            br.consume(e & 15);
+            out.put(e >> 4);
+            // >= 17 bits left: enough for one more literal/length code without a refill
+            e = lds_u16(s_ll + (br.peek(LL_ROOT) << 1));
+            if (e < 0x1000u) {
+                br.consume(e & 15);
+                out.put(e >> 4);
+                continue;
+            }
+            br.refill();
+        }
+        if (e >= LUT_SLOW) {
+            if (e != LUT_SLOW) return -INF_BAD_SYMBOL;
+            e = slow_decode(&T->ll_hd, T->ll_sym, br.peek(15), LL_ROOT);
+            if (!e) return -INF_BAD_SYMBOL;
+            if (e < 0x1000u) {
+                br.consume(e & 15);
+                out.put(e >> 4);
+                continue;
+            }
+        }
+        br.consume(e & 15);
+        uint32_t sym = e >> 4;
+        if (sym == 256) return DEC_END_BLOCK;
+        sym -= 257;
+        if (sym >= 29) return -INF_BAD_SYMBOL;
+        const uint32_t len = MBF_TBL(LEN_BASE, sym) + br.take(MBF_TBL(LEN_EXTRA, sym));
+        br.refill();
+        e = lds_u16(s_d + (br.peek(D_ROOT) << 1));
+        if (e >= LUT_SLOW) {
+            if (e != LUT_SLOW) return -INF_BAD_DISTANCE;
+            e = slow_decode(&T->d_hd, T->d_sym, br.peek(15), D_ROOT);
+            if (!e) return -INF_BAD_DISTANCE;
+        }
+        br.consume(e & 15);
+        const uint32_t ds = e >> 4;
+        if (ds >= 30) return -INF_BAD_DISTANCE;
+        const uint32_t dist = MBF_TBL(DIST_BASE, ds) + br.take(MBF_TBL(DIST_EXTRA, ds));
+        if (!out.copy(dist, len)) return -INF_BAD_DISTANCE;
+    }
+}
 
 __device__ __forceinline__ void ring_flush(const uint8_t* ring, uint8_t* U, uint32_t from, uint32_t to, int lane) {
     if (from >= to) return;
@@ -318,11 +411,13 @@ __global__ void __launch_bounds__(32) k_inflate(InflateArgs a) {
     int st = 0;  // 0 header, 1 huffman, 2 stored, 3 done
     int err = 0;
     uint32_t flushed = ostart;
+    const uint32_t s_ll = smem_addr(T.ll_lut);
+    const uint32_t s_d = smem_addr(T.d_lut);
     if (lane == 0) {
         const uint8_t* p = a.cbuf + a.blk.cpos[b];
         mis = (uint32_t)((uintptr_t)p & 3);
         br.init(p, a.blk.clen[b]);
-        out.ring = ring;
+        out.s_ring = smem_addr(ring);
         out.U = a.U;
         out.opos = out.ostart = ostart;
         out.soft_lim = min(flushed + (uint32_t)RING - 258u, oend);
@@ -357,7 +452,7 @@ __global__ void __launch_bounds__(32) k_inflate(InflateArgs a) {
                         err = INF_BAD_BTYPE; action = 1; break;
                     }
                 } else if (st == 1) {
-                    int rc = decode_symbols(&T, br, out);
+                    int rc = decode_symbols_fast(&T, s_ll, s_d, br, out);
                     if (rc == DEC_END_BLOCK) { st = 0; continue; }
                     if (rc == DEC_NEED_FLUSH) {
                         if (out.opos > oend) { err = INF_OUTPUT_OVERRUN; action = 1; }

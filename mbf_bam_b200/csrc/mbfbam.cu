@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include <chrono>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -172,7 +173,7 @@ struct Pipeline {
     uint8_t* out_host = nullptr;
     uint64_t out_cap = 0, out_len = 0;
 
-    Pipeline(int dev, const Source* s, JobKind k) : device(dev), src(s), kind(k) {
+    explicit Pipeline(int dev) : device(dev), src(nullptr), kind(JOB_INFLATE) {
         int n = 0;
         cudaError_t e = cudaGetDeviceCount(&n);
         if (e != cudaSuccess || n == 0)
@@ -181,19 +182,12 @@ struct Pipeline {
         if (dev < 0 || dev >= n) throw Error(MBFBAM_ERR_ARG, fmt("device %d out of range (have %d)", dev, n));
         CK(cudaSetDevice(dev));
         CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        W = env_u32("MBF_BAM_WINDOW_MB", 32) << 20;
-        if (W < (1u << 20)) W = 1u << 20;
-        if (W > (1024u << 20)) W = 1024u << 20;
-        cand_cap = W / 64 + 1024;
-        sync_debug = env_u32("MBF_BAM_SYNC", 0) != 0;
         CK(cudaStreamCreateWithFlags(&s_front, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s_main, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ev_reuse, cudaEventDisableTiming));
         d_meta.ensure(2 * sizeof(WinMeta));
         d_chain.ensure(sizeof(ChainState));
         d_carry.ensure(16);
-        CK(cudaMemsetAsync(d_chain.p, 0, sizeof(ChainState), s_front));
-        CK(cudaMemsetAsync(d_carry.p, 0, 16, s_main));
         h_meta_front.ensure(2 * sizeof(WinMeta));
         h_meta_main.ensure(2 * sizeof(WinMeta));
         for (int i = 0; i < 2; i++) {
@@ -201,14 +195,47 @@ struct Pipeline {
             CK(cudaEventCreateWithFlags(&w.ev_front, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&w.ev_main, cudaEventDisableTiming));
             for (auto& t : w.t) CK(cudaEventCreate(&t));
-            size_t ntile = (size_t)W / SCAN_TILE + 2;
-            w.tile_count.ensure(ntile * 4);
-            w.tile_base.ensure(ntile * 4);
-            for (DevBuf* b : {&w.cand_pos, &w.cand_bsize, &w.cpos, &w.clen, &w.isize, &w.uoff, &w.blk_start,
-                              &w.blk_end, &w.blk_nrec, &w.rec_base})
-                b->ensure((size_t)(cand_cap + 8) * 4);
         }
-        ensure_U((size_t)W * 5);
+    }
+
+    // The pipeline object (streams, events, device and pinned buffers) is cached per device and reused
+    // by every call; begin_job() resets the per-job state.  `job_bytes`: compressed bytes this job will
+    // stream, so that small jobs do not allocate full-size windows.
+    void begin_job(const Source* s, JobKind k, uint64_t job_bytes) {
+        CK(cudaSetDevice(device));
+        src = s;
+        kind = k;
+        st = mbfbam_stats{};
+        uint64_t w = (uint64_t)env_u32("MBF_BAM_WINDOW_MB", 256) << 20;
+        w = std::min<uint64_t>(std::max<uint64_t>(w, 1u << 20), 1024u << 20);
+        uint64_t need = ((job_bytes + (1u << 20)) >> 20) << 20;
+        W = (uint32_t)std::max<uint64_t>(1u << 20, std::min(w, need));
+        cand_cap = W / 64 + 1024;
+        sync_debug = env_u32("MBF_BAM_SYNC", 0) != 0;
+        CK(cudaMemsetAsync(d_chain.p, 0, sizeof(ChainState), s_front));
+        CK(cudaMemsetAsync(d_carry.p, 0, 16, s_main));
+        uint32_t mm_env = env_u32("MBF_BAM_MM_CAP", 0);
+        for (int i = 0; i < 2; i++) {
+            WinBufs& wbi = wb[i];
+            size_t ntile = (size_t)W / SCAN_TILE + 2;
+            wbi.tile_count.ensure(ntile * 4);
+            wbi.tile_base.ensure(ntile * 4);
+            for (DevBuf* b : {&wbi.cand_pos, &wbi.cand_bsize, &wbi.cpos, &wbi.clen, &wbi.isize, &wbi.uoff, &wbi.blk_start,
+                              &wbi.blk_end, &wbi.blk_nrec, &wbi.rec_base})
+                b->ensure((size_t)(cand_cap + 8) * 4);
+            wbi.in_flight = wbi.timed = false;
+            if (mm_env) wbi.mm_cap = 0;  // tests force a tiny key buffer
+        }
+        ensure_U((size_t)W * 4);
+        mode = 0;
+        cc = CountCtx{};
+        ic = IntronCtx{};
+        set_cap = set_ub = 0;
+        map_cap = map_ub = 0;
+        n_genes = n_count_words = 0;
+        out_host = nullptr;
+        out_cap = out_len = 0;
+        outside_total = 0;
     }
     ~Pipeline() {
         cudaSetDevice(device);
@@ -391,7 +418,7 @@ struct Pipeline {
     void launch_count(int bi, int emit_only) {
         WinBufs& w = wb[bi];
         if (!w.mm_cap) {
-            w.mm_cap = std::max<uint32_t>(env_u32("MBF_BAM_MM_CAP", 1u << 20), 16);
+            w.mm_cap = std::max<uint32_t>(env_u32("MBF_BAM_MM_CAP", 4u << 20), 16);
             w.mm_fp.ensure((size_t)w.mm_cap * 16);
             w.mm_slot.ensure((size_t)w.mm_cap * 4);
         }
@@ -570,6 +597,20 @@ struct Pipeline {
 
 // one pipeline call at a time per process keeps the pinned/device footprint bounded
 std::mutex g_mu;
+
+// per-device pipeline cache (guarded by g_mu)
+Pipeline& get_pipeline(int device) {
+    static std::map<int, std::unique_ptr<Pipeline>> pipes;
+    auto it = pipes.find(device);
+    if (it == pipes.end()) it = pipes.emplace(device, std::unique_ptr<Pipeline>(new Pipeline(device))).first;
+    return *it->second;
+}
+
+uint64_t range_bytes(const std::vector<ByteRange>& r) {
+    uint64_t n = 0;
+    for (const auto& x : r) n += x.cend - x.cbeg;
+    return n;
+}
 
 void copy_err(char* err, size_t errlen, const std::string& m) {
     if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
@@ -794,7 +835,8 @@ int mbfbam_count_reads(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_co
         slot_iv_off[slot_iv.size()] = (uint32_t)ivs.size();
 
         FileSource src(&r);
-        Pipeline p(job->device, &src, JOB_COUNT);
+        Pipeline& p = get_pipeline(job->device);
+        p.begin_job(&src, JOB_COUNT, range_bytes(plan.ranges));
         p.mode = job->mode;
         p.n_genes = G;
         p.n_count_words = (job->mode == MBFBAM_MODE_WEIGHTED ? (size_t)NH_DENSE * 2 : 2) * std::max<size_t>(G, 1);
@@ -872,7 +914,8 @@ int mbfbam_count_introns(mbfbam_reader* rd, int32_t device, int32_t shard_index,
         for (size_t i = 0; i < r.names.size(); i++) ref_chunk_off[i + 1] += ref_chunk_off[i];
         plan_shard(r, plan, shard_index, shard_count < 1 ? 1 : shard_count);
         FileSource src(&r);
-        Pipeline p(device, &src, JOB_INTRONS);
+        Pipeline& p = get_pipeline(device);
+        p.begin_job(&src, JOB_INTRONS, range_bytes(plan.ranges));
         const size_t n_ref = r.names.size();
         p.d_hist.ensure(std::max<size_t>(1, n_ref) * HIST_DENSE * 8);
         CK(cudaMemsetAsync(p.d_hist.p, 0, std::max<size_t>(1, n_ref) * HIST_DENSE * 8, p.s_main));
@@ -944,7 +987,8 @@ int mbfbam_inflate_buffer(const uint8_t* bgzf, uint64_t n, uint8_t* out, uint64_
         std::lock_guard<std::mutex> lk(g_mu);
         double t0 = now_ms();
         MemSource src(bgzf, n);
-        Pipeline p(device, &src, JOB_INFLATE);
+        Pipeline& p = get_pipeline(device);
+        p.begin_job(&src, JOB_INFLATE, n);
         p.out_host = out;
         p.out_cap = out_cap;
         std::vector<ByteRange> ranges;
