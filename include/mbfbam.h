@@ -156,6 +156,14 @@ void mbfbam_free_introns(mbfbam_introns* x);
 int64_t mbfbam_chunks(const mbfbam_reader* r, const mbfbam_intervals* gene_intervals,
                       int32_t* tid, uint32_t* start, uint32_t* stop, int64_t cap);
 
+/* Shard planning (host only, no GPU needed): the owned chunk range [*chunk_lo, *chunk_hi) of shard
+ * `shard_index` of `shard_count` over the ChunkedGenome table of `gene_intervals` (NULL = all header
+ * contigs), and the BGZF byte ranges [cbeg[i], cend[i]) that can hold its records.  Returns the number
+ * of byte ranges (up to `cap` are written) or -1.  See DESIGN.md (e). */
+int64_t mbfbam_plan_shard(const mbfbam_reader* r, const mbfbam_intervals* gene_intervals, int32_t shard_index,
+                          int32_t shard_count, int64_t* chunk_lo, int64_t* chunk_hi, uint64_t* cbeg,
+                          uint64_t* cend, int64_t cap);
+
 /* Stage-level entry points, used by the parity tests (and usable on their own). */
 /* Inflate every BGZF member of `bgzf` (n bytes, host memory) on `device`; `out` must hold
  * the sum of ISIZEs (returned through *out_len; query with out == NULL). */

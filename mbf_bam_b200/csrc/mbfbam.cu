@@ -769,6 +769,25 @@ int64_t mbfbam_chunks(const mbfbam_reader* r, const mbfbam_intervals* gene_inter
     }
 }
 
+int64_t mbfbam_plan_shard(const mbfbam_reader* r, const mbfbam_intervals* gene_intervals, int32_t shard_index,
+                          int32_t shard_count, int64_t* chunk_lo, int64_t* chunk_hi, uint64_t* cbeg, uint64_t* cend,
+                          int64_t cap) {
+    try {
+        ShardPlan plan;
+        plan.chunks = make_chunks(r->r, gene_intervals);
+        plan_shard(r->r, plan, shard_index, shard_count < 1 ? 1 : shard_count);
+        if (chunk_lo) *chunk_lo = (int64_t)plan.lo;
+        if (chunk_hi) *chunk_hi = (int64_t)plan.hi;
+        for (size_t i = 0; i < plan.ranges.size() && (int64_t)i < cap; i++) {
+            cbeg[i] = plan.ranges[i].cbeg;
+            cend[i] = plan.ranges[i].cend;
+        }
+        return (int64_t)plan.ranges.size();
+    } catch (...) {
+        return -1;
+    }
+}
+
 int mbfbam_count_reads(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_counts* out, mbfbam_stats* stats, char* err,
                        size_t errlen) {
     if (stats) memset(stats, 0, sizeof *stats);

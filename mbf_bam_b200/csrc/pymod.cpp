@@ -175,6 +175,22 @@ struct PyReader {
         return out;
     }
 
+    py::tuple plan(py::object gene_intervals, int shard, int nshards) {
+        Flat g;
+        const mbfbam_intervals* gp = nullptr;
+        if (!gene_intervals.is_none()) {
+            flatten(py::cast<py::dict>(gene_intervals), g);
+            gp = &g.c;
+        }
+        int64_t lo = 0, hi = 0;
+        std::vector<uint64_t> b(4096), e(4096);
+        int64_t n = mbfbam_plan_shard(r, gp, shard, nshards, &lo, &hi, b.data(), e.data(), 4096);
+        if (n < 0) value_error("could not plan the shard");
+        py::list ranges;
+        for (int64_t i = 0; i < n && i < 4096; i++) ranges.append(py::make_tuple(b[(size_t)i], e[(size_t)i]));
+        return py::make_tuple(lo, hi, ranges);
+    }
+
     // dense results: used by the dict assembly below and by the multi-process (one rank per GPU) merge
     struct Raw {
         Flat iv;
@@ -447,6 +463,7 @@ PYBIND11_MODULE(mbf_bam, m) {
         .def("drop_preload", &PyReader::drop_preload)
         .def("targets", &PyReader::targets)
         .def("chunks", &PyReader::chunks, py::arg("gene_intervals") = py::none())
+        .def("plan", &PyReader::plan, py::arg("gene_intervals"), py::arg("shard_index") = 0, py::arg("shard_count") = 1)
         .def("count_reads", &PyReader::count_reads, py::arg("mode"), py::arg("intervals"), py::arg("gene_intervals"),
              py::arg("each_read_counts_once") = py::none())
         .def("count_reads_raw", &PyReader::count_reads_raw)

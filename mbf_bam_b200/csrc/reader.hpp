@@ -333,8 +333,10 @@ inline void add_range(std::vector<ByteRange>& v, uint64_t voff_beg, uint64_t vof
                                        // end is found by the scanner (scan_len reaches one byte into it)
     if (cend > file_size) cend = file_size;
     if (cbeg >= cend) return;
-    if (!v.empty() && cbeg <= v.back().cend) {
-        // overlapping / adjacent in the file: extend (records in the shared block are walked once)
+    if (!v.empty() && cbeg <= v.back().cend + (1u << 20)) {
+        // overlapping, adjacent or separated by less than 1 MiB (e.g. the rest of the previous range's
+        // last block): one range.  Blocks in between are scanned too; their records fail the
+        // ownership test, so this only trades a little extra work for fewer, fuller windows.
         v.back().cend = std::max(v.back().cend, cend);
         return;
     }
