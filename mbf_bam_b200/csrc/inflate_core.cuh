@@ -213,8 +213,10 @@ MBF_HD int build_fixed(DecoderTables* T) {
     return build_table(T->lens + 288, 32, D_ROOT, T->d_lut, T->d_sym, &T->d_hd, false);
 }
 
-// Parse a dynamic-Huffman block header (RFC 1951 3.2.7) and build both tables.
-MBF_HD int build_dynamic(DecoderTables* T, BitReader& br) {
+// Parse a dynamic-Huffman block header (RFC 1951 3.2.7) and build both tables.  The pieces may live
+// in different memories (LUTs in shared, the rest in global scratch in the multi-decoder kernel).
+MBF_HD int build_dynamic_parts(BitReader& br, uint8_t* lens, uint16_t* ll_lut, uint16_t* ll_sym, HuffDec* ll_hd,
+                               uint16_t* d_lut, uint16_t* d_sym, HuffDec* d_hd) {
     br.refill();
     uint32_t hlit = br.take(5) + 257;
     uint32_t hdist = br.take(5) + 1;
@@ -228,24 +230,24 @@ MBF_HD int build_dynamic(DecoderTables* T, BitReader& br) {
     }
     // the code-length code's LUT (128 entries) and lists live in d_lut / d_sym until the real
     // distance table is built
-    int rc = build_table(cl, 19, CL_ROOT, T->d_lut, T->d_sym, &T->d_hd, true);
+    int rc = build_table(cl, 19, CL_ROOT, d_lut, d_sym, d_hd, true);
     if (rc) return rc;
     uint32_t n = hlit + hdist, i = 0;
     while (i < n) {
         br.refill();
-        uint32_t e = T->d_lut[br.peek(CL_ROOT)];
+        uint32_t e = d_lut[br.peek(CL_ROOT)];
         if (e >= LUT_SLOW) return INF_BAD_HEADER;  // code-length codes are <= 7 bits = CL_ROOT
         uint32_t l = e & 15;
         br.consume(l);
         uint32_t s = e >> 4;
         if (s < 16) {
-            T->lens[i++] = (uint8_t)s;
+            lens[i++] = (uint8_t)s;
             continue;
         }
         uint32_t rep, val = 0;
         if (s == 16) {
             if (i == 0) return INF_BAD_HEADER;
-            val = T->lens[i - 1];
+            val = lens[i - 1];
             rep = 3 + br.take(2);
         } else if (s == 17) {
             rep = 3 + br.take(3);
@@ -253,13 +255,15 @@ MBF_HD int build_dynamic(DecoderTables* T, BitReader& br) {
             rep = 11 + br.take(7);
         }
         if (i + rep > n) return INF_BAD_HEADER;
-        for (uint32_t k = 0; k < rep; k++) T->lens[i++] = (uint8_t)val;
+        for (uint32_t k = 0; k < rep; k++) lens[i++] = (uint8_t)val;
     }
-    if (T->lens[256] == 0) return INF_BAD_HEADER;  // no end-of-block code
-    // distance lengths must move out of the way before d_lut is rebuilt: build litlen first
-    rc = build_table(T->lens, (int)hlit, LL_ROOT, T->ll_lut, T->ll_sym, &T->ll_hd, false);
+    if (lens[256] == 0) return INF_BAD_HEADER;  // no end-of-block code
+    rc = build_table(lens, (int)hlit, LL_ROOT, ll_lut, ll_sym, ll_hd, false);
     if (rc) return rc;
-    return build_table(T->lens + hlit, (int)hdist, D_ROOT, T->d_lut, T->d_sym, &T->d_hd, false);
+    return build_table(lens + hlit, (int)hdist, D_ROOT, d_lut, d_sym, d_hd, false);
+}
+MBF_HD int build_dynamic(DecoderTables* T, BitReader& br) {
+    return build_dynamic_parts(br, T->lens, T->ll_lut, T->ll_sym, &T->ll_hd, T->d_lut, T->d_sym, &T->d_hd);
 }
 
 // Status of decode_symbols

@@ -150,7 +150,7 @@ struct Pipeline {
     WinBufs wb[2];
     DevBuf U[2];
     size_t U_cap = 0;    // data bytes (without prefix/slack)
-    DevBuf d_meta, d_chain, d_carry;
+    DevBuf d_meta, d_chain, d_carry, d_scratch;
     PinnedBuf h_meta_front, h_meta_main;
     int sm_count = 148;
     bool sync_debug = false;
@@ -371,11 +371,7 @@ struct Pipeline {
         CK(cudaStreamWaitEvent(s_main, w.ev_front, 0));
         BlockArrays b{w.cpos.as<uint32_t>(), w.clen.as<uint32_t>(), w.isize.as<uint32_t>(), w.uoff.as<uint32_t>()};
         CK(cudaEventRecord(w.t[2], s_main));
-        if (m.n_blocks) {
-            InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
-            k_inflate<<<m.n_blocks, 32, 0, s_main>>>(ia);
-            launched("k_inflate", s_main);
-        }
+        if (m.n_blocks) launch_inflate(w, b, bi, m.n_blocks);
         CK(cudaEventRecord(w.t[3], s_main));
         if (kind == JOB_INFLATE) {
             if (out_host) {
@@ -411,6 +407,34 @@ struct Pipeline {
         st.d2h_bytes += sizeof(WinMeta);
         CK(cudaEventRecord(w.ev_main, s_main));
         w.timed = true;
+    }
+
+    // K1: multi-decoder kernel (D lanes per warp, MBF_BAM_INFLATE_D = 4/8/16/32) or, with D = 0, the
+    // one-block-per-warp kernel
+    template <int D>
+    void launch_multi(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks) {
+        const int smem = D * DEC_SMEM;
+        CK(cudaFuncSetAttribute(k_inflate_multi<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
+        uint32_t grid = std::min<uint32_t>((n_blocks + D - 1) / D, (uint32_t)(sm_count * per_sm));
+        d_scratch.ensure((size_t)sm_count * 32 * 32 * sizeof(DecoderScratch));
+        InflateArgs3 ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi), d_scratch.as<DecoderScratch>()};
+        k_inflate_multi<D><<<grid, 32, smem, s_main>>>(ia);
+        launched("k_inflate_multi", s_main);
+    }
+    void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks) {
+        switch (env_u32("MBF_BAM_INFLATE_D", 8)) {
+            case 0: {
+                InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
+                k_inflate<<<n_blocks, 32, 0, s_main>>>(ia);
+                launched("k_inflate", s_main);
+                break;
+            }
+            case 4: launch_multi<4>(w, b, bi, n_blocks); break;
+            case 16: launch_multi<16>(w, b, bi, n_blocks); break;
+            case 32: launch_multi<32>(w, b, bi, n_blocks); break;
+            default: launch_multi<8>(w, b, bi, n_blocks); break;
+        }
     }
 
     int count_grid() const { return sm_count * 8; }
