@@ -377,18 +377,22 @@ __device__ __forceinline__ int decode_symbols_fast(const DecoderTables* T, uint3
     }
 }
 
-__device__ __forceinline__ void ring_flush(const uint8_t* ring, uint8_t* U, uint32_t from, uint32_t to, int lane) {
+template <uint32_t MASK>
+__device__ __forceinline__ void ring_flush_n(const uint8_t* ring, uint8_t* U, uint32_t from, uint32_t to, int lane) {
     if (from >= to) return;
     uint32_t head_end = min(to, (from + 15u) & ~15u);
-    for (uint32_t i = from + lane; i < head_end; i += 32) U[i] = ring[i & RING_MASK];
+    for (uint32_t i = from + lane; i < head_end; i += 32) U[i] = ring[i & MASK];
     uint32_t body_end = to & ~15u;
     if (body_end > head_end) {
         for (uint32_t i = head_end + 16u * lane; i < body_end; i += 512u)
-            *(uint4*)(U + i) = *(const uint4*)(ring + (i & RING_MASK));
+            *(uint4*)(U + i) = *(const uint4*)(ring + (i & MASK));
     } else {
         body_end = head_end;
     }
-    for (uint32_t i = body_end + lane; i < to; i += 32) U[i] = ring[i & RING_MASK];
+    for (uint32_t i = body_end + lane; i < to; i += 32) U[i] = ring[i & MASK];
+}
+__device__ __forceinline__ void ring_flush(const uint8_t* ring, uint8_t* U, uint32_t from, uint32_t to, int lane) {
+    ring_flush_n<RING_MASK>(ring, U, from, to, lane);
 }
 
 struct InflateArgs {
@@ -491,6 +495,180 @@ __global__ void __launch_bounds__(32) k_inflate(InflateArgs a) {
         if (lane == 0) out.soft_lim = min(flushed + (uint32_t)RING - 258u, oend);
     }
     if (lane == 0 && err) set_err(a.meta, WERR_INFLATE + (uint32_t)err, b);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 (batched form): one BGZF block per warp.  Measured on the synthetic BAMs, 40 % of the DEFLATE
+// symbols are matches and they produce 86 % of the output bytes, so the byte copies -- not the
+// Huffman decode -- dominated the single-lane kernel.  Here lane 0 only DECODES: it fills a queue
+// of up to 32 symbols (literal byte, or length+distance); then the whole warp materialises the
+// batch: an inclusive scan over the symbol lengths gives every symbol its output offset, all
+// literals are stored in one step, and each match is copied by up to 32 lanes at once (a periodic
+// source index handles distance < length).  Sources within BATCH_NEAR bytes come from the ring in
+// shared memory, older ones from L2/HBM (flushed before the batch is materialised).
+constexpr int RING4 = 2048;
+constexpr uint32_t RING4_MASK = RING4 - 1;
+constexpr uint32_t BATCH_MAX_OUT = 512;               // output bytes per batch
+constexpr uint32_t BATCH_NEAR = RING4 - BATCH_MAX_OUT;  // matches with dist <= this read the ring
+
+struct BatchShared {
+    DecoderTables T;
+    __align__(16) uint8_t ring[RING4];
+    uint32_t q[32];
+    uint32_t qn;
+    int status;  // 0 more symbols follow, 1 member finished, <0 -InflateError
+};
+
+__global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
+    __shared__ BatchShared S;
+    const uint32_t b = blockIdx.x;
+    if (b >= a.meta->n_blocks) return;
+    const int lane = threadIdx.x;
+    const uint32_t ostart = a.blk.uoff[b], isize = a.blk.isize[b], oend = ostart + isize;
+    uint8_t* const U = a.U;
+    const uint32_t s_ll = smem_addr(S.T.ll_lut);
+    const uint32_t s_d = smem_addr(S.T.d_lut);
+    const uint32_t s_ring = smem_addr(S.ring);
+    const uint32_t s_q = smem_addr(S.q);
+    // lane-0 decoder state
+    BitReader br;
+    uint32_t mis = 0, bfinal = 0, stored_left = 0;
+    int st = 0;  // 0 header, 1 huffman, 2 stored
+    if (lane == 0) {
+        const uint8_t* p = a.cbuf + a.blk.cpos[b];
+        mis = (uint32_t)((uintptr_t)p & 3);
+        br.init(p, a.blk.clen[b]);
+    }
+    uint32_t opos = ostart, flushed = ostart;  // warp-uniform
+    int err = 0;
+    for (;;) {
+        if (lane == 0) {
+            // ---- decode up to 32 symbols / BATCH_MAX_OUT bytes into the queue
+            uint32_t n = 0, acc = 0;
+            int status = 0;
+            while (n < 32 && acc + 258 <= BATCH_MAX_OUT) {
+                if (st == 0) {
+                    if (bfinal) { status = 1; break; }
+                    br.refill();
+                    bfinal = br.take(1);
+                    const uint32_t btype = br.take(2);
+                    if (btype == 0) {
+                        br.consume(br.cnt & 7);
+                        br.refill();
+                        const uint32_t len = br.take(16);
+                        br.refill();
+                        const uint32_t nlen = br.take(16);
+                        if ((len ^ 0xffffu) != nlen) { status = -INF_BAD_STORED; break; }
+                        stored_left = len;
+                        st = len ? 2 : 0;
+                    } else if (btype == 1) {
+                        const int rc = build_fixed(&S.T);
+                        if (rc) { status = -rc; break; }
+                        st = 1;
+                    } else if (btype == 2) {
+                        const int rc = build_dynamic(&S.T, br);
+                        if (rc) { status = -rc; break; }
+                        st = 1;
+                    } else {
+                        status = -INF_BAD_BTYPE;
+                        break;
+                    }
+                    continue;
+                }
+                if (st == 2) {
+                    br.refill();
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_q + 4 * n), "r"(br.take(8)) : "memory");
+                    n++;
+                    acc++;
+                    if (--stored_left == 0) st = 0;
+                    continue;
+                }
+                br.refill();
+                uint32_t e = lds_u16(s_ll + (br.peek(LL_ROOT) << 1));
+                if (e >= LUT_SLOW) {
+                    e = e == LUT_SLOW ? slow_decode(&S.T.ll_hd, S.T.ll_sym, br.peek(15), LL_ROOT) : 0u;
+                    if (!e) { status = -INF_BAD_SYMBOL; break; }
+                }
+                br.consume(e & 15);
+                uint32_t sym = e >> 4;
+                if (sym < 256) {
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_q + 4 * n), "r"(sym) : "memory");
+                    n++;
+                    acc++;
+                    continue;
+                }
+                if (sym == 256) { st = 0; continue; }
+                sym -= 257;
+                if (sym >= 29) { status = -INF_BAD_SYMBOL; break; }
+                const uint32_t len = MBF_TBL(LEN_BASE, sym) + br.take(MBF_TBL(LEN_EXTRA, sym));
+                br.refill();
+                e = lds_u16(s_d + (br.peek(D_ROOT) << 1));
+                if (e >= LUT_SLOW) e = e == LUT_SLOW ? slow_decode(&S.T.d_hd, S.T.d_sym, br.peek(15), D_ROOT) : 0u;
+                const uint32_t ds = e >> 4;
+                if (!e || ds >= 30) { status = -INF_BAD_DISTANCE; break; }
+                br.consume(e & 15);
+                const uint32_t dist = MBF_TBL(DIST_BASE, ds) + br.take(MBF_TBL(DIST_EXTRA, ds));
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_q + 4 * n), "r"(0x80000000u | (len << 16) | (dist - 1)) : "memory");
+                n++;
+                acc += len;
+            }
+            S.qn = n;
+            S.status = status;
+        }
+        __syncwarp();
+        const uint32_t n = S.qn;
+        const int status = S.status;
+        // ---- older output goes to HBM first (far matches read it back through L2)
+        {
+            const uint32_t upto = min(opos & ~15u, oend);
+            ring_flush_n<RING4_MASK>(S.ring, U, flushed, upto, lane);
+            if (upto > flushed) flushed = upto;
+        }
+        const uint32_t e = (uint32_t)lane < n ? S.q[lane] : 0u;
+        const bool is_match = (e >> 31) != 0;
+        const uint32_t mylen = (uint32_t)lane < n ? (is_match ? ((e >> 16) & 0x1ffu) : 1u) : 0u;
+        uint32_t incl = mylen;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t myoff = incl - mylen;
+        if (opos + total > oend) { err = INF_OUTPUT_OVERRUN; break; }
+        if ((uint32_t)lane < n && !is_match) sts_u8(s_ring + ((opos + myoff) & RING4_MASK), e & 0xffu);
+        __syncwarp();
+        unsigned mm = __ballot_sync(0xffffffffu, is_match);
+        bool bad = false;
+        while (mm) {
+            const int j = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+            const uint32_t dst = opos + __shfl_sync(0xffffffffu, myoff, j);
+            const uint32_t len = (ej >> 16) & 0x1ffu, dist = (ej & 0x7fffu) + 1u;
+            if (dist > dst - ostart) { bad = true; break; }
+            const uint32_t sbase = dst - dist;
+            for (uint32_t i = lane; i < len; i += 32) {
+                const uint32_t k = dist >= len ? i : i % dist;
+                uint32_t v;
+                if (dist <= BATCH_NEAR) v = lds_u8(s_ring + ((sbase + k) & RING4_MASK));
+                else v = __ldcg(U + sbase + k);
+                sts_u8(s_ring + ((dst + i) & RING4_MASK), v);
+            }
+            __syncwarp();
+        }
+        if (bad) { err = INF_BAD_DISTANCE; break; }
+        opos += total;
+        if (status < 0) { err = -status; break; }
+        if (status == 1) break;
+    }
+    __syncwarp();
+    if (!err) {
+        ring_flush_n<RING4_MASK>(S.ring, U, flushed, min(opos, oend), lane);
+        if (opos != oend) err = INF_SIZE_MISMATCH;
+        else if (lane == 0 && br.bytes_consumed(mis) > a.blk.clen[b]) err = INF_INPUT_OVERRUN;
+    }
+    if (err && lane == 0) set_err(a.meta, WERR_INFLATE + (uint32_t)err, b);
 }
 
 // ---------------------------------------------------------------------------------------------

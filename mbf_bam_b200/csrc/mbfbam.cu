@@ -423,11 +423,17 @@ struct Pipeline {
         launched("k_inflate_multi", s_main);
     }
     void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks) {
-        switch (env_u32("MBF_BAM_INFLATE_D", 8)) {
+        switch (env_u32("MBF_BAM_INFLATE_D", 1)) {
             case 0: {
                 InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
                 k_inflate<<<n_blocks, 32, 0, s_main>>>(ia);
                 launched("k_inflate", s_main);
+                break;
+            }
+            case 1: {
+                InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
+                k_inflate_batched<<<n_blocks, 32, 0, s_main>>>(ia);
+                launched("k_inflate_batched", s_main);
                 break;
             }
             case 4: launch_multi<4>(w, b, bi, n_blocks); break;
