@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "inflate_core.cuh"
+#include "inflate_batched.cuh"
 
 namespace mbf {
 
@@ -498,27 +499,7 @@ __global__ void __launch_bounds__(32) k_inflate(InflateArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1 (batched form): one BGZF block per warp.  Measured on the synthetic BAMs, 40 % of the DEFLATE
-// symbols are matches and they produce 86 % of the output bytes, so the byte copies -- not the
-// Huffman decode -- dominated the single-lane kernel.  Here lane 0 only DECODES: it fills a queue
-// of up to 32 symbols (literal byte, or length+distance); then the whole warp materialises the
-// batch: an inclusive scan over the symbol lengths gives every symbol its output offset, all
-// literals are stored in one step, and each match is copied by up to 32 lanes at once (a periodic
-// source index handles distance < length).  Sources within BATCH_NEAR bytes come from the ring in
-// shared memory, older ones from L2/HBM (flushed before the batch is materialised).
-constexpr int RING4 = 2048;
-constexpr uint32_t RING4_MASK = RING4 - 1;
-constexpr uint32_t BATCH_MAX_OUT = 512;               // output bytes per batch
-constexpr uint32_t BATCH_NEAR = RING4 - BATCH_MAX_OUT;  // matches with dist <= this read the ring
-
-struct BatchShared {
-    DecoderTables T;
-    __align__(16) uint8_t ring[RING4];
-    uint32_t q[32];
-    uint32_t qn;
-    int status;  // 0 more symbols follow, 1 member finished, <0 -InflateError
-};
-
+// K1 (batched form; see inflate_batched.cuh for the design)
 __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
     __shared__ BatchShared S;
     const uint32_t b = blockIdx.x;
@@ -526,8 +507,8 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
     const int lane = threadIdx.x;
     const uint32_t ostart = a.blk.uoff[b], isize = a.blk.isize[b], oend = ostart + isize;
     uint8_t* const U = a.U;
-    const uint32_t s_ll = smem_addr(S.T.ll_lut);
-    const uint32_t s_d = smem_addr(S.T.d_lut);
+    const uint32_t s_ll = smem_addr(S.ll_lut);
+    const uint32_t s_d = smem_addr(S.d_lut);
     const uint32_t s_ring = smem_addr(S.ring);
     const uint32_t s_q = smem_addr(S.q);
     // lane-0 decoder state
@@ -543,74 +524,131 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
     int err = 0;
     for (;;) {
         if (lane == 0) {
-            // ---- decode up to 32 symbols / BATCH_MAX_OUT bytes into the queue
             uint32_t n = 0, acc = 0;
             int status = 0;
-            while (n < 32 && acc + 258 <= BATCH_MAX_OUT) {
-                if (st == 0) {
-                    if (bfinal) { status = 1; break; }
+            if (st == 1) {
+                // ---- hot loop: Huffman symbols -> queue
+                for (;;) {
+                    if (n >= 32 || acc > BATCH_MAX_OUT - 258) break;
                     br.refill();
-                    bfinal = br.take(1);
-                    const uint32_t btype = br.take(2);
-                    if (btype == 0) {
-                        br.consume(br.cnt & 7);
-                        br.refill();
-                        const uint32_t len = br.take(16);
-                        br.refill();
-                        const uint32_t nlen = br.take(16);
-                        if ((len ^ 0xffffu) != nlen) { status = -INF_BAD_STORED; break; }
-                        stored_left = len;
-                        st = len ? 2 : 0;
-                    } else if (btype == 1) {
-                        const int rc = build_fixed(&S.T);
-                        if (rc) { status = -rc; break; }
-                        st = 1;
-                    } else if (btype == 2) {
-                        const int rc = build_dynamic(&S.T, br);
-                        if (rc) { status = -rc; break; }
-                        st = 1;
-                    } else {
-                        status = -INF_BAD_BTYPE;
+                    uint32_t e = lds_u32(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOT) - 1)) << 2));
+                    if (e < K_LEN) {  // literal
+                        br.consume(e & 15);
+                        sts_u32(s_q + 4 * n, e);
+                        n++;
+                        acc++;
+                        continue;
+                    }
+                    if (e >= K_SPECIAL) {
+                        if (e == E_SLOW) e = slow_entry<false>(&S.ll_hd, S.ll_sym, br.peek(15), LL_ROOT);
+                        if (e >= K_SPECIAL) { status = -INF_BAD_SYMBOL; break; }
+                        if (e < K_LEN) {
+                            br.consume(e & 15);
+                            sts_u32(s_q + 4 * n, e);
+                            n++;
+                            acc++;
+                            continue;
+                        }
+                    }
+                    if (e >= K_EOB) {  // end of this deflate block
+                        br.consume(e & 15);
+                        st = 0;
                         break;
                     }
-                    continue;
-                }
-                if (st == 2) {
+                    // length + distance
+                    const uint32_t cl = e & 15, xb = (e >> 4) & 15;
+                    const uint32_t len = ((e >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, cl, xb);
+                    br.consume(cl + xb);
                     br.refill();
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_q + 4 * n), "r"(br.take(8)) : "memory");
+                    uint32_t d = lds_u32(s_d + (((uint32_t)br.buf & ((1u << D_ROOT) - 1)) << 2));
+                    if (d >= K_SPECIAL) {
+                        if (d == E_SLOW) d = slow_entry<true>(&S.d_hd, S.d_sym, br.peek(15), D_ROOT);
+                        if (d >= K_SPECIAL) { status = -INF_BAD_DISTANCE; break; }
+                    }
+                    const uint32_t dcl = d & 15, dxb = (d >> 4) & 15;
+                    const uint32_t dist = ((d >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, dcl, dxb);
+                    br.consume(dcl + dxb);
+                    sts_u32(s_q + 4 * n, 0x80000000u | (len << 16) | (dist - 1));
                     n++;
-                    acc++;
-                    if (--stored_left == 0) st = 0;
-                    continue;
+                    acc += len;
                 }
-                br.refill();
-                uint32_t e = lds_u16(s_ll + (br.peek(LL_ROOT) << 1));
-                if (e >= LUT_SLOW) {
-                    e = e == LUT_SLOW ? slow_decode(&S.T.ll_hd, S.T.ll_sym, br.peek(15), LL_ROOT) : 0u;
-                    if (!e) { status = -INF_BAD_SYMBOL; break; }
-                }
-                br.consume(e & 15);
-                uint32_t sym = e >> 4;
-                if (sym < 256) {
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_q + 4 * n), "r"(sym) : "memory");
+            } else if (st == 2) {
+                // ---- stored block: bytes enter the queue as literals
+                while (n < 32 && stored_left) {
+                    br.refill();
+                    sts_u32(s_q + 4 * n, br.take(8) << 8);
                     n++;
-                    acc++;
-                    continue;
+                    stored_left--;
                 }
-                if (sym == 256) { st = 0; continue; }
-                sym -= 257;
-                if (sym >= 29) { status = -INF_BAD_SYMBOL; break; }
-                const uint32_t len = MBF_TBL(LEN_BASE, sym) + br.take(MBF_TBL(LEN_EXTRA, sym));
+                if (!stored_left) st = 0;
+            } else if (bfinal) {
+                status = 1;
+            } else {
+                // ---- block header
                 br.refill();
-                e = lds_u16(s_d + (br.peek(D_ROOT) << 1));
-                if (e >= LUT_SLOW) e = e == LUT_SLOW ? slow_decode(&S.T.d_hd, S.T.d_sym, br.peek(15), D_ROOT) : 0u;
-                const uint32_t ds = e >> 4;
-                if (!e || ds >= 30) { status = -INF_BAD_DISTANCE; break; }
-                br.consume(e & 15);
-                const uint32_t dist = MBF_TBL(DIST_BASE, ds) + br.take(MBF_TBL(DIST_EXTRA, ds));
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_q + 4 * n), "r"(0x80000000u | (len << 16) | (dist - 1)) : "memory");
-                n++;
-                acc += len;
+                bfinal = br.take(1);
+                const uint32_t btype = br.take(2);
+                if (btype == 0) {
+                    br.consume(br.cnt & 7);
+                    br.refill();
+                    const uint32_t len = br.take(16);
+                    br.refill();
+                    const uint32_t nlen = br.take(16);
+                    if ((len ^ 0xffffu) != nlen) status = -INF_BAD_STORED;
+                    stored_left = len;
+                    st = len ? 2 : 0;
+                } else if (btype == 1) {
+                    for (int i = 0; i < 144; i++) S.lens[i] = 8;
+                    for (int i = 144; i < 256; i++) S.lens[i] = 9;
+                    for (int i = 256; i < 280; i++) S.lens[i] = 7;
+                    for (int i = 280; i < 288; i++) S.lens[i] = 8;
+                    for (int i = 0; i < 32; i++) S.lens[288 + i] = 5;
+                    S.hlit = 288;
+                    S.hdist = 32;
+                    status = 2;
+                    st = 1;
+                } else if (btype == 2) {
+                    // code-length code -> lens[]; its small LUT lives in d_lut until the real one is built
+                    br.refill();
+                    const uint32_t hlit = br.take(5) + 257, hdist = br.take(5) + 1, hclen = br.take(4) + 4;
+                    uint8_t cl[19];
+                    for (int i = 0; i < 19; i++) cl[i] = 0;
+                    for (uint32_t i = 0; i < hclen; i++) {
+                        br.refill();
+                        cl[MBF_TBL(CL_ORDER, i)] = (uint8_t)br.take(3);
+                    }
+                    uint16_t* cl_lut = (uint16_t*)S.d_lut;
+                    int rc = (hlit > 286 || hdist > 30) ? (int)INF_BAD_HEADER
+                                                        : build_table(cl, 19, CL_ROOT, cl_lut, S.d_sym, &S.d_hd, true);
+                    uint32_t nn = hlit + hdist, i = 0;
+                    while (!rc && i < nn) {
+                        br.refill();
+                        const uint32_t e = cl_lut[br.peek(CL_ROOT)];
+                        if (e >= LUT_SLOW) { rc = INF_BAD_HEADER; break; }
+                        br.consume(e & 15);
+                        const uint32_t s2 = e >> 4;
+                        if (s2 < 16) { S.lens[i++] = (uint8_t)s2; continue; }
+                        uint32_t rep, val = 0;
+                        if (s2 == 16) {
+                            if (i == 0) { rc = INF_BAD_HEADER; break; }
+                            val = S.lens[i - 1];
+                            rep = 3 + br.take(2);
+                        } else if (s2 == 17) {
+                            rep = 3 + br.take(3);
+                        } else {
+                            rep = 11 + br.take(7);
+                        }
+                        if (i + rep > nn) { rc = INF_BAD_HEADER; break; }
+                        for (uint32_t k = 0; k < rep; k++) S.lens[i++] = (uint8_t)val;
+                    }
+                    if (!rc && S.lens[256] == 0) rc = INF_BAD_HEADER;
+                    S.hlit = hlit;
+                    S.hdist = hdist;
+                    status = rc ? -rc : 2;
+                    st = 1;
+                } else {
+                    status = -INF_BAD_BTYPE;
+                }
             }
             S.qn = n;
             S.status = status;
@@ -618,53 +656,64 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
         __syncwarp();
         const uint32_t n = S.qn;
         const int status = S.status;
-        // ---- older output goes to HBM first (far matches read it back through L2)
-        {
+        if (n) {
+            // ---- older output goes to HBM first (far matches read it back through L2)
             const uint32_t upto = min(opos & ~15u, oend);
-            ring_flush_n<RING4_MASK>(S.ring, U, flushed, upto, lane);
+            ring_flush_n<RINGB_MASK>(S.ring, U, flushed, upto, lane);
             if (upto > flushed) flushed = upto;
-        }
-        const uint32_t e = (uint32_t)lane < n ? S.q[lane] : 0u;
-        const bool is_match = (e >> 31) != 0;
-        const uint32_t mylen = (uint32_t)lane < n ? (is_match ? ((e >> 16) & 0x1ffu) : 1u) : 0u;
-        uint32_t incl = mylen;
+            const uint32_t e = (uint32_t)lane < n ? S.q[lane] : 0u;
+            const bool is_match = (e >> 31) != 0;
+            const uint32_t mylen = (uint32_t)lane < n ? (is_match ? ((e >> 16) & 0x1ffu) : 1u) : 0u;
+            uint32_t incl = mylen;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += y;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t myoff = incl - mylen;
-        if (opos + total > oend) { err = INF_OUTPUT_OVERRUN; break; }
-        if ((uint32_t)lane < n && !is_match) sts_u8(s_ring + ((opos + myoff) & RING4_MASK), e & 0xffu);
-        __syncwarp();
-        unsigned mm = __ballot_sync(0xffffffffu, is_match);
-        bool bad = false;
-        while (mm) {
-            const int j = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
-            const uint32_t dst = opos + __shfl_sync(0xffffffffu, myoff, j);
-            const uint32_t len = (ej >> 16) & 0x1ffu, dist = (ej & 0x7fffu) + 1u;
-            if (dist > dst - ostart) { bad = true; break; }
-            const uint32_t sbase = dst - dist;
-            for (uint32_t i = lane; i < len; i += 32) {
-                const uint32_t k = dist >= len ? i : i % dist;
-                uint32_t v;
-                if (dist <= BATCH_NEAR) v = lds_u8(s_ring + ((sbase + k) & RING4_MASK));
-                else v = __ldcg(U + sbase + k);
-                sts_u8(s_ring + ((dst + i) & RING4_MASK), v);
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += y;
             }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t myoff = incl - mylen;
+            if (opos + total > oend) { err = INF_OUTPUT_OVERRUN; break; }
+            if ((uint32_t)lane < n && !is_match) sts_u8(s_ring + ((opos + myoff) & RINGB_MASK), (e >> 8) & 0xffu);
             __syncwarp();
+            unsigned mm = __ballot_sync(0xffffffffu, is_match);
+            bool bad = false;
+            while (mm) {
+                const int j = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+                const uint32_t dst = opos + __shfl_sync(0xffffffffu, myoff, j);
+                const uint32_t len = (ej >> 16) & 0x1ffu, dist = (ej & 0x7fffu) + 1u;
+                if (dist > dst - ostart) { bad = true; break; }
+                const uint32_t sbase = dst - dist;
+                if (dist >= len) {
+                    if (dist <= BATCH_NEAR) {
+                        for (uint32_t i = lane; i < len; i += 32)
+                            sts_u8(s_ring + ((dst + i) & RINGB_MASK), lds_u8(s_ring + ((sbase + i) & RINGB_MASK)));
+                    } else {
+                        for (uint32_t i = lane; i < len; i += 32)
+                            sts_u8(s_ring + ((dst + i) & RINGB_MASK), __ldcg(U + sbase + i));
+                    }
+                } else {  // overlapping: the source repeats with period dist (all of it precedes dst)
+                    for (uint32_t i = lane; i < len; i += 32)
+                        sts_u8(s_ring + ((dst + i) & RINGB_MASK), lds_u8(s_ring + ((sbase + i % dist) & RINGB_MASK)));
+                }
+                __syncwarp();
+            }
+            if (bad) { err = INF_BAD_DISTANCE; break; }
+            opos += total;
         }
-        if (bad) { err = INF_BAD_DISTANCE; break; }
-        opos += total;
         if (status < 0) { err = -status; break; }
         if (status == 1) break;
+        if (status == 2) {
+            const uint32_t hlit = S.hlit, hdist = S.hdist;
+            err = build_lut_warp<false>(S.lens, (int)hlit, LL_ROOT, S.ll_lut, S.ll_sym, &S.ll_hd, S.run, lane);
+            if (!err) err = build_lut_warp<true>(S.lens + hlit, (int)hdist, D_ROOT, S.d_lut, S.d_sym, &S.d_hd, S.run, lane);
+            if (err) break;
+        }
     }
     __syncwarp();
     if (!err) {
-        ring_flush_n<RING4_MASK>(S.ring, U, flushed, min(opos, oend), lane);
+        ring_flush_n<RINGB_MASK>(S.ring, U, flushed, min(opos, oend), lane);
         if (opos != oend) err = INF_SIZE_MISMATCH;
         else if (lane == 0 && br.bytes_consumed(mis) > a.blk.clen[b]) err = INF_INPUT_OVERRUN;
     }
