@@ -14,7 +14,9 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -297,9 +299,7 @@ struct Pipeline {
         } else {
             w.h_c.ensure((size_t)W + 65536 + 256);
             w.d_c.ensure((size_t)W + 65536 + 256);
-            src->read(win_off, (size_t)avail, w.h_c.as<uint8_t>());
-            memset(w.h_c.as<uint8_t>() + avail, 0, 128);
-            CK(cudaMemcpyAsync(w.d_c.p, w.h_c.p, (size_t)avail + 128, cudaMemcpyHostToDevice, s_front));
+            stage_window(w, win_off, (size_t)avail);
             st.h2d_bytes += avail;
             w.c_ptr = w.d_c.as<uint8_t>();
         }
@@ -340,6 +340,60 @@ struct Pipeline {
         st.d2h_bytes += sizeof(WinMeta);
         CK(cudaEventRecord(w.ev_front, s_front));
         w.in_flight = true;
+    }
+
+    // Host bytes -> pinned staging -> HBM.  The window is cut into pieces read by a few threads (pread
+    // from the page cache runs at 2-4 GB/s per thread, far below PCIe); every piece is copied to the
+    // device as soon as it and its predecessors have landed, so reading and H2D overlap.
+    void stage_window(WinBufs& w, uint64_t win_off, size_t avail) {
+        uint8_t* h = w.h_c.as<uint8_t>();
+        uint8_t* d = w.d_c.as<uint8_t>();
+        const size_t PIECE = 8u << 20;
+        const size_t n_pieces = (avail + PIECE - 1) / PIECE;
+        int n_threads = (int)env_u32("MBF_BAM_READ_THREADS", 8);
+        n_threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, n_pieces));
+        if (n_pieces <= 1 || n_threads <= 1) {
+            src->read(win_off, avail, h);
+            memset(h + avail, 0, 128);
+            CK(cudaMemcpyAsync(d, h, avail + 128, cudaMemcpyHostToDevice, s_front));
+            return;
+        }
+        std::vector<std::atomic<int>> done(n_pieces);
+        for (auto& x : done) x.store(0);
+        std::atomic<size_t> next{0};
+        std::atomic<int> failed{0};
+        std::string fail_msg;
+        std::mutex fail_mu;
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++)
+            th.emplace_back([&] {
+                for (;;) {
+                    size_t i = next.fetch_add(1);
+                    if (i >= n_pieces) break;
+                    size_t off = i * PIECE, len = std::min(PIECE, avail - off);
+                    try {
+                        if (!failed.load()) src->read(win_off + off, len, h + off);
+                    } catch (const std::exception& e) {
+                        std::lock_guard<std::mutex> lk(fail_mu);
+                        fail_msg = e.what();
+                        failed.store(1);
+                    }
+                    done[i].store(1, std::memory_order_release);
+                }
+            });
+        cudaError_t cerr = cudaSuccess;
+        for (size_t i = 0; i < n_pieces; i++) {
+            while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+            size_t off = i * PIECE, len = std::min(PIECE, avail - off);
+            if (i + 1 == n_pieces) {
+                memset(h + avail, 0, 128);
+                len += 128;
+            }
+            if (!failed.load() && cerr == cudaSuccess) cerr = cudaMemcpyAsync(d + off, h + off, len, cudaMemcpyHostToDevice, s_front);
+        }
+        for (auto& t : th) t.join();
+        if (failed.load()) throw Error(MBFBAM_ERR_IO, fail_msg);
+        CK(cerr);
     }
 
     static std::string err_text(const WinMeta& m) {
@@ -594,7 +648,8 @@ struct Pipeline {
             bool first = true;
             while (pos < r.cend) {
                 uint64_t base = pos & ~(uint64_t)15;
-                uint64_t scan_end = std::min<uint64_t>(r.cend, base + W);
+                // the very first window is a quarter of the others so that the GPU starts early
+                uint64_t scan_end = std::min<uint64_t>(r.cend, base + (wins.empty() && !src->resident(device) ? std::max<uint32_t>(W / 4, 1u << 20) : W));
                 wins.push_back({base, (uint32_t)(scan_end - base), src->size(), first ? 1 : 0, r.cbeg, first ? r.first_uoff : 0u});
                 first = false;
                 pos = scan_end;
