@@ -590,7 +590,10 @@ struct Pipeline {
     void finish_main(int bi) {
         WinBufs& w = wb[bi];
         if (!w.in_flight) return;
+        const bool trace = env_u32("MBF_BAM_TRACE", 0) != 0;
+        double t_a = now_ms();
         CK(cudaEventSynchronize(w.ev_main));
+        double t_b = now_ms();
         WinMeta m = h_meta_main.as<WinMeta>()[bi];
         if (m.err) throw Error(MBFBAM_ERR_FORMAT, err_text(m));
         st.n_records += m.n_records;
@@ -612,7 +615,9 @@ struct Pipeline {
             }
             if (m.mm_count) {
                 st.n_mm_keys += m.mm_count;
+                double t_c = now_ms();
                 ensure_set(m.mm_count);
+                if (trace) fprintf(stderr, "[mbfbam]   finish: wait %.2f ms, ensure_set %.2f ms (keys %u, cap %llu)\n", t_b - t_a, now_ms() - t_c, m.mm_count, (unsigned long long)set_cap);
                 k_mm_insert<<<sm_count * 4, 256, 0, s_main>>>(w.mm_fp.as<ulonglong2>(), w.mm_slot.as<uint32_t>(), dmeta(bi), w.mm_cap,
                                                              d_set.as<ulonglong2>(), (uint32_t)(set_cap - 1),
                                                              d_counts.as<unsigned long long>(), (uint32_t)n_genes,
@@ -660,16 +665,23 @@ struct Pipeline {
             const Win& w0 = wins[0];
             issue_front(0, w0.off, w0.scan_len, w0.src_end, w0.range_start, w0.range_off, w0.first_uoff);
         }
+        const bool trace = env_u32("MBF_BAM_TRACE", 0) != 0;
         for (size_t k = 0; k < wins.size(); k++) {
             int bi = (int)(k & 1);
+            double ta = now_ms();
             finish_main(bi ^ 1);  // second half of window k-1 (must precede window k's carry copy)
+            double tb = now_ms();
             issue_main(bi);
+            double tc = now_ms();
+            if (trace) fprintf(stderr, "[mbfbam] win %zu t=%.2f finish_prev %.2f ms, issue_main %.2f ms (scan_len %u)\n", k, ta - t0, tb - ta, tc - tb, wins[k].scan_len);
             if (k + 1 < wins.size()) {
                 // buffers of parity bi^1 are reused: everything of window k-1 is queued on s_main by now
                 CK(cudaEventRecord(ev_reuse, s_main));
                 CK(cudaStreamWaitEvent(s_front, ev_reuse, 0));
                 const Win& wn = wins[k + 1];
+                double td = now_ms();
                 issue_front(bi ^ 1, wn.off, wn.scan_len, wn.src_end, wn.range_start, wn.range_off, wn.first_uoff);
+                if (trace) fprintf(stderr, "[mbfbam] win %zu issue_front(next) %.2f ms\n", k, now_ms() - td);
             }
         }
         finish_main(0);
