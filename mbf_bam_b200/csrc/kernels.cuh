@@ -81,6 +81,15 @@ __device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {
     if (sh == 0) return lo;
     return __funnelshift_r(lo, w[1], sh);
 }
+// same through L2 only (.cg): for bytes other lanes of this SM may have written recently
+__device__ __forceinline__ uint32_t ldu32_cg(const uint8_t* p) {
+    uintptr_t a = (uintptr_t)p;
+    uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    uint32_t lo = __ldcg(w);
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, __ldcg(w + 1), sh);
+}
 __device__ __forceinline__ uint32_t ldu16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 
 // ---------------------------------------------------------------------------------------------
@@ -937,6 +946,10 @@ __global__ void __launch_bounds__(32) k_inflate_multi(InflateArgs3 a) {
         }
     }
 }
+
+}  // namespace mbf
+#include "inflate_group.cuh"
+namespace mbf {
 
 // ---------------------------------------------------------------------------------------------
 // K2: record framing.  One walker thread per BGZF block follows the block_size chain of the records

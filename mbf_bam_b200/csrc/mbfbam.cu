@@ -490,6 +490,17 @@ struct Pipeline {
                 launched("k_inflate_batched", s_main);
                 break;
             }
+            case 6: {
+                const int smem = (int)sizeof(Group6Shared);
+                CK(cudaFuncSetAttribute(k_inflate_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                int per_sm = std::max(1, (227 * 1024) / (smem + 1024));
+                uint32_t grid = std::min<uint32_t>((n_blocks + G6 - 1) / G6, (uint32_t)(sm_count * per_sm));
+                InflateArgs6 ia{w.c_ptr, b.cpos, b.clen, b.isize, b.uoff, U[bi].as<uint8_t>(), &dmeta(bi)->n_blocks,
+                                &dmeta(bi)->inflate_next, &dmeta(bi)->err, &dmeta(bi)->err_info};
+                k_inflate_group<<<grid, 32, smem, s_main>>>(ia);
+                launched("k_inflate_group", s_main);
+                break;
+            }
             case 4: launch_multi<4>(w, b, bi, n_blocks); break;
             case 16: launch_multi<16>(w, b, bi, n_blocks); break;
             case 32: launch_multi<32>(w, b, bi, n_blocks); break;
