@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(32) k_inflate_group(InflateArgs6 a) {
         uint32_t nm = 0, acc = 0, flags = 0;
         int err = 0;
         uint32_t new_ostart = 0, new_oend = 0;
-        if (sub == 0) {
-            // ================================================================ phase A (leaders)
+        // ================================================================ phase A0: rare leader states
+        if (sub == 0 && st != ST6_HUFF && st != ST6_DONE) {
             if (st == ST6_IDLE) {
                 b = atomicAdd(a.queue_head, 1u);
                 if (b >= n_blocks) {
@@ -130,58 +130,7 @@ __global__ void __launch_bounds__(32) k_inflate_group(InflateArgs6 a) {
                     st = ST6_HEADER;
                 }
             }
-            if (st == ST6_HUFF) {
-                uint32_t nsym = 0;
-                if (held) {
-                    const uint32_t len = held >> 16;
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(s_mq), "r"(held), "r"(0u) : "memory");
-                    nm = 1;
-                    acc = len;
-                    held = 0;
-                }
-                while (nsym < Q6 && nm < MQ6 && acc < MAXOUT6) {
-                    br.refill();
-                    uint32_t e = lds_u32(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOT6) - 1)) << 2));
-                    if (e >= K_SPECIAL) {
-                        if (e == E_SLOW) e = slow_entry<false>(&D.ll_hd, D.ll_sym, br.peek(15), LL_ROOT6);
-                        if (e >= K_SPECIAL) { err = INF_BAD_SYMBOL; break; }
-                    }
-                    if (e < K_LEN) {  // literal: straight into the ring
-                        br.consume(e & 15);
-                        sts_u8(s_ring + ((opos + acc) & RING6_MASK), (e >> 8) & 0xffu);
-                        acc++;
-                        nsym++;
-                        continue;
-                    }
-                    if (e >= K_EOB) {
-                        br.consume(e & 15);
-                        st = ST6_HEADER;
-                        break;
-                    }
-                    const uint32_t cl = e & 15, xb = (e >> 4) & 15;
-                    const uint32_t len = ((e >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, cl, xb);
-                    br.consume(cl + xb);
-                    br.refill();
-                    uint32_t d = lds_u32(s_d + (((uint32_t)br.buf & ((1u << D_ROOT6) - 1)) << 2));
-                    if (d >= K_SPECIAL) {
-                        if (d == E_SLOW) d = slow_entry<true>(&D.d_hd, D.d_sym, br.peek(15), D_ROOT6);
-                        if (d >= K_SPECIAL) { err = INF_BAD_DISTANCE; break; }
-                    }
-                    const uint32_t dcl = d & 15, dxb = (d >> 4) & 15;
-                    const uint32_t dist = ((d >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, dcl, dxb);
-                    br.consume(dcl + dxb);
-                    if (dist > opos + acc - ostart) { err = INF_BAD_DISTANCE; break; }
-                    const uint32_t packed = (len << 16) | (dist - 1);
-                    if (acc + len > MAXOUT6) {  // does not fit this batch: first entry of the next one
-                        held = packed;
-                        break;
-                    }
-                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(s_mq + 8 * nm), "r"(packed), "r"(acc) : "memory");
-                    nm++;
-                    acc += len;
-                    nsym++;
-                }
-            } else if (st == ST6_STORED) {
+            if (st == ST6_STORED) {
                 while (stored_left && acc < MAXOUT6) {
                     br.refill();
                     sts_u8(s_ring + ((opos + acc) & RING6_MASK), br.take(8));
@@ -261,12 +210,75 @@ __global__ void __launch_bounds__(32) k_inflate_group(InflateArgs6 a) {
                     }
                 }
             }
-            if (!err && opos + acc > oend) err = INF_OUTPUT_OVERRUN;
+        }
+        // ================================================================ phase A1: SIMT decode
+        // The loop is warp-uniform (every lane iterates, the vote at its top is the reconvergence
+        // point); only active leaders do work, one symbol per trip, no early exits inside.
+        bool act = sub == 0 && st == ST6_HUFF && !(flags & F6_BUILD) && !err;
+        if (act && held) {
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(s_mq), "r"(held), "r"(0u) : "memory");
+            nm = 1;
+            acc = held >> 16;
+            held = 0;
+        }
+        for (uint32_t it = 0; it < Q6; it++) {
+            if (!__any_sync(0xffffffffu, act)) break;
+            if (act) {
+                br.refill();
+                uint32_t e = lds_u32(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOT6) - 1)) << 2));
+                if (e >= K_SPECIAL) {
+                    if (e == E_SLOW) e = slow_entry<false>(&D.ll_hd, D.ll_sym, br.peek(15), LL_ROOT6);
+                    if (e >= K_SPECIAL) err = INF_BAD_SYMBOL;
+                }
+                if (err) {
+                    act = false;
+                } else if (e < K_LEN) {  // literal: straight into the ring
+                    br.consume(e & 15);
+                    sts_u8(s_ring + ((opos + acc) & RING6_MASK), (e >> 8) & 0xffu);
+                    acc++;
+                } else if (e >= K_EOB) {
+                    br.consume(e & 15);
+                    st = ST6_HEADER;
+                    act = false;
+                } else {
+                    const uint32_t cl = e & 15, xb = (e >> 4) & 15;
+                    const uint32_t len = ((e >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, cl, xb);
+                    br.consume(cl + xb);
+                    br.refill();
+                    uint32_t d = lds_u32(s_d + (((uint32_t)br.buf & ((1u << D_ROOT6) - 1)) << 2));
+                    if (d >= K_SPECIAL) {
+                        if (d == E_SLOW) d = slow_entry<true>(&D.d_hd, D.d_sym, br.peek(15), D_ROOT6);
+                        if (d >= K_SPECIAL) err = INF_BAD_DISTANCE;
+                    }
+                    const uint32_t dcl = d & 15, dxb = (d >> 4) & 15;
+                    const uint32_t dist = ((d >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, dcl, dxb);
+                    if (!err && dist > opos + acc - ostart) err = INF_BAD_DISTANCE;
+                    if (err) {
+                        act = false;
+                    } else {
+                        br.consume(dcl + dxb);
+                        const uint32_t packed = (len << 16) | (dist - 1);
+                        if (acc + len > MAXOUT6) {  // does not fit this batch: first entry of the next one
+                            held = packed;
+                            act = false;
+                        } else {
+                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(s_mq + 8 * nm), "r"(packed), "r"(acc) : "memory");
+                            nm++;
+                            acc += len;
+                        }
+                    }
+                }
+                if (nm >= MQ6 || acc >= MAXOUT6) act = false;
+            }
+        }
+        if (sub == 0) {
+            if (!err && st != ST6_DONE && opos + acc > oend) err = INF_OUTPUT_OVERRUN;
             if (err) {
                 set_err6(a, WERR_INFLATE + (uint32_t)err, b);
                 st = ST6_IDLE;  // drop this member
                 nm = 0;
                 acc = 0;
+                held = 0;
                 flags &= F6_NEW;
             }
         }
@@ -275,77 +287,87 @@ __global__ void __launch_bounds__(32) k_inflate_group(InflateArgs6 a) {
         nm = __shfl_sync(0xffffffffu, nm, leader_lane);
         acc = __shfl_sync(0xffffffffu, acc, leader_lane);
         flags = __shfl_sync(0xffffffffu, flags, leader_lane);
-        if (flags & F6_NEW) {
-            ostart = __shfl_sync(grp_mask, new_ostart, leader_lane);
-            oend = __shfl_sync(grp_mask, new_oend, leader_lane);
-            opos = flushed = ostart;
+        {
+            const uint32_t os = __shfl_sync(0xffffffffu, new_ostart, leader_lane);
+            const uint32_t oe = __shfl_sync(0xffffffffu, new_oend, leader_lane);
+            if (flags & F6_NEW) {
+                ostart = os;
+                oend = oe;
+                opos = flushed = os;
+            }
         }
-        // ================================================================ phase B (copies)
+        // ================================================================ phase B: copies
         if (acc) {
             const uint32_t upto = min(opos & ~15u, oend);
             group_flush(D.ring, U, flushed, upto, sub);
             if (upto > flushed) flushed = upto;
         }
         __syncwarp();
-        // pass 1: matches that read nothing of this batch, one whole match per lane
-        for (uint32_t j = sub; j < nm; j += 4) {
-            const uint2 m = D.mq[j];
-            const uint32_t len = m.x >> 16, dist = (m.x & 0x7fffu) + 1u, off = m.y;
-            if (dist < off + len) continue;  // pass 2
+        const uint32_t max_nm = __reduce_max_sync(0xffffffffu, nm);
+        bool has_dep = false;
+        // pass 1: matches that read nothing of this batch -- one whole match per lane, 16 bytes per step
+        for (uint32_t r = 0; r * 4 < max_nm; r++) {
+            const uint32_t j = r * 4 + sub;
+            uint32_t len = 0, dist = 1, off = 0;
+            if (j < nm) {
+                const uint2 m = D.mq[j];
+                len = m.x >> 16;
+                dist = (m.x & 0x7fffu) + 1u;
+                off = m.y;
+                if (dist < off + len) {  // reads this batch (or overlaps itself): pass 2
+                    has_dep = true;
+                    len = 0;
+                }
+            }
             const uint32_t dst = opos + off, src = dst - dist;
-            if (dist <= NEAR6) {
-                uint32_t i = 0;
-                for (; i + 4 <= len; i += 4) {
-                    const uint32_t b0 = lds_u8(s_ring + ((src + i) & RING6_MASK));
-                    const uint32_t b1 = lds_u8(s_ring + ((src + i + 1) & RING6_MASK));
-                    const uint32_t b2 = lds_u8(s_ring + ((src + i + 2) & RING6_MASK));
-                    const uint32_t b3 = lds_u8(s_ring + ((src + i + 3) & RING6_MASK));
-                    sts_u8(s_ring + ((dst + i) & RING6_MASK), b0);
-                    sts_u8(s_ring + ((dst + i + 1) & RING6_MASK), b1);
-                    sts_u8(s_ring + ((dst + i + 2) & RING6_MASK), b2);
-                    sts_u8(s_ring + ((dst + i + 3) & RING6_MASK), b3);
-                }
-                for (; i < len; i++) sts_u8(s_ring + ((dst + i) & RING6_MASK), lds_u8(s_ring + ((src + i) & RING6_MASK)));
-            } else {
-                const uint8_t* sp = U + src;  // flushed before this batch
-                uint32_t i = 0;
-                for (; i + 16 <= len; i += 16) {
-                    const uint32_t w0 = ldu32_cg(sp + i), w1 = ldu32_cg(sp + i + 4), w2 = ldu32_cg(sp + i + 8), w3 = ldu32_cg(sp + i + 12);
-                    const uint32_t w[4] = {w0, w1, w2, w3};
+            const bool near = dist <= NEAR6;
+            for (uint32_t base = 0; __any_sync(0xffffffffu, base < len); base += 16) {
+                if (base < len) {
+                    const uint32_t rem = min(16u, len - base);
+                    uint32_t w[4];
+                    if (near) {
 #pragma unroll
-                    for (int k = 0; k < 16; k++) sts_u8(s_ring + ((dst + i + k) & RING6_MASK), (w[k >> 2] >> (8 * (k & 3))) & 0xffu);
-                }
-                if (i < len) {
-                    // tail of up to 15 bytes: loads first (may touch up to 3 bytes past the source, inside U)
-                    const uint32_t rem = len - i;
-                    const uint32_t w0 = ldu32_cg(sp + i);
-                    const uint32_t w1 = rem > 4 ? ldu32_cg(sp + i + 4) : 0u;
-                    const uint32_t w2 = rem > 8 ? ldu32_cg(sp + i + 8) : 0u;
-                    const uint32_t w3 = rem > 12 ? ldu32_cg(sp + i + 12) : 0u;
-                    const uint32_t w[4] = {w0, w1, w2, w3};
+                        for (int q = 0; q < 4; q++) {
+                            w[q] = 0;
 #pragma unroll
-                    for (int k = 0; k < 15; k++)
-                        if ((uint32_t)k < rem) sts_u8(s_ring + ((dst + i + k) & RING6_MASK), (w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                            for (int k = 0; k < 4; k++)
+                                if ((uint32_t)(4 * q + k) < rem) w[q] |= lds_u8(s_ring + ((src + base + 4 * q + k) & RING6_MASK)) << (8 * k);
+                        }
+                    } else {
+                        const uint8_t* sp = U + src + base;  // flushed before this batch; read through L2
+#pragma unroll
+                        for (int q = 0; q < 4; q++) w[q] = (uint32_t)(4 * q) < rem ? ldu32_cg(sp + 4 * q) : 0u;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 16; k++)
+                        if ((uint32_t)k < rem) sts_u8(s_ring + ((dst + base + k) & RING6_MASK), (w[k >> 2] >> (8 * (k & 3))) & 0xffu);
                 }
             }
         }
         __syncwarp();
-        // pass 2: matches that read this batch's own output (or overlap themselves), in order
-        for (uint32_t j = 0; j < nm; j++) {
-            const uint2 m = D.mq[j];
-            const uint32_t len = m.x >> 16, dist = (m.x & 0x7fffu) + 1u, off = m.y;
-            if (dist >= off + len) continue;
-            const uint32_t dst = opos + off, src = dst - dist;
-            if (dist >= len) {
-                for (uint32_t i = sub; i < len; i += 4) sts_u8(s_ring + ((dst + i) & RING6_MASK), lds_u8(s_ring + ((src + i) & RING6_MASK)));
-            } else {
-                for (uint32_t i = sub; i < len; i += 4) sts_u8(s_ring + ((dst + i) & RING6_MASK), lds_u8(s_ring + ((src + i % dist) & RING6_MASK)));
+        // pass 2: matches that read this batch's own output (or overlap themselves), in order, 4 lanes each
+        if (__any_sync(0xffffffffu, has_dep)) {
+            for (uint32_t j = 0; j < max_nm; j++) {
+                uint32_t len = 0, dist = 1, off = 0;
+                if (j < nm) {
+                    const uint2 m = D.mq[j];
+                    const uint32_t l = m.x >> 16, d = (m.x & 0x7fffu) + 1u;
+                    if (d < m.y + l) { len = l; dist = d; off = m.y; }
+                }
+                if (!__any_sync(0xffffffffu, len != 0)) continue;
+                const uint32_t dst = opos + off, src = dst - dist;
+                for (uint32_t i0 = 0; __any_sync(0xffffffffu, i0 < len); i0 += 4) {
+                    const uint32_t i = i0 + sub;
+                    if (i < len) {
+                        const uint32_t k = dist >= len ? i : i % dist;  // periodic source when it overlaps itself
+                        sts_u8(s_ring + ((dst + i) & RING6_MASK), lds_u8(s_ring + ((src + k) & RING6_MASK)));
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp(grp_mask);
         }
         opos += acc;
-        __syncwarp();
-        // ================================================================ phase C (table builds)
+        // ================================================================ phase C: table builds
         unsigned need = __ballot_sync(0xffffffffu, sub == 0 && (flags & F6_BUILD));
         while (need) {
             const int g = (__ffs(need) - 1) >> 2;
@@ -359,7 +381,7 @@ __global__ void __launch_bounds__(32) k_inflate_group(InflateArgs6 a) {
                 st = ST6_IDLE;
             }
         }
-        // ================================================================ phase D (finished members)
+        // ================================================================ phase D: finished members
         if (flags & F6_FIN) {
             group_flush(D.ring, U, flushed, min(opos, oend), sub);
             if (sub == 0) {
