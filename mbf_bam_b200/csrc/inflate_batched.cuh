@@ -21,6 +21,7 @@ namespace mbf {
 constexpr int RINGB = 2048;
 constexpr uint32_t RINGB_MASK = RINGB - 1;
 constexpr uint32_t BATCH_MAX_OUT = 512;                 // output bytes per batch
+constexpr uint32_t BQ_MATCHES = 32;                     // matches per batch: one per lane in the copy pass
 constexpr uint32_t BATCH_NEAR = RINGB - BATCH_MAX_OUT;  // matches with dist <= this read the ring
 
 // 32-bit LUT entry: [3:0] code length, [7:4] extra bits, [23:8] value, [31:30] kind
@@ -31,13 +32,13 @@ struct BatchShared {
     uint32_t ll_lut[1 << LL_ROOT];
     uint32_t d_lut[1 << D_ROOT];
     __align__(16) uint8_t ring[RINGB];
-    uint32_t q[32];
+    uint32_t q[2 * 32];  // (len << 16 | dist - 1, output offset) per queued match
     uint16_t ll_sym[288];
     uint16_t d_sym[32];
     HuffDec ll_hd, d_hd;
     uint32_t run[16];
     uint8_t lens[320];
-    uint32_t qn;
+    uint32_t qn, qacc;
     int status;  // 0 more symbols follow, 1 member finished, 2 table build requested, <0 -InflateError
     uint32_t hlit, hdist;
 };

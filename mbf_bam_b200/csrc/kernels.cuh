@@ -522,7 +522,8 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
     const uint32_t s_q = smem_addr(S.q);
     // lane-0 decoder state
     BitReader br;
-    uint32_t mis = 0, bfinal = 0, stored_left = 0;
+    br.words = nullptr; br.wpos = br.wlimit = 0; br.buf = 0; br.cnt = 0; br.nextw = 0;
+    uint32_t mis = 0, bfinal = 0, stored_left = 0, held = 0;
     int st = 0;  // 0 header, 1 huffman, 2 stored
     if (lane == 0) {
         const uint8_t* p = a.cbuf + a.blk.cpos[b];
@@ -533,18 +534,23 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
     int err = 0;
     for (;;) {
         if (lane == 0) {
-            uint32_t n = 0, acc = 0;
+            // ================================================== decode: literals -> ring, matches -> queue
+            uint32_t nm = 0, acc = 0;
             int status = 0;
             if (st == 1) {
-                // ---- hot loop: Huffman symbols -> queue
-                for (;;) {
-                    if (n >= 32 || acc > BATCH_MAX_OUT - 258) break;
+                if (held) {
+                    sts_u32(s_q, held);
+                    sts_u32(s_q + 4, 0u);
+                    nm = 1;
+                    acc = held >> 16;
+                    held = 0;
+                }
+                while (nm < BQ_MATCHES && acc < BATCH_MAX_OUT) {
                     br.refill();
                     uint32_t e = lds_u32(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOT) - 1)) << 2));
                     if (e < K_LEN) {  // literal
                         br.consume(e & 15);
-                        sts_u32(s_q + 4 * n, e);
-                        n++;
+                        sts_u8(s_ring + ((opos + acc) & RINGB_MASK), (e >> 8) & 0xffu);
                         acc++;
                         continue;
                     }
@@ -553,8 +559,7 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
                         if (e >= K_SPECIAL) { status = -INF_BAD_SYMBOL; break; }
                         if (e < K_LEN) {
                             br.consume(e & 15);
-                            sts_u32(s_q + 4 * n, e);
-                            n++;
+                            sts_u8(s_ring + ((opos + acc) & RINGB_MASK), (e >> 8) & 0xffu);
                             acc++;
                             continue;
                         }
@@ -564,7 +569,6 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
                         st = 0;
                         break;
                     }
-                    // length + distance
                     const uint32_t cl = e & 15, xb = (e >> 4) & 15;
                     const uint32_t len = ((e >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, cl, xb);
                     br.consume(cl + xb);
@@ -577,16 +581,22 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
                     const uint32_t dcl = d & 15, dxb = (d >> 4) & 15;
                     const uint32_t dist = ((d >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, dcl, dxb);
                     br.consume(dcl + dxb);
-                    sts_u32(s_q + 4 * n, 0x80000000u | (len << 16) | (dist - 1));
-                    n++;
+                    if (dist > opos + acc - ostart) { status = -INF_BAD_DISTANCE; break; }
+                    const uint32_t packed = (len << 16) | (dist - 1);
+                    if (acc + len > BATCH_MAX_OUT) {  // does not fit: first entry of the next batch
+                        held = packed;
+                        break;
+                    }
+                    sts_u32(s_q + 8 * nm, packed);
+                    sts_u32(s_q + 8 * nm + 4, acc);
+                    nm++;
                     acc += len;
                 }
             } else if (st == 2) {
-                // ---- stored block: bytes enter the queue as literals
-                while (n < 32 && stored_left) {
+                while (stored_left && acc < BATCH_MAX_OUT) {
                     br.refill();
-                    sts_u32(s_q + 4 * n, br.take(8) << 8);
-                    n++;
+                    sts_u8(s_ring + ((opos + acc) & RINGB_MASK), br.take(8));
+                    acc++;
                     stored_left--;
                 }
                 if (!stored_left) st = 0;
@@ -659,57 +669,84 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
                     status = -INF_BAD_BTYPE;
                 }
             }
-            S.qn = n;
+            S.qn = nm;
+            S.qacc = acc;
             S.status = status;
         }
         __syncwarp();
-        const uint32_t n = S.qn;
+        const uint32_t nm = S.qn, acc = S.qacc;
         const int status = S.status;
-        if (n) {
-            // ---- older output goes to HBM first (far matches read it back through L2)
+        if (opos + acc > oend) { err = INF_OUTPUT_OVERRUN; break; }
+        if (acc) {
+            // ================================================== materialise the batch
+            // older output goes to HBM first (far matches read it back through L2)
             const uint32_t upto = min(opos & ~15u, oend);
             ring_flush_n<RINGB_MASK>(S.ring, U, flushed, upto, lane);
             if (upto > flushed) flushed = upto;
-            const uint32_t e = (uint32_t)lane < n ? S.q[lane] : 0u;
-            const bool is_match = (e >> 31) != 0;
-            const uint32_t mylen = (uint32_t)lane < n ? (is_match ? ((e >> 16) & 0x1ffu) : 1u) : 0u;
-            uint32_t incl = mylen;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += y;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t myoff = incl - mylen;
-            if (opos + total > oend) { err = INF_OUTPUT_OVERRUN; break; }
-            if ((uint32_t)lane < n && !is_match) sts_u8(s_ring + ((opos + myoff) & RINGB_MASK), (e >> 8) & 0xffu);
             __syncwarp();
-            unsigned mm = __ballot_sync(0xffffffffu, is_match);
-            bool bad = false;
+            // pass 1: one whole match per lane, provided it reads nothing of this batch
+            uint32_t len = 0, dist = 1, off = 0;
+            bool dep = false;
+            if ((uint32_t)lane < nm) {
+                const uint32_t m = lds_u32(s_q + 8 * lane);
+                off = lds_u32(s_q + 8 * lane + 4);
+                len = m >> 16;
+                dist = (m & 0x7fffu) + 1u;
+                dep = dist < off + len;
+            }
+            const uint32_t dst = opos + off, src = dst - dist;
+            const uint32_t len1 = dep ? 0u : len;
+            const bool near = dist <= BATCH_NEAR;
+            for (uint32_t base = 0; __any_sync(0xffffffffu, base < len1); base += 16) {
+                if (base < len1) {
+                    const uint32_t rem = min(16u, len1 - base);
+                    uint32_t w[4];
+                    if (near) {
+                        // 16 source bytes from the ring with aligned 32-bit loads + funnel shifts
+                        const uint32_t s0 = src + base;
+                        const uint32_t sh = (s0 & 3u) * 8u;
+                        uint32_t x[5];
+#pragma unroll
+                        for (int q = 0; q < 5; q++) x[q] = lds_u32(s_ring + (((s0 & ~3u) + 4u * q) & RINGB_MASK));
+#pragma unroll
+                        for (int q = 0; q < 4; q++) w[q] = __funnelshift_r(x[q], x[q + 1], sh);
+                    } else {
+                        const uint8_t* sp = U + src + base;  // flushed before this batch; through L2
+#pragma unroll
+                        for (int q = 0; q < 4; q++) w[q] = (uint32_t)(4 * q) < rem ? ldu32_cg(sp + 4 * q) : 0u;
+                    }
+                    const uint32_t d0 = (dst + base) & RINGB_MASK;
+                    if (d0 + 16 <= (uint32_t)RINGB) {
+#pragma unroll
+                        for (int k = 0; k < 16; k++)
+                            if ((uint32_t)k < rem) sts_u8(s_ring + d0 + k, (w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 16; k++)
+                            if ((uint32_t)k < rem) sts_u8(s_ring + ((d0 + k) & RINGB_MASK), (w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                    }
+                }
+            }
+            __syncwarp();
+            // pass 2: matches that read this batch's own output (or overlap themselves), in order, 32 lanes each
+            unsigned mm = __ballot_sync(0xffffffffu, dep);
             while (mm) {
                 const int j = __ffs(mm) - 1;
                 mm &= mm - 1;
-                const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
-                const uint32_t dst = opos + __shfl_sync(0xffffffffu, myoff, j);
-                const uint32_t len = (ej >> 16) & 0x1ffu, dist = (ej & 0x7fffu) + 1u;
-                if (dist > dst - ostart) { bad = true; break; }
-                const uint32_t sbase = dst - dist;
-                if (dist >= len) {
-                    if (dist <= BATCH_NEAR) {
-                        for (uint32_t i = lane; i < len; i += 32)
-                            sts_u8(s_ring + ((dst + i) & RINGB_MASK), lds_u8(s_ring + ((sbase + i) & RINGB_MASK)));
-                    } else {
-                        for (uint32_t i = lane; i < len; i += 32)
-                            sts_u8(s_ring + ((dst + i) & RINGB_MASK), __ldcg(U + sbase + i));
-                    }
-                } else {  // overlapping: the source repeats with period dist (all of it precedes dst)
-                    for (uint32_t i = lane; i < len; i += 32)
-                        sts_u8(s_ring + ((dst + i) & RINGB_MASK), lds_u8(s_ring + ((sbase + i % dist) & RINGB_MASK)));
+                const uint32_t lj = __shfl_sync(0xffffffffu, len, j);
+                const uint32_t dj = __shfl_sync(0xffffffffu, dist, j);
+                const uint32_t dstj = opos + __shfl_sync(0xffffffffu, off, j);
+                const uint32_t sj = dstj - dj;
+                if (dj >= lj) {
+                    for (uint32_t i = lane; i < lj; i += 32)
+                        sts_u8(s_ring + ((dstj + i) & RINGB_MASK), lds_u8(s_ring + ((sj + i) & RINGB_MASK)));
+                } else {  // the source repeats with period dist (all of it precedes dst)
+                    for (uint32_t i = lane; i < lj; i += 32)
+                        sts_u8(s_ring + ((dstj + i) & RINGB_MASK), lds_u8(s_ring + ((sj + i % dj) & RINGB_MASK)));
                 }
                 __syncwarp();
             }
-            if (bad) { err = INF_BAD_DISTANCE; break; }
-            opos += total;
+            opos += acc;
         }
         if (status < 0) { err = -status; break; }
         if (status == 1) break;
