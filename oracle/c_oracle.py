@@ -80,7 +80,7 @@ def flatten(intervals: dict):
     return iv, a, names, gene_ids
 
 
-def raw_counts(path, index_path, intervals, gene_intervals, mode, nthreads=1, sample_chunks=0):
+def raw_counts(path, index_path, intervals, gene_intervals, mode, nthreads=1, sample_chunks=0, chunk_lo=-1, chunk_hi=-1):
     iv, keep1, names, gene_ids = flatten(intervals)
     gv, keep2, _, _ = flatten(gene_intervals)
     tot = int(keep1["n_genes"].sum())
@@ -95,7 +95,7 @@ def raw_counts(path, index_path, intervals, gene_intervals, mode, nthreads=1, sa
     err = C.create_string_buffer(512)
     rc = lib().oracle_count_reads(
         path.encode(), index_path.encode() if index_path else None, C.byref(iv), C.byref(gv),
-        C.c_int(mode), C.c_int(nthreads), C.c_int64(sample_chunks),
+        C.c_int(mode), C.c_int(nthreads), C.c_int64(sample_chunks), C.c_int64(chunk_lo), C.c_int64(chunk_hi),
         fwd.ctypes.data_as(C.c_void_p), rev.ctypes.data_as(C.c_void_p),
         wf.ctypes.data_as(C.c_void_p), wr.ctypes.data_as(C.c_void_p),
         scanned.ctypes.data_as(C.c_void_p), C.byref(outside), C.byref(nrec), C.byref(nck), err,
@@ -105,6 +105,11 @@ def raw_counts(path, index_path, intervals, gene_intervals, mode, nthreads=1, sa
     return dict(names=names, gene_ids=gene_ids, fwd=fwd[:tot], rev=rev[:tot], wfwd=wf[:tot],
                 wrev=wr[:tot], scanned=scanned[:len(names)], outside=outside.value,
                 n_records=nrec.value, n_chunks=nck.value)
+
+
+def raw_counts_chunks(path, intervals, gene_intervals, mode, chunk_lo, chunk_hi, nthreads=1):
+    """dense counts over the chunks [chunk_lo, chunk_hi) only -- what one shard of a sharded job owns"""
+    return raw_counts(path, None, intervals, gene_intervals, mode, nthreads=nthreads, chunk_lo=chunk_lo, chunk_hi=chunk_hi)
 
 
 def _assemble_unstranded(r):

@@ -723,9 +723,11 @@ static int open_idx(const char* bam, const char* bai, bamidx_t* idx, char* err, 
 
 /* counters.rs:204-260 / :276-323 without the String maps (assembled by the test helper).
  * sample_chunks > 0: run only every k-th chunk so that about `sample_chunks` chunks run
- * (bench.py's bounded CPU sample); n_records_out reports the records they owned. */
+ * (bench.py's bounded CPU sample); n_records_out reports the records they owned.
+ * chunk_lo >= 0: only chunks [chunk_lo, chunk_hi) of the chunk table (what one shard owns). */
 int oracle_count_reads(const char* bam, const char* bai, const mbfbam_intervals* iv,
                        const mbfbam_intervals* genes, int mode, int nthreads, int64_t sample_chunks,
+                       int64_t chunk_lo, int64_t chunk_hi,
                        uint64_t* fwd, uint64_t* rev, double* wfwd, double* wrev, uint8_t* scanned,
                        uint64_t* outside, uint64_t* n_records_out, int64_t* n_chunks_out, char* err,
                        size_t errlen) {
@@ -756,6 +758,12 @@ int oracle_count_reads(const char* bam, const char* bai, const mbfbam_intervals*
         if (c2 < 0) { snprintf(err, errlen, "contig %s is in gene_intervals but not in intervals", nm); rc = MBFBAM_ERR_ARG; break; }
         cks[i].contig = c2;
         if (scanned) scanned[c2] = 1;
+    }
+    if (!rc && chunk_lo >= 0) { /* only the chunks [chunk_lo, chunk_hi) of the table (one shard) */
+        size_t lo = (size_t)chunk_lo < nck ? (size_t)chunk_lo : nck, hi = (size_t)chunk_hi < nck ? (size_t)chunk_hi : nck;
+        if (hi < lo) hi = lo;
+        memmove(cks, cks + lo, (hi - lo) * sizeof *cks);
+        nck = hi - lo;
     }
     if (!rc) {
         if (sample_chunks > 0 && (size_t)sample_chunks < nck) {
