@@ -986,6 +986,7 @@ __global__ void __launch_bounds__(32) k_inflate_multi(InflateArgs3 a) {
 
 }  // namespace mbf
 #include "inflate_group.cuh"
+#include "inflate_twopass.cuh"
 namespace mbf {
 
 // ---------------------------------------------------------------------------------------------

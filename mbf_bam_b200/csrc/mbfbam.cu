@@ -152,7 +152,7 @@ struct Pipeline {
     WinBufs wb[2];
     DevBuf U[2];
     size_t U_cap = 0;    // data bytes (without prefix/slack)
-    DevBuf d_meta, d_chain, d_carry, d_scratch;
+    DevBuf d_meta, d_chain, d_carry, d_scratch, d_tscratch, d_tok, d_ntok;
     PinnedBuf h_meta_front, h_meta_main;
     int sm_count = 148;
     bool sync_debug = false;
@@ -488,6 +488,26 @@ struct Pipeline {
                 InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
                 k_inflate_batched<<<n_blocks, 32, 0, s_main>>>(ia);
                 launched("k_inflate_batched", s_main);
+                break;
+            }
+            case 2: {
+                // two-pass: SIMT token decode (32 blocks per warp), then one warp per block resolves LZ77
+                const int smem = 32 * LANE_LUT_BYTES;
+                CK(cudaFuncSetAttribute(k_inflate_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                const int per_sm = 4;
+                uint32_t grid = std::min<uint32_t>((n_blocks + 31) / 32, (uint32_t)(sm_count * per_sm));
+                d_tscratch.ensure((size_t)sm_count * per_sm * 32 * sizeof(TokScratch));
+                d_tok.ensure((U_cap + 65536) * 4);
+                d_ntok.ensure((size_t)(cand_cap + 8) * 4);
+                TokenArgs ta{w.c_ptr, b.cpos, b.clen, b.isize, b.uoff, d_tok.as<uint32_t>(), d_ntok.as<uint32_t>(), U_PREFIX,
+                             &dmeta(bi)->n_blocks, &dmeta(bi)->inflate_next, &dmeta(bi)->err, &dmeta(bi)->err_info,
+                             d_tscratch.as<TokScratch>()};
+                k_inflate_tokens<<<grid, 32, smem, s_main>>>(ta);
+                launched("k_inflate_tokens", s_main);
+                ResolveArgs ra{d_tok.as<uint32_t>(), d_ntok.as<uint32_t>(), b.isize, b.uoff, U_PREFIX, U[bi].as<uint8_t>(),
+                               &dmeta(bi)->n_blocks, &dmeta(bi)->err, &dmeta(bi)->err_info};
+                k_lz_resolve<<<n_blocks, 32, 0, s_main>>>(ra);
+                launched("k_lz_resolve", s_main);
                 break;
             }
             case 6: {
