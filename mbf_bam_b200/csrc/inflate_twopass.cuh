@@ -25,12 +25,24 @@ namespace mbf {
 
 constexpr int LL_ROOT2 = 8;
 constexpr int D_ROOT2 = 7;
-constexpr int LANE_LUT_BYTES = ((1 << LL_ROOT2) + (1 << D_ROOT2)) * 4;  // 1536
 
-struct TokScratch {  // global memory, one per decoder lane slot
+// Everything a lane needs while decoding lives in shared memory (1.6 KB per lane): a trip must never
+// wait for HBM/L2 -- with 32 decoders in lock step some lane takes the long-code path in most trips.
+struct LaneTables {
+    uint16_t ll_lut[1 << LL_ROOT2];  // (symbol << 4 | length), LUT_SLOW, LUT_INVALID
+    uint16_t d_lut[1 << D_ROOT2];    // doubles as the code-length code's LUT while a header is parsed
     uint16_t ll_sym[288];
     uint16_t d_sym[32];
     HuffDec ll_hd, d_hd;
+};
+struct TokensShared {
+    LaneTables lane[32];
+    uint32_t lenx[32];   // LEN_BASE << 8 | LEN_EXTRA
+    uint32_t distx[32];  // DIST_BASE << 8 | DIST_EXTRA
+    uint32_t run[16];
+};
+
+struct TokScratch {  // global memory, one per decoder lane slot: code lengths while a header is parsed
     uint8_t lens[320];
     uint32_t hlit, hdist;
 };
@@ -59,14 +71,18 @@ __device__ __forceinline__ void tok_err(const TokenArgs& a, uint32_t code, uint3
 
 __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
     extern __shared__ __align__(16) uint8_t tk_smem[];
-    __shared__ uint32_t run[16];
+    TokensShared& S = *reinterpret_cast<TokensShared*>(tk_smem);
     const int lane = threadIdx.x;
-    uint32_t* const my_ll = (uint32_t*)(tk_smem + lane * LANE_LUT_BYTES);
-    uint32_t* const my_d = my_ll + (1 << LL_ROOT2);
-    const uint32_t s_ll = smem_addr(my_ll);
-    const uint32_t s_d = smem_addr(my_d);
+    LaneTables& T = S.lane[lane];
+    const uint32_t s_ll = smem_addr(T.ll_lut);
+    const uint32_t s_d = smem_addr(T.d_lut);
+    const uint32_t s_lenx = smem_addr(S.lenx);
+    const uint32_t s_distx = smem_addr(S.distx);
     TokScratch* const sc = a.scratch + (size_t)blockIdx.x * 32 + lane;
     const uint32_t n_blocks = *a.n_blocks;
+    S.lenx[lane] = lane < 29 ? ((uint32_t)MBF_TBL(LEN_BASE, lane) << 8) | MBF_TBL(LEN_EXTRA, lane) : 0u;
+    S.distx[lane] = lane < 30 ? ((uint32_t)MBF_TBL(DIST_BASE, lane) << 8) | MBF_TBL(DIST_EXTRA, lane) : 0u;
+    __syncwarp();
 
     BitReader br;
     br.words = nullptr; br.wpos = br.wlimit = 0; br.buf = 0; br.cnt = 0; br.nextw = 0;
@@ -81,37 +97,40 @@ __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
         if (st == T_HUFF) {
             // ------------------------------------------------------------ one symbol
             br.refill();
-            uint32_t e = lds_u32(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOT2) - 1)) << 2));
-            if (e >= K_SPECIAL) {
-                if (e == E_SLOW) e = slow_entry<false>(&sc->ll_hd, sc->ll_sym, br.peek(15), LL_ROOT2);
-                if (e >= K_SPECIAL) err = INF_BAD_SYMBOL;
+            uint32_t e = lds_u16(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOT2) - 1)) << 1));
+            if (e >= LUT_SLOW) {
+                e = e == LUT_SLOW ? slow_decode(&T.ll_hd, T.ll_sym, br.peek(15), LL_ROOT2) : 0u;
+                if (!e) err = INF_BAD_SYMBOL;
             }
-            if (err) {
-            } else if (e < K_LEN) {
+            if (!err) {
                 br.consume(e & 15);
-                tk[ntok++] = (e >> 8) & 0xffu;
-                out_bytes++;
-            } else if (e >= K_EOB) {
-                br.consume(e & 15);
-                st = bfinal ? T_FIN : T_HEADER;
-            } else {
-                const uint32_t cl = e & 15, xb = (e >> 4) & 15;
-                const uint32_t len = ((e >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, cl, xb);
-                br.consume(cl + xb);
-                br.refill();
-                uint32_t d = lds_u32(s_d + (((uint32_t)br.buf & ((1u << D_ROOT2) - 1)) << 2));
-                if (d >= K_SPECIAL) {
-                    if (d == E_SLOW) d = slow_entry<true>(&sc->d_hd, sc->d_sym, br.peek(15), D_ROOT2);
-                    if (d >= K_SPECIAL) err = INF_BAD_DISTANCE;
-                }
-                if (!err) {
-                    const uint32_t dcl = d & 15, dxb = (d >> 4) & 15;
-                    const uint32_t dist = ((d >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, dcl, dxb);
-                    br.consume(dcl + dxb);
-                    if (dist > out_bytes) err = INF_BAD_DISTANCE;
-                    else {
-                        tk[ntok++] = 0x80000000u | (len << 16) | (dist - 1);
-                        out_bytes += len;
+                uint32_t sym = e >> 4;
+                if (sym < 256) {
+                    tk[ntok++] = sym;
+                    out_bytes++;
+                } else if (sym == 256) {
+                    st = bfinal ? T_FIN : T_HEADER;
+                } else if (sym >= 257 + 29) {
+                    err = INF_BAD_SYMBOL;
+                } else {
+                    const uint32_t lx = lds_u32(s_lenx + ((sym - 257) << 2));
+                    const uint32_t len = (lx >> 8) + br.take(lx & 0xff);
+                    br.refill();
+                    uint32_t d = lds_u16(s_d + (((uint32_t)br.buf & ((1u << D_ROOT2) - 1)) << 1));
+                    if (d >= LUT_SLOW) {
+                        d = d == LUT_SLOW ? slow_decode(&T.d_hd, T.d_sym, br.peek(15), D_ROOT2) : 0u;
+                        if (!d) err = INF_BAD_DISTANCE;
+                    }
+                    if (!err && (d >> 4) >= 30) err = INF_BAD_DISTANCE;
+                    if (!err) {
+                        br.consume(d & 15);
+                        const uint32_t dx = lds_u32(s_distx + ((d >> 4) << 2));
+                        const uint32_t dist = (dx >> 8) + br.take(dx & 0xff);
+                        if (dist > out_bytes) err = INF_BAD_DISTANCE;
+                        else {
+                            tk[ntok++] = 0x80000000u | (len << 16) | (dist - 1);
+                            out_bytes += len;
+                        }
                     }
                 }
             }
@@ -119,8 +138,7 @@ __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
         } else if (st == T_CLEN) {
             // ------------------------------------------------------------ one code length (header)
             br.refill();
-            const uint16_t* cl_lut = (const uint16_t*)my_d;  // 16-bit LUT of the code-length code
-            const uint32_t e = cl_lut[br.peek(CL_ROOT)];
+            const uint32_t e = T.d_lut[br.peek(CL_ROOT)];  // LUT of the code-length code
             if (e >= LUT_SLOW) {
                 err = INF_BAD_HEADER;
             } else {
@@ -203,9 +221,9 @@ __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
                         br.refill();
                         cl[MBF_TBL(CL_ORDER, i)] = (uint8_t)br.take(3);
                     }
-                    // the code-length code's 16-bit LUT (128 entries) lives in this lane's d_lut
+                    // the code-length code's LUT (128 entries) lives in this lane's d_lut
                     int rc = (hlit > 286 || hdist > 30) ? (int)INF_BAD_HEADER
-                                                        : build_table(cl, 19, CL_ROOT, (uint16_t*)my_d, sc->d_sym, &sc->d_hd, true);
+                                                        : build_table(cl, 19, CL_ROOT, T.d_lut, T.d_sym, &T.d_hd, true);
                     if (rc) err = rc;
                     sc->hlit = hlit;
                     sc->hdist = hdist;
@@ -227,11 +245,10 @@ __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
             TokScratch* t = a.scratch + (size_t)blockIdx.x * 32 + src;
-            uint32_t* t_ll = (uint32_t*)(tk_smem + src * LANE_LUT_BYTES);
-            uint32_t* t_d = t_ll + (1 << LL_ROOT2);
+            LaneTables& L = S.lane[src];
             const uint32_t hlit = t->hlit, hdist = t->hdist;
-            int rc = build_lut_warp<false>(t->lens, (int)hlit, LL_ROOT2, t_ll, t->ll_sym, &t->ll_hd, run, lane);
-            if (!rc) rc = build_lut_warp<true>(t->lens + hlit, (int)hdist, D_ROOT2, t_d, t->d_sym, &t->d_hd, run, lane);
+            int rc = build_lut16_warp(t->lens, (int)hlit, LL_ROOT2, L.ll_lut, L.ll_sym, &L.ll_hd, S.run, lane);
+            if (!rc) rc = build_lut16_warp(t->lens + hlit, (int)hdist, D_ROOT2, L.d_lut, L.d_sym, &L.d_hd, S.run, lane);
             if (lane == src) {
                 if (rc) {
                     tok_err(a, WERR_INFLATE + (uint32_t)rc, b);

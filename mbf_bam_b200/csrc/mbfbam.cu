@@ -492,7 +492,7 @@ struct Pipeline {
             }
             case 2: {
                 // two-pass: SIMT token decode (32 blocks per warp), then one warp per block resolves LZ77
-                const int smem = 32 * LANE_LUT_BYTES;
+                const int smem = (int)sizeof(TokensShared);
                 CK(cudaFuncSetAttribute(k_inflate_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                 const int per_sm = 4;
                 uint32_t grid = std::min<uint32_t>((n_blocks + 31) / 32, (uint32_t)(sm_count * per_sm));
