@@ -35,8 +35,9 @@ struct LaneTables {
     uint16_t d_sym[32];
     HuffDec ll_hd, d_hd;
 };
+template <int DL>
 struct TokensShared {
-    LaneTables lane[32];
+    LaneTables lane[DL];
     uint32_t lenx[32];   // LEN_BASE << 8 | LEN_EXTRA
     uint32_t distx[32];  // DIST_BASE << 8 | DIST_EXTRA
     uint32_t run[16];
@@ -69,16 +70,20 @@ __device__ __forceinline__ void tok_err(const TokenArgs& a, uint32_t code, uint3
     if (atomicCAS(a.err, 0u, code) == 0u) *a.err_info = info;
 }
 
+// DL = decoders per warp (lanes 0..DL-1 decode; all 32 lanes help with table builds).  Fewer decoders
+// per warp means more warps per SM for the same shared memory: better latency hiding, fewer lanes
+// served per issued instruction.
+template <int DL>
 __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
     extern __shared__ __align__(16) uint8_t tk_smem[];
-    TokensShared& S = *reinterpret_cast<TokensShared*>(tk_smem);
+    TokensShared<DL>& S = *reinterpret_cast<TokensShared<DL>*>(tk_smem);
     const int lane = threadIdx.x;
-    LaneTables& T = S.lane[lane];
+    LaneTables& T = S.lane[lane < DL ? lane : 0];
     const uint32_t s_ll = smem_addr(T.ll_lut);
     const uint32_t s_d = smem_addr(T.d_lut);
     const uint32_t s_lenx = smem_addr(S.lenx);
     const uint32_t s_distx = smem_addr(S.distx);
-    TokScratch* const sc = a.scratch + (size_t)blockIdx.x * 32 + lane;
+    TokScratch* const sc = a.scratch + (size_t)blockIdx.x * DL + (lane < DL ? lane : 0);
     const uint32_t n_blocks = *a.n_blocks;
     S.lenx[lane] = lane < 29 ? ((uint32_t)MBF_TBL(LEN_BASE, lane) << 8) | MBF_TBL(LEN_EXTRA, lane) : 0u;
     S.distx[lane] = lane < 30 ? ((uint32_t)MBF_TBL(DIST_BASE, lane) << 8) | MBF_TBL(DIST_EXTRA, lane) : 0u;
@@ -86,9 +91,9 @@ __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
 
     BitReader br;
     br.words = nullptr; br.wpos = br.wlimit = 0; br.buf = 0; br.cnt = 0; br.nextw = 0;
-    int st = T_IDLE;
+    int st = lane < DL ? T_IDLE : T_DONE;
     uint32_t b = 0, mis = 0, clen_b = 0, isize_b = 0, bfinal = 0, stored_left = 0;
-    uint32_t out_bytes = 0, ntok = 0;
+    uint32_t out_bytes = 0, ntok = 0, prev_len = 0;
     uint32_t* tk = nullptr;
     uint32_t cl_i = 0, cl_n = 0;  // code-length decoding progress
 
@@ -146,11 +151,12 @@ __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
                 const uint32_t s2 = e >> 4;
                 if (s2 < 16) {
                     sc->lens[cl_i++] = (uint8_t)s2;
+                    prev_len = s2;
                 } else {
                     uint32_t rep, val = 0;
                     if (s2 == 16) {
                         if (cl_i == 0) err = INF_BAD_HEADER;
-                        else val = sc->lens[cl_i - 1];
+                        else val = prev_len;
                         rep = 3 + br.take(2);
                     } else if (s2 == 17) {
                         rep = 3 + br.take(3);
@@ -158,13 +164,12 @@ __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
                         rep = 11 + br.take(7);
                     }
                     if (cl_i + rep > cl_n) err = INF_BAD_HEADER;
-                    if (!err)
+                    if (!err) {
                         for (uint32_t k = 0; k < rep; k++) sc->lens[cl_i++] = (uint8_t)val;
+                        prev_len = val;
+                    }
                 }
-                if (!err && cl_i >= cl_n) {
-                    if (sc->lens[256] == 0) err = INF_BAD_HEADER;
-                    st = T_BUILD;
-                }
+                if (!err && cl_i >= cl_n) st = T_BUILD;  // (a missing end-of-block code is caught by the build)
             }
         } else if (st == T_STORED) {
             br.refill();
@@ -244,10 +249,11 @@ __global__ void __launch_bounds__(32) k_inflate_tokens(TokenArgs a) {
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
-            TokScratch* t = a.scratch + (size_t)blockIdx.x * 32 + src;
+            TokScratch* t = a.scratch + (size_t)blockIdx.x * DL + src;
             LaneTables& L = S.lane[src];
             const uint32_t hlit = t->hlit, hdist = t->hdist;
-            int rc = build_lut16_warp(t->lens, (int)hlit, LL_ROOT2, L.ll_lut, L.ll_sym, &L.ll_hd, S.run, lane);
+            int rc = t->lens[256] == 0 ? (int)INF_BAD_HEADER
+                                       : build_lut16_warp(t->lens, (int)hlit, LL_ROOT2, L.ll_lut, L.ll_sym, &L.ll_hd, S.run, lane);
             if (!rc) rc = build_lut16_warp(t->lens + hlit, (int)hdist, D_ROOT2, L.d_lut, L.d_sym, &L.d_hd, S.run, lane);
             if (lane == src) {
                 if (rc) {

@@ -477,7 +477,8 @@ struct Pipeline {
         launched("k_inflate_multi", s_main);
     }
     void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks) {
-        switch (env_u32("MBF_BAM_INFLATE_D", 1)) {
+        const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 1);
+        switch (mode_d) {
             case 0: {
                 InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
                 k_inflate<<<n_blocks, 32, 0, s_main>>>(ia);
@@ -490,19 +491,24 @@ struct Pipeline {
                 launched("k_inflate_batched", s_main);
                 break;
             }
-            case 2: {
-                // two-pass: SIMT token decode (32 blocks per warp), then one warp per block resolves LZ77
-                const int smem = (int)sizeof(TokensShared);
-                CK(cudaFuncSetAttribute(k_inflate_tokens, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                const int per_sm = 4;
-                uint32_t grid = std::min<uint32_t>((n_blocks + 31) / 32, (uint32_t)(sm_count * per_sm));
-                d_tscratch.ensure((size_t)sm_count * per_sm * 32 * sizeof(TokScratch));
+            case 2: case 216: case 208: {
+                // two-pass: SIMT token decode (DL blocks per warp), then one warp per block resolves LZ77
+                const int dl = mode_d == 216 ? 16 : mode_d == 208 ? 8 : 32;
                 d_tok.ensure((U_cap + 65536) * 4);
                 d_ntok.ensure((size_t)(cand_cap + 8) * 4);
+                d_tscratch.ensure((size_t)sm_count * 32 * 32 * sizeof(TokScratch));
                 TokenArgs ta{w.c_ptr, b.cpos, b.clen, b.isize, b.uoff, d_tok.as<uint32_t>(), d_ntok.as<uint32_t>(), U_PREFIX,
                              &dmeta(bi)->n_blocks, &dmeta(bi)->inflate_next, &dmeta(bi)->err, &dmeta(bi)->err_info,
                              d_tscratch.as<TokScratch>()};
-                k_inflate_tokens<<<grid, 32, smem, s_main>>>(ta);
+                auto launch_tokens = [&](auto kernel, int smem) {
+                    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                    const int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
+                    uint32_t grid = std::min<uint32_t>((n_blocks + dl - 1) / dl, (uint32_t)(sm_count * per_sm));
+                    kernel<<<grid, 32, smem, s_main>>>(ta);
+                };
+                if (dl == 32) launch_tokens(k_inflate_tokens<32>, (int)sizeof(TokensShared<32>));
+                else if (dl == 16) launch_tokens(k_inflate_tokens<16>, (int)sizeof(TokensShared<16>));
+                else launch_tokens(k_inflate_tokens<8>, (int)sizeof(TokensShared<8>));
                 launched("k_inflate_tokens", s_main);
                 ResolveArgs ra{d_tok.as<uint32_t>(), d_ntok.as<uint32_t>(), b.isize, b.uoff, U_PREFIX, U[bi].as<uint8_t>(),
                                &dmeta(bi)->n_blocks, &dmeta(bi)->err, &dmeta(bi)->err_info};
