@@ -28,9 +28,11 @@ constexpr uint32_t BATCH_NEAR = RINGB - BATCH_MAX_OUT;  // matches with dist <= 
 constexpr uint32_t K_LIT = 0u, K_LEN = 1u << 30, K_EOB = 2u << 30, K_SPECIAL = 3u << 30;
 constexpr uint32_t E_INVALID = K_SPECIAL | 0xffu, E_SLOW = K_SPECIAL;
 
+constexpr int LL_ROOTB = 9;  // 32-bit entries; literal codes of the BAM streams are <= 7 or >= 10 bits long
+constexpr int D_ROOTB = 8;
 struct BatchShared {
-    uint32_t ll_lut[1 << LL_ROOT];
-    uint32_t d_lut[1 << D_ROOT];
+    uint32_t ll_lut[1 << LL_ROOTB];
+    uint32_t d_lut[1 << D_ROOTB];
     __align__(16) uint8_t ring[RINGB];
     uint32_t q[2 * 32];  // (len << 16 | dist - 1, output offset) per queued match
     uint16_t ll_sym[288];

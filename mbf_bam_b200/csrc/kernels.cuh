@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(32) k_inflate(InflateArgs a) {
 
 // ---------------------------------------------------------------------------------------------
 // K1 (batched form; see inflate_batched.cuh for the design)
-__global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
+__global__ void __launch_bounds__(32, 32) k_inflate_batched(InflateArgs a) {
     __shared__ BatchShared S;
     const uint32_t b = blockIdx.x;
     if (b >= a.meta->n_blocks) return;
@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
                 }
                 while (nm < BQ_MATCHES && acc < BATCH_MAX_OUT) {
                     br.refill();
-                    uint32_t e = lds_u32(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOT) - 1)) << 2));
+                    uint32_t e = lds_u32(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOTB) - 1)) << 2));
                     if (e < K_LEN) {  // literal
                         br.consume(e & 15);
                         sts_u8(s_ring + ((opos + acc) & RINGB_MASK), (e >> 8) & 0xffu);
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
                         continue;
                     }
                     if (e >= K_SPECIAL) {
-                        if (e == E_SLOW) e = slow_entry<false>(&S.ll_hd, S.ll_sym, br.peek(15), LL_ROOT);
+                        if (e == E_SLOW) e = slow_entry<false>(&S.ll_hd, S.ll_sym, br.peek(15), LL_ROOTB);
                         if (e >= K_SPECIAL) { status = -INF_BAD_SYMBOL; break; }
                         if (e < K_LEN) {
                             br.consume(e & 15);
@@ -573,9 +573,9 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
                     const uint32_t len = ((e >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, cl, xb);
                     br.consume(cl + xb);
                     br.refill();
-                    uint32_t d = lds_u32(s_d + (((uint32_t)br.buf & ((1u << D_ROOT) - 1)) << 2));
+                    uint32_t d = lds_u32(s_d + (((uint32_t)br.buf & ((1u << D_ROOTB) - 1)) << 2));
                     if (d >= K_SPECIAL) {
-                        if (d == E_SLOW) d = slow_entry<true>(&S.d_hd, S.d_sym, br.peek(15), D_ROOT);
+                        if (d == E_SLOW) d = slow_entry<true>(&S.d_hd, S.d_sym, br.peek(15), D_ROOTB);
                         if (d >= K_SPECIAL) { status = -INF_BAD_DISTANCE; break; }
                     }
                     const uint32_t dcl = d & 15, dxb = (d >> 4) & 15;
@@ -752,8 +752,8 @@ __global__ void __launch_bounds__(32) k_inflate_batched(InflateArgs a) {
         if (status == 1) break;
         if (status == 2) {
             const uint32_t hlit = S.hlit, hdist = S.hdist;
-            err = build_lut_warp<false>(S.lens, (int)hlit, LL_ROOT, S.ll_lut, S.ll_sym, &S.ll_hd, S.run, lane);
-            if (!err) err = build_lut_warp<true>(S.lens + hlit, (int)hdist, D_ROOT, S.d_lut, S.d_sym, &S.d_hd, S.run, lane);
+            err = build_lut_warp<false>(S.lens, (int)hlit, LL_ROOTB, S.ll_lut, S.ll_sym, &S.ll_hd, S.run, lane);
+            if (!err) err = build_lut_warp<true>(S.lens + hlit, (int)hdist, D_ROOTB, S.d_lut, S.d_sym, &S.d_hd, S.run, lane);
             if (err) break;
         }
     }
