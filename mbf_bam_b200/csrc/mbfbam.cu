@@ -232,8 +232,11 @@ struct Pipeline {
         mode = 0;
         cc = CountCtx{};
         ic = IntronCtx{};
-        set_cap = set_ub = 0;
-        map_cap = map_ub = 0;
+        // the multi-mapper set and the intron map keep their allocation between jobs; only their contents go
+        set_ub = 0;
+        if (set_cap) CK(cudaMemsetAsync(d_set.p, 0, set_cap * 16, s_main));
+        map_ub = 0;
+        if (map_cap) CK(cudaMemsetAsync(d_map.p, 0xff, map_cap * 16, s_main));
         n_genes = n_count_words = 0;
         out_host = nullptr;
         out_cap = out_len = 0;
@@ -578,7 +581,7 @@ struct Pipeline {
         if (set_cap) CK(cudaMemcpy(&live, d_set_size.p, 8, cudaMemcpyDeviceToHost));
         set_ub = live + extra;
         if (set_ub * 2 <= set_cap) return;
-        uint64_t ncap = 1u << 16;
+        uint64_t ncap = 1u << 22;
         while (ncap < set_ub * 4) ncap <<= 1;
         if (ncap > (1ull << 31)) throw Error(MBFBAM_ERR_UNSUPPORTED, "multi-mapper set exceeds 2^31 slots");
         DevBuf nb;
