@@ -710,13 +710,14 @@ struct Pipeline {
             int bi = (int)(k & 1);
             double ta = now_ms();
             finish_main(bi ^ 1);  // second half of window k-1 (must precede window k's carry copy)
+            // everything that touches window k-1's buffers is queued on s_main now: window k+1's front
+            // stage (same buffers) may start behind it, i.e. while window k's main stage is running
+            CK(cudaEventRecord(ev_reuse, s_main));
             double tb = now_ms();
             issue_main(bi);
             double tc = now_ms();
             if (trace) fprintf(stderr, "[mbfbam] win %zu t=%.2f finish_prev %.2f ms, issue_main %.2f ms (scan_len %u)\n", k, ta - t0, tb - ta, tc - tb, wins[k].scan_len);
             if (k + 1 < wins.size()) {
-                // buffers of parity bi^1 are reused: everything of window k-1 is queued on s_main by now
-                CK(cudaEventRecord(ev_reuse, s_main));
                 CK(cudaStreamWaitEvent(s_front, ev_reuse, 0));
                 const Win& wn = wins[k + 1];
                 double td = now_ms();

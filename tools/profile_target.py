@@ -10,7 +10,10 @@ import mbf_bam_b200 as mb  # noqa: E402
 reads = int(os.environ.get("MBF_BENCH_READS", "4000000"))
 path, iv, giv, info, _ = bench.ensure_bam(os.environ.get("MBF_BENCH_DIR", "/tmp/mbf_bench"), reads, 0, 1, lambda: None)
 rd = mb.Reader(path)
-rd.preload()
+if os.environ.get("MBF_PROFILE_RESIDENT", "1") != "0":
+    rd.preload()
+else:
+    rd.count_reads(1, iv, giv)  # warm the pipeline buffers
 f, r = rd.count_reads(1, iv, giv)
 st = rd.stats()
 print("records", st["n_records"], "launches", st["n_kernel_launches"], "fwd", f["_total"], "rev", r["_total"],
