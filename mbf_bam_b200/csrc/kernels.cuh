@@ -766,226 +766,7 @@ __global__ void __launch_bounds__(32, 32) k_inflate_batched(InflateArgs a) {
     if (err && lane == 0) set_err(a.meta, WERR_INFLATE + (uint32_t)err, b);
 }
 
-// ---------------------------------------------------------------------------------------------
-// K1 (multi-decoder form): D lanes of every warp each decode their own BGZF block, pulled from a
-// work queue.  The single-lane kernel above is issue-bound with one useful lane per instruction;
-// here every issued instruction serves up to D decoders.  To keep the lanes of a warp on short,
-// similar paths every loop trip does ONE small unit of work per lane: decode one or two symbols, or
-// copy at most 8 bytes of a pending match, or move 4 stored bytes.  Hot state (both LUTs and a
-// 1 KB output ring) is in shared memory, the rarely used canonical tables are in an L2-resident
-// scratch record per decoder slot.
-constexpr int RING3 = 1024;
-constexpr uint32_t RING3_MASK = RING3 - 1;
-constexpr int DEC_SMEM = (1 << LL_ROOT) * 2 + (1 << D_ROOT) * 2 + RING3;  // 3584 bytes per decoder
-
-struct DecoderScratch {  // global memory, one per decoder slot
-    uint16_t ll_sym[288];
-    uint16_t d_sym[32];
-    HuffDec ll_hd, d_hd;
-    uint8_t lens[320];
-};
-
-struct InflateArgs3 {
-    const uint8_t* cbuf;
-    BlockArrays blk;
-    uint8_t* U;
-    WinMeta* meta;
-    DecoderScratch* scratch;  // gridDim.x * D records
-};
-
-__device__ __forceinline__ uint4 lds_u128(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-
-template <int D>
-__global__ void __launch_bounds__(32) k_inflate_multi(InflateArgs3 a) {
-    extern __shared__ __align__(16) uint8_t dsm[];
-    const int lane = threadIdx.x;
-    if (lane >= D) return;
-    uint8_t* my = dsm + lane * DEC_SMEM;
-    uint16_t* ll_lut = (uint16_t*)my;
-    uint16_t* d_lut = (uint16_t*)(my + (1 << LL_ROOT) * 2);
-    const uint32_t s_ll = smem_addr(ll_lut);
-    const uint32_t s_d = smem_addr(d_lut);
-    const uint32_t s_ring = s_d + (1 << D_ROOT) * 2;
-    DecoderScratch* sc = a.scratch + (size_t)blockIdx.x * D + lane;
-    const uint32_t n_blocks = a.meta->n_blocks;
-    uint8_t* const U = a.U;
-
-    enum { S_IDLE = 0, S_HEADER = 1, S_HUFF = 2, S_STORED = 3 };
-    int st = S_IDLE;
-    BitReader br;
-    uint32_t b = 0, mis = 0, bfinal = 0, stored_left = 0;
-    uint32_t opos = 0, ostart = 0, oend = 0, flushed = 0;
-    uint32_t cp_left = 0, cp_dist = 0;
-    int err = 0;
-
-    for (;;) {
-        if (st == S_HUFF) {
-            if (cp_left) {
-                // ---- continue a match: at most 8 bytes per trip
-                uint32_t n = min(cp_left, 8u);
-                if (cp_dist == 1) {
-                    const uint32_t v = lds_u8(s_ring + ((opos - 1) & RING3_MASK));
-                    for (uint32_t i = 0; i < n; i++) sts_u8(s_ring + ((opos + i) & RING3_MASK), v);
-                } else {
-                    n = min(n, cp_dist);
-                    const uint32_t src = opos - cp_dist;
-                    uint32_t v[8];
-                    if (cp_dist <= (uint32_t)RING3) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) v[i] = (uint32_t)i < n ? lds_u8(s_ring + ((src + i) & RING3_MASK)) : 0u;
-                    } else {
-                        const uint8_t* sp = U + src;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) v[i] = (uint32_t)i < n ? (uint32_t)__ldcg(sp + i) : 0u;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        if ((uint32_t)i < n) sts_u8(s_ring + ((opos + i) & RING3_MASK), v[i]);
-                }
-                opos += n;
-                cp_left -= n;
-            } else {
-                // ---- decode one symbol (two when both are literals)
-                br.refill();
-                uint32_t e = lds_u16(s_ll + (br.peek(LL_ROOT) << 1));
-                bool lit = e < 0x1000u;
-                if (lit) {
-                    br.consume(e & 15);
-                    sts_u8(s_ring + (opos & RING3_MASK), e >> 4);
-                    opos++;
-                    e = lds_u16(s_ll + (br.peek(LL_ROOT) << 1));
-                    lit = e < 0x1000u;
-                    if (lit) {
-                        br.consume(e & 15);
-                        sts_u8(s_ring + (opos & RING3_MASK), e >> 4);
-                        opos++;
-                    } else {
-                        br.refill();
-                    }
-                }
-                if (!lit) {
-                    if (e >= LUT_SLOW) {
-                        e = e == LUT_SLOW ? slow_decode(&sc->ll_hd, sc->ll_sym, br.peek(15), LL_ROOT) : 0u;
-                        if (!e) err = INF_BAD_SYMBOL;
-                    }
-                    if (!err) {
-                        br.consume(e & 15);
-                        uint32_t sym = e >> 4;
-                        if (sym < 256) {
-                            sts_u8(s_ring + (opos & RING3_MASK), sym);
-                            opos++;
-                        } else if (sym == 256) {
-                            st = S_HEADER;
-                        } else {
-                            sym -= 257;
-                            if (sym >= 29) {
-                                err = INF_BAD_SYMBOL;
-                            } else {
-                                const uint32_t len = MBF_TBL(LEN_BASE, sym) + br.take(MBF_TBL(LEN_EXTRA, sym));
-                                br.refill();
-                                e = lds_u16(s_d + (br.peek(D_ROOT) << 1));
-                                if (e >= LUT_SLOW) e = e == LUT_SLOW ? slow_decode(&sc->d_hd, sc->d_sym, br.peek(15), D_ROOT) : 0u;
-                                const uint32_t ds = e >> 4;
-                                if (!e || ds >= 30) {
-                                    err = INF_BAD_DISTANCE;
-                                } else {
-                                    br.consume(e & 15);
-                                    const uint32_t dist = MBF_TBL(DIST_BASE, ds) + br.take(MBF_TBL(DIST_EXTRA, ds));
-                                    if (dist > opos - ostart) err = INF_BAD_DISTANCE;
-                                    else { cp_left = len; cp_dist = dist; }
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        } else if (st == S_STORED) {
-            uint32_t n = min(stored_left, 4u);
-            for (uint32_t i = 0; i < n; i++) {
-                br.refill();
-                sts_u8(s_ring + ((opos + i) & RING3_MASK), br.take(8));
-            }
-            opos += n;
-            stored_left -= n;
-            if (!stored_left) st = S_HEADER;
-        } else if (st == S_HEADER) {
-            if (bfinal) {
-                // member complete: flush the tail, verify sizes, release the slot
-                for (uint32_t i = flushed; i < min(opos, oend); i++) U[i] = (uint8_t)lds_u8(s_ring + (i & RING3_MASK));
-                if (opos != oend) err = INF_SIZE_MISMATCH;
-                else if (br.bytes_consumed(mis) > a.blk.clen[b]) err = INF_INPUT_OVERRUN;
-                st = S_IDLE;
-            } else {
-                br.refill();
-                bfinal = br.take(1);
-                const uint32_t btype = br.take(2);
-                if (btype == 0) {
-                    br.consume(br.cnt & 7);
-                    br.refill();
-                    const uint32_t len = br.take(16);
-                    br.refill();
-                    const uint32_t nlen = br.take(16);
-                    if ((len ^ 0xffffu) != nlen) err = INF_BAD_STORED;
-                    stored_left = len;
-                    st = len ? S_STORED : S_HEADER;
-                } else if (btype == 1 || btype == 2) {
-                    if (btype == 1) {
-                        for (int i = 0; i < 144; i++) sc->lens[i] = 8;
-                        for (int i = 144; i < 256; i++) sc->lens[i] = 9;
-                        for (int i = 256; i < 280; i++) sc->lens[i] = 7;
-                        for (int i = 280; i < 288; i++) sc->lens[i] = 8;
-                        for (int i = 0; i < 32; i++) sc->lens[288 + i] = 5;
-                        err = build_table(sc->lens, 288, LL_ROOT, ll_lut, sc->ll_sym, &sc->ll_hd, false);
-                        if (!err) err = build_table(sc->lens + 288, 32, D_ROOT, d_lut, sc->d_sym, &sc->d_hd, false);
-                    } else {
-                        err = build_dynamic_parts(br, sc->lens, ll_lut, sc->ll_sym, &sc->ll_hd, d_lut, sc->d_sym, &sc->d_hd);
-                    }
-                    st = S_HUFF;
-                } else {
-                    err = INF_BAD_BTYPE;
-                }
-            }
-        } else {  // S_IDLE: next block from the queue
-            b = atomicAdd(&a.meta->inflate_next, 1u);
-            if (b >= n_blocks) break;
-            const uint8_t* p = a.cbuf + a.blk.cpos[b];
-            mis = (uint32_t)((uintptr_t)p & 3);
-            br.init(p, a.blk.clen[b]);
-            opos = ostart = flushed = a.blk.uoff[b];
-            oend = ostart + a.blk.isize[b];
-            bfinal = 0;
-            cp_left = 0;
-            st = S_HEADER;
-        }
-        if (err) {
-            set_err(a.meta, WERR_INFLATE + (uint32_t)err, b);
-            err = 0;
-            st = S_IDLE;
-            continue;
-        }
-        if (opos > oend) {  // more output than ISIZE promised
-            set_err(a.meta, WERR_INFLATE + (uint32_t)INF_OUTPUT_OVERRUN, b);
-            st = S_IDLE;
-            continue;
-        }
-        // ---- drain the ring in 16-byte stores once half of it is pending
-        if (opos - flushed >= (uint32_t)RING3 / 2) {
-            uint32_t i = flushed;
-            const uint32_t head_end = min(opos, (i + 15u) & ~15u);
-            for (; i < head_end; i++) U[i] = (uint8_t)lds_u8(s_ring + (i & RING3_MASK));
-            const uint32_t body_end = opos & ~15u;
-            for (; i + 16 <= body_end; i += 16) *(uint4*)(U + i) = lds_u128(s_ring + (i & RING3_MASK));
-            flushed = i;
-        }
-    }
-}
-
 }  // namespace mbf
-#include "inflate_group.cuh"
 #include "inflate_twopass.cuh"
 namespace mbf {
 

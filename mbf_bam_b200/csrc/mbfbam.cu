@@ -152,7 +152,7 @@ struct Pipeline {
     WinBufs wb[2];
     DevBuf U[2];
     size_t U_cap = 0;    // data bytes (without prefix/slack)
-    DevBuf d_meta, d_chain, d_carry, d_scratch, d_tscratch, d_tok, d_ntok;
+    DevBuf d_meta, d_chain, d_carry, d_tscratch, d_tok, d_ntok;
     PinnedBuf h_meta_front, h_meta_main;
     int sm_count = 148;
     bool sync_debug = false;
@@ -466,19 +466,8 @@ struct Pipeline {
         w.timed = true;
     }
 
-    // K1: multi-decoder kernel (D lanes per warp, MBF_BAM_INFLATE_D = 4/8/16/32) or, with D = 0, the
-    // one-block-per-warp kernel
-    template <int D>
-    void launch_multi(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks) {
-        const int smem = D * DEC_SMEM;
-        CK(cudaFuncSetAttribute(k_inflate_multi<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
-        uint32_t grid = std::min<uint32_t>((n_blocks + D - 1) / D, (uint32_t)(sm_count * per_sm));
-        d_scratch.ensure((size_t)sm_count * 32 * 32 * sizeof(DecoderScratch));
-        InflateArgs3 ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi), d_scratch.as<DecoderScratch>()};
-        k_inflate_multi<D><<<grid, 32, smem, s_main>>>(ia);
-        launched("k_inflate_multi", s_main);
-    }
+    // K1 selection (MBF_BAM_INFLATE_D): 1 = batched warp-per-block kernel (production), 0 = single-lane
+    // reference kernel, 2 / 216 / 208 = two-pass kernels with 32 / 16 / 8 decoders per warp
     void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks) {
         const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 1);
         switch (mode_d) {
@@ -519,21 +508,8 @@ struct Pipeline {
                 launched("k_lz_resolve", s_main);
                 break;
             }
-            case 6: {
-                const int smem = (int)sizeof(Group6Shared);
-                CK(cudaFuncSetAttribute(k_inflate_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                int per_sm = std::max(1, (227 * 1024) / (smem + 1024));
-                uint32_t grid = std::min<uint32_t>((n_blocks + G6 - 1) / G6, (uint32_t)(sm_count * per_sm));
-                InflateArgs6 ia{w.c_ptr, b.cpos, b.clen, b.isize, b.uoff, U[bi].as<uint8_t>(), &dmeta(bi)->n_blocks,
-                                &dmeta(bi)->inflate_next, &dmeta(bi)->err, &dmeta(bi)->err_info};
-                k_inflate_group<<<grid, 32, smem, s_main>>>(ia);
-                launched("k_inflate_group", s_main);
-                break;
-            }
-            case 4: launch_multi<4>(w, b, bi, n_blocks); break;
-            case 16: launch_multi<16>(w, b, bi, n_blocks); break;
-            case 32: launch_multi<32>(w, b, bi, n_blocks); break;
-            default: launch_multi<8>(w, b, bi, n_blocks); break;
+            default:
+                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 0, 1, 2, 216 or 208");
         }
     }
 

@@ -219,3 +219,35 @@ def test_preloaded_file_gives_same_result(mb, tmp_path):
     assert rd.stats()["h2d_bytes"] == 0
     rd.drop_preload()
     assert a == b == c_oracle.count_reads_stranded(path, None, iv, giv)
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE.json configs
+@pytest.mark.parametrize("cfg,reads", [("cfg1", 1_000_000), ("cfg2", 1_500_000), ("cfg3", 1_500_000), ("cfg4", 1_000_000)],
+                         ids=["cfg1_unstranded_1M", "cfg2_stranded", "cfg3_weighted_introns", "cfg4_paired"])
+def test_baseline_config_shapes(mb, tmp_path, cfg, reads):
+    """The BASELINE.json config shapes (tools/bamgen, reduced read counts except config 1 which runs at
+    its full 1M reads): every entry point against the multi-threaded C oracle."""
+    from mbf_bam_b200.synth import model
+
+    path = str(tmp_path / (cfg + ".bam"))
+    iv, giv, info = model.build_config(cfg, path, reads=reads, threads=os.cpu_count() or 4)
+    assert abs(info["records"] - reads) <= 2
+    nt = min(16, os.cpu_count() or 4)
+    got_u = mb.count_reads_unstranded(path, None, iv, giv)
+    assert mb.last_stats()["n_records"] == info["records"]
+    assert got_u == c_oracle.count_reads_unstranded(path, None, iv, giv, nthreads=nt)
+    assert mb.count_reads_stranded(path, None, iv, giv) == c_oracle.count_reads_stranded(path, None, iv, giv, nthreads=nt)
+    assert_weighted_close(mb.count_reads_weighted(path, None, iv, giv), c_oracle.count_reads_weighted(path, None, iv, giv, nthreads=nt))
+    assert mb.count_introns(path) == c_oracle.count_introns(path, nthreads=nt)
+    assert got_u["_total"] > 0 and got_u["_outside"] > 0
+
+
+def test_alternate_inflate_kernels_agree(mb, tmp_path, monkeypatch):
+    """The single-lane and the two-pass inflate kernels (MBF_BAM_INFLATE_D) must give the same bytes as the
+    production kernel and zlib."""
+    path, *_ = make_case(tmp_path, 17, n_reads=30_000, random_seq=True)
+    data = open(path, "rb").read()
+    want = b"".join(p for _, _, p in bamio.iter_bgzf_blocks(data))
+    for d in ("0", "1", "2", "208"):
+        monkeypatch.setenv("MBF_BAM_INFLATE_D", d)
+        assert mb.inflate_buffer(data) == want, d
