@@ -231,7 +231,7 @@ def test_baseline_config_shapes(mb, tmp_path, cfg, reads):
 
     path = str(tmp_path / (cfg + ".bam"))
     iv, giv, info = model.build_config(cfg, path, reads=reads, threads=os.cpu_count() or 4)
-    assert abs(info["records"] - reads) <= 2
+    assert abs(info["records"] - reads) <= 16  # multi-mapper groups are emitted whole
     nt = min(16, os.cpu_count() or 4)
     got_u = mb.count_reads_unstranded(path, None, iv, giv)
     assert mb.last_stats()["n_records"] == info["records"]
