@@ -131,8 +131,9 @@ struct WinBufs {
     const uint8_t* c_ptr = nullptr;  // device pointer of this window's bytes (d_c or a view of the preload)
     uint64_t win_off = 0;
     uint32_t scan_len = 0, avail = 0;
-    cudaEvent_t ev_front = nullptr, ev_main = nullptr;
-    cudaEvent_t t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_front = nullptr, ev_main = nullptr, ev_inf = nullptr;
+    cudaEvent_t t[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    WinMeta front_meta{};
     bool timed = false;
     bool in_flight = false;
     int range_start = 0;
@@ -147,7 +148,7 @@ struct Pipeline {
     mbfbam_stats st{};
     uint32_t W;          // window size in compressed bytes
     uint32_t cand_cap;
-    cudaStream_t s_front = nullptr, s_main = nullptr;
+    cudaStream_t s_front = nullptr, s_main = nullptr, s_inf[2] = {nullptr, nullptr};
     cudaEvent_t ev_reuse = nullptr;
     WinBufs wb[2];
     DevBuf U[2];
@@ -186,6 +187,8 @@ struct Pipeline {
         CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         CK(cudaStreamCreateWithFlags(&s_front, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s_main, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s_inf[0], cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s_inf[1], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ev_reuse, cudaEventDisableTiming));
         d_meta.ensure(2 * sizeof(WinMeta));
         d_chain.ensure(sizeof(ChainState));
@@ -196,6 +199,7 @@ struct Pipeline {
             WinBufs& w = wb[i];
             CK(cudaEventCreateWithFlags(&w.ev_front, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&w.ev_main, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&w.ev_inf, cudaEventDisableTiming));
             for (auto& t : w.t) CK(cudaEventCreate(&t));
         }
     }
@@ -248,9 +252,11 @@ struct Pipeline {
         for (auto& w : wb) {
             if (w.ev_front) cudaEventDestroy(w.ev_front);
             if (w.ev_main) cudaEventDestroy(w.ev_main);
+            if (w.ev_inf) cudaEventDestroy(w.ev_inf);
             for (auto& t : w.t) if (t) cudaEventDestroy(t);
         }
         if (ev_reuse) cudaEventDestroy(ev_reuse);
+        for (auto& x : s_inf) if (x) cudaStreamDestroy(x);
         if (s_front) cudaStreamDestroy(s_front);
         if (s_main) cudaStreamDestroy(s_main);
     }
@@ -272,6 +278,8 @@ struct Pipeline {
         if (data_bytes <= U_cap) return;
         size_t cap = std::max(data_bytes, U_cap * 2);
         if ((uint64_t)cap + U_PREFIX + 65536 > 0xffff0000ull) throw Error(MBFBAM_ERR_UNSUPPORTED, "window inflates past 4 GiB; lower MBF_BAM_WINDOW_MB");
+        CK(cudaStreamSynchronize(s_inf[0]));
+        CK(cudaStreamSynchronize(s_inf[1]));
         CK(cudaStreamSynchronize(s_main));
         for (int i = 0; i < 2; i++) {
             DevBuf nb;
@@ -416,20 +424,38 @@ struct Pipeline {
     }
 
     // ---------------------------------------------------------------- main stage
-    void issue_main(int bi) {
+    // K1 of window k runs on its own stream (two alternate) so that it can start while the tail of window
+    // k-1's K1 is still draining: a BGZF block takes milliseconds, and with one launch at a time the last
+    // partial wave of every window would leave most SMs idle.
+    void issue_inflate(int bi) {
         WinBufs& w = wb[bi];
         CK(cudaEventSynchronize(w.ev_front));
         WinMeta m = h_meta_front.as<WinMeta>()[bi];
         if (m.err) throw Error(MBFBAM_ERR_FORMAT, err_text(m));
+        w.front_meta = m;
         ensure_U((size_t)m.u_total + 1024, bi);
         st.n_bgzf_blocks += m.n_blocks;
         st.uncompressed_bytes += m.u_total;
         st.n_windows++;
-        CK(cudaStreamWaitEvent(s_main, w.ev_front, 0));
+        const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 1);
+        cudaStream_t si = (mode_d == 0 || mode_d == 1) ? s_inf[bi] : s_inf[0];  // the two-pass kernels share one token buffer
+        CK(cudaStreamWaitEvent(si, w.ev_front, 0));
+        // U[bi] was last read by window k-2 (main stage + its second half); ev_reuse was recorded behind both
+        // in the previous iteration of run()
+        CK(cudaStreamWaitEvent(si, ev_reuse, 0));
         BlockArrays b{w.cpos.as<uint32_t>(), w.clen.as<uint32_t>(), w.isize.as<uint32_t>(), w.uoff.as<uint32_t>()};
-        CK(cudaEventRecord(w.t[2], s_main));
-        if (m.n_blocks) launch_inflate(w, b, bi, m.n_blocks);
-        CK(cudaEventRecord(w.t[3], s_main));
+        CK(cudaEventRecord(w.t[2], si));
+        if (m.n_blocks) launch_inflate(w, b, bi, m.n_blocks, si);
+        CK(cudaEventRecord(w.t[3], si));
+        CK(cudaEventRecord(w.ev_inf, si));
+    }
+
+    void issue_main(int bi) {
+        WinBufs& w = wb[bi];
+        const WinMeta m = w.front_meta;
+        CK(cudaStreamWaitEvent(s_main, w.ev_inf, 0));
+        BlockArrays b{w.cpos.as<uint32_t>(), w.clen.as<uint32_t>(), w.isize.as<uint32_t>(), w.uoff.as<uint32_t>()};
+        CK(cudaEventRecord(w.t[6], s_main));
         if (kind == JOB_INFLATE) {
             if (out_host) {
                 if (out_len + m.u_total > out_cap) throw Error(MBFBAM_ERR_ARG, "output buffer too small");
@@ -468,19 +494,19 @@ struct Pipeline {
 
     // K1 selection (MBF_BAM_INFLATE_D): 1 = batched warp-per-block kernel (production), 0 = single-lane
     // reference kernel, 2 / 216 / 208 = two-pass kernels with 32 / 16 / 8 decoders per warp
-    void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks) {
+    void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks, cudaStream_t si) {
         const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 1);
         switch (mode_d) {
             case 0: {
                 InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
-                k_inflate<<<n_blocks, 32, 0, s_main>>>(ia);
-                launched("k_inflate", s_main);
+                k_inflate<<<n_blocks, 32, 0, si>>>(ia);
+                launched("k_inflate", si);
                 break;
             }
             case 1: {
                 InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
-                k_inflate_batched<<<n_blocks, 32, 0, s_main>>>(ia);
-                launched("k_inflate_batched", s_main);
+                k_inflate_batched<<<n_blocks, 32, 0, si>>>(ia);
+                launched("k_inflate_batched", si);
                 break;
             }
             case 2: case 216: case 208: {
@@ -496,16 +522,16 @@ struct Pipeline {
                     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                     const int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
                     uint32_t grid = std::min<uint32_t>((n_blocks + dl - 1) / dl, (uint32_t)(sm_count * per_sm));
-                    kernel<<<grid, 32, smem, s_main>>>(ta);
+                    kernel<<<grid, 32, smem, si>>>(ta);
                 };
                 if (dl == 32) launch_tokens(k_inflate_tokens<32>, (int)sizeof(TokensShared<32>));
                 else if (dl == 16) launch_tokens(k_inflate_tokens<16>, (int)sizeof(TokensShared<16>));
                 else launch_tokens(k_inflate_tokens<8>, (int)sizeof(TokensShared<8>));
-                launched("k_inflate_tokens", s_main);
+                launched("k_inflate_tokens", si);
                 ResolveArgs ra{d_tok.as<uint32_t>(), d_ntok.as<uint32_t>(), b.isize, b.uoff, U_PREFIX, U[bi].as<uint8_t>(),
                                &dmeta(bi)->n_blocks, &dmeta(bi)->err, &dmeta(bi)->err_info};
-                k_lz_resolve<<<n_blocks, 32, 0, s_main>>>(ra);
-                launched("k_lz_resolve", s_main);
+                k_lz_resolve<<<n_blocks, 32, 0, si>>>(ra);
+                launched("k_lz_resolve", si);
                 break;
             }
             default:
@@ -652,7 +678,7 @@ struct Pipeline {
             float ms = 0;
             cudaEventElapsedTime(&ms, w.t[0], w.t[1]); st.ms_gpu_scan += ms;
             cudaEventElapsedTime(&ms, w.t[2], w.t[3]); st.ms_gpu_inflate += ms;
-            cudaEventElapsedTime(&ms, w.t[3], w.t[4]); st.ms_gpu_frame += ms;
+            cudaEventElapsedTime(&ms, w.t[6], w.t[4]); st.ms_gpu_frame += ms;
             cudaEventElapsedTime(&ms, w.t[4], w.t[5]); st.ms_gpu_count += ms;
             w.timed = false;
         }
@@ -685,6 +711,7 @@ struct Pipeline {
         for (size_t k = 0; k < wins.size(); k++) {
             int bi = (int)(k & 1);
             double ta = now_ms();
+            issue_inflate(bi);    // may overlap the tail of window k-1's K1
             finish_main(bi ^ 1);  // second half of window k-1 (must precede window k's carry copy)
             // everything that touches window k-1's buffers is queued on s_main now: window k+1's front
             // stage (same buffers) may start behind it, i.e. while window k's main stage is running
@@ -703,6 +730,8 @@ struct Pipeline {
         }
         finish_main(0);
         finish_main(1);
+        CK(cudaStreamSynchronize(s_inf[0]));
+        CK(cudaStreamSynchronize(s_inf[1]));
         CK(cudaStreamSynchronize(s_main));
         CK(cudaStreamSynchronize(s_front));
         st.ms_gpu_all = now_ms() - t0;
