@@ -185,10 +185,14 @@ struct Pipeline {
         if (dev < 0 || dev >= n) throw Error(MBFBAM_ERR_ARG, fmt("device %d out of range (have %d)", dev, n));
         CK(cudaSetDevice(dev));
         CK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        CK(cudaStreamCreateWithFlags(&s_front, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&s_main, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&s_inf[0], cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&s_inf[1], cudaStreamNonBlocking));
+        // K1 launches thousands of CTAs that each live for milliseconds; the short kernels of the other
+        // stages must not queue behind them, so their streams get the higher priority
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&s_front, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithPriority(&s_main, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithPriority(&s_inf[0], cudaStreamNonBlocking, prio_lo));
+        CK(cudaStreamCreateWithPriority(&s_inf[1], cudaStreamNonBlocking, prio_lo));
         CK(cudaEventCreateWithFlags(&ev_reuse, cudaEventDisableTiming));
         d_meta.ensure(2 * sizeof(WinMeta));
         d_chain.ensure(sizeof(ChainState));
