@@ -297,9 +297,12 @@ struct Pipeline {
     }
 
     // ---------------------------------------------------------------- front stage
-    void issue_front(int bi, uint64_t win_off, uint32_t scan_len, uint64_t src_end, int range_start,
+    // front stage, first half: bytes of the window into HBM.  Only the compressed-byte buffers of this
+    // parity are touched, so this may start as soon as K1 of window k-2 (their last reader) is done.
+    void stage_front(int bi, uint64_t win_off, uint32_t scan_len, uint64_t src_end, int range_start,
                      uint64_t range_off, uint32_t first_uoff) {
         WinBufs& w = wb[bi];
+        CK(cudaStreamWaitEvent(s_front, w.ev_inf, 0));
         uint64_t want = (uint64_t)scan_len + 65536 + 64;
         uint64_t avail = std::min<uint64_t>(want, src_end - win_off);
         w.win_off = win_off;
@@ -319,6 +322,19 @@ struct Pipeline {
             w.c_ptr = w.d_c.as<uint8_t>();
         }
         st.compressed_bytes += scan_len;
+    }
+
+    // front stage, second half: K0 + block table + WinMeta.  Writes the per-window arrays that window k-2's
+    // main stage may still be reading, hence the wait for ev_reuse.
+    void scan_front(int bi) {
+        WinBufs& w = wb[bi];
+        const uint64_t win_off = w.win_off;
+        const uint32_t scan_len = w.scan_len;
+        const uint64_t avail = w.avail;
+        const int range_start = w.range_start;
+        const uint64_t range_off = w.range_off;
+        const uint32_t first_uoff = w.first_uoff;
+        CK(cudaStreamWaitEvent(s_front, ev_reuse, 0));
         CK(cudaEventRecord(w.t[0], s_front));
         k_win_begin<<<1, 1, 0, s_front>>>(d_chain.as<ChainState>(), dmeta(bi), range_start, range_off, first_uoff);
         launched("k_win_begin", s_front);
@@ -709,28 +725,30 @@ struct Pipeline {
         double t0 = now_ms();
         if (!wins.empty()) {
             const Win& w0 = wins[0];
-            issue_front(0, w0.off, w0.scan_len, w0.src_end, w0.range_start, w0.range_off, w0.first_uoff);
+            stage_front(0, w0.off, w0.scan_len, w0.src_end, w0.range_start, w0.range_off, w0.first_uoff);
+            scan_front(0);
         }
         const bool trace = env_u32("MBF_BAM_TRACE", 0) != 0;
         for (size_t k = 0; k < wins.size(); k++) {
             int bi = (int)(k & 1);
             double ta = now_ms();
-            issue_inflate(bi);    // may overlap the tail of window k-1's K1
-            finish_main(bi ^ 1);  // second half of window k-1 (must precede window k's carry copy)
-            // everything that touches window k-1's buffers is queued on s_main now: window k+1's front
-            // stage (same buffers) may start behind it, i.e. while window k's main stage is running
-            CK(cudaEventRecord(ev_reuse, s_main));
+            issue_inflate(bi);    // waits for window k's block table; may overlap the tail of window k-1's K1
             double tb = now_ms();
-            issue_main(bi);
-            double tc = now_ms();
-            if (trace) fprintf(stderr, "[mbfbam] win %zu t=%.2f finish_prev %.2f ms, issue_main %.2f ms (scan_len %u)\n", k, ta - t0, tb - ta, tc - tb, wins[k].scan_len);
             if (k + 1 < wins.size()) {
-                CK(cudaStreamWaitEvent(s_front, ev_reuse, 0));
+                // bytes of window k+1 (host read + H2D) while the GPU works on windows k-1 / k
                 const Win& wn = wins[k + 1];
-                double td = now_ms();
-                issue_front(bi ^ 1, wn.off, wn.scan_len, wn.src_end, wn.range_start, wn.range_off, wn.first_uoff);
-                if (trace) fprintf(stderr, "[mbfbam] win %zu issue_front(next) %.2f ms\n", k, now_ms() - td);
+                stage_front(bi ^ 1, wn.off, wn.scan_len, wn.src_end, wn.range_start, wn.range_off, wn.first_uoff);
             }
+            double tc = now_ms();
+            finish_main(bi ^ 1);  // second half of window k-1 (must precede window k's carry copy)
+            // everything that touches window k-1's per-window arrays is queued on s_main now
+            CK(cudaEventRecord(ev_reuse, s_main));
+            double td = now_ms();
+            issue_main(bi);
+            if (k + 1 < wins.size()) scan_front(bi ^ 1);
+            if (trace)
+                fprintf(stderr, "[mbfbam] win %zu t=%.2f issue_inflate %.2f ms, stage_next %.2f ms, finish_prev %.2f ms, rest %.2f ms (scan_len %u)\n",
+                        k, ta - t0, tb - ta, tc - tb, td - tc, now_ms() - td, wins[k].scan_len);
         }
         finish_main(0);
         finish_main(1);
