@@ -135,6 +135,15 @@ struct BitReader {
     MBF_HD uint32_t peek(int n) const { return (uint32_t)buf & ((1u << n) - 1); }
     MBF_HD void consume(int n) { buf >>= n; cnt -= n; }
     MBF_HD uint32_t take(int n) { uint32_t v = peek(n); consume(n); return v; }
+    // position of the next unread bit, counted from bit 0 of words[0]
+    MBF_HD uint32_t bit_position() const { return (wpos - 1) * 32 - cnt; }
+    MBF_HD void seek(uint32_t bitpos) {
+        const uint32_t i = bitpos >> 5, sh = bitpos & 31;
+        buf = (uint64_t)load(i) >> sh;
+        cnt = 32 - sh;
+        nextw = load(i + 1);
+        wpos = i + 2;
+    }
     // bytes of payload consumed so far (rounded up to whole bytes), given the initial misalignment
     MBF_HD uint32_t bytes_consumed(uint32_t mis) const {
         uint64_t bits = (uint64_t)(wpos - 1) * 32 - cnt - 8ull * mis;
