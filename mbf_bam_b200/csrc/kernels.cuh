@@ -545,66 +545,53 @@ __global__ void __launch_bounds__(32, 32) k_inflate_batched(InflateArgs a) {
                     acc = held >> 16;
                     held = 0;
                 }
-                // Hot loop with a BIT POINTER instead of a shifting 64-bit buffer: every symbol fetches its own
-                // 32-bit window (two L1-resident words + one funnel shift), consuming bits is one add, and
-                // there is no refill branch.  (Words just past the member are readable slack of the window.)
-                const uint32_t* const words = br.words;
-                uint32_t bp = br.bit_position();
-                uint32_t wp = opos + acc;
-                const uint32_t wlim = opos + BATCH_MAX_OUT;
-                const uint32_t wmax = br.wlimit;  // a corrupt stream must not walk the pointer out of the window buffer
-                while (wp < wlim) {
-                    uint32_t wi = min(bp >> 5, wmax);
-                    uint32_t win = __funnelshift_r(__ldg(words + wi), __ldg(words + wi + 1), bp & 31);
-                    uint32_t e = lds_u32(s_ll + ((win & ((1u << LL_ROOTB) - 1)) << 2));
+                while (nm < BQ_MATCHES && acc < BATCH_MAX_OUT) {
+                    br.refill();
+                    uint32_t e = lds_u32(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOTB) - 1)) << 2));
                     if (e < K_LEN) {  // literal
-                        bp += e & 15;
-                        sts_u8(s_ring + (wp & RINGB_MASK), (e >> 8) & 0xffu);
-                        wp++;
+                        br.consume(e & 15);
+                        sts_u8(s_ring + ((opos + acc) & RINGB_MASK), (e >> 8) & 0xffu);
+                        acc++;
                         continue;
                     }
                     if (e >= K_SPECIAL) {
-                        if (e == E_SLOW) e = slow_entry<false>(&S.ll_hd, S.ll_sym, win & 0x7fffu, LL_ROOTB);
+                        if (e == E_SLOW) e = slow_entry<false>(&S.ll_hd, S.ll_sym, br.peek(15), LL_ROOTB);
                         if (e >= K_SPECIAL) { status = -INF_BAD_SYMBOL; break; }
                         if (e < K_LEN) {
-                            bp += e & 15;
-                            sts_u8(s_ring + (wp & RINGB_MASK), (e >> 8) & 0xffu);
-                            wp++;
+                            br.consume(e & 15);
+                            sts_u8(s_ring + ((opos + acc) & RINGB_MASK), (e >> 8) & 0xffu);
+                            acc++;
                             continue;
                         }
                     }
                     if (e >= K_EOB) {  // end of this deflate block
-                        bp += e & 15;
+                        br.consume(e & 15);
                         st = 0;
                         break;
                     }
                     const uint32_t cl = e & 15, xb = (e >> 4) & 15;
-                    const uint32_t len = ((e >> 8) & 0xffffu) + bfe_u32(win, cl, xb);
-                    bp += cl + xb;
-                    wi = min(bp >> 5, wmax);
-                    win = __funnelshift_r(__ldg(words + wi), __ldg(words + wi + 1), bp & 31);
-                    uint32_t d = lds_u32(s_d + ((win & ((1u << D_ROOTB) - 1)) << 2));
+                    const uint32_t len = ((e >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, cl, xb);
+                    br.consume(cl + xb);
+                    br.refill();
+                    uint32_t d = lds_u32(s_d + (((uint32_t)br.buf & ((1u << D_ROOTB) - 1)) << 2));
                     if (d >= K_SPECIAL) {
-                        if (d == E_SLOW) d = slow_entry<true>(&S.d_hd, S.d_sym, win & 0x7fffu, D_ROOTB);
+                        if (d == E_SLOW) d = slow_entry<true>(&S.d_hd, S.d_sym, br.peek(15), D_ROOTB);
                         if (d >= K_SPECIAL) { status = -INF_BAD_DISTANCE; break; }
                     }
                     const uint32_t dcl = d & 15, dxb = (d >> 4) & 15;
-                    const uint32_t dist = ((d >> 8) & 0xffffu) + bfe_u32(win, dcl, dxb);
-                    bp += dcl + dxb;
-                    if (dist > wp - ostart) { status = -INF_BAD_DISTANCE; break; }
+                    const uint32_t dist = ((d >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, dcl, dxb);
+                    br.consume(dcl + dxb);
+                    if (dist > opos + acc - ostart) { status = -INF_BAD_DISTANCE; break; }
                     const uint32_t packed = (len << 16) | (dist - 1);
-                    if (wp + len > wlim) {  // does not fit: first entry of the next batch
+                    if (acc + len > BATCH_MAX_OUT) {  // does not fit: first entry of the next batch
                         held = packed;
                         break;
                     }
                     sts_u32(s_q + 8 * nm, packed);
-                    sts_u32(s_q + 8 * nm + 4, wp - opos);
+                    sts_u32(s_q + 8 * nm + 4, acc);
                     nm++;
-                    wp += len;
-                    if (nm == BQ_MATCHES) break;
+                    acc += len;
                 }
-                acc = wp - opos;
-                br.seek(bp);
             } else if (st == 2) {
                 while (stored_left && acc < BATCH_MAX_OUT) {
                     br.refill();
