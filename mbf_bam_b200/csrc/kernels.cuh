@@ -828,23 +828,31 @@ __global__ void __launch_bounds__(128) k_frame_walk(FrameArgs a) {
     }
 }
 
-// single thread: validate the walker chain, repair serially where speculation failed, derive the carry
-__global__ void __launch_bounds__(32) k_frame_fix(FrameArgs a) {
+// one CTA: validate the walker chain in parallel; only when speculation failed somewhere does thread 0
+// repair the affected blocks serially; then derive the carry
+__global__ void __launch_bounds__(1024) k_frame_fix(FrameArgs a) {
+    __shared__ uint32_t s_bad, s_malformed;
     const uint32_t nb = a.meta->n_blocks;
     const uint32_t u_end = U_PREFIX + a.meta->u_total;
-    const int lane = threadIdx.x;
-    // parallel check first (one warp)
-    uint32_t bad = 0;
-    for (uint32_t b = lane; b + 1 < nb; b += 32)
-        if (a.blk_end[b] != a.blk_start[b + 1]) bad = 1;
-    bad = __any_sync(0xffffffffu, bad);
-    if (lane != 0) return;
+    if (threadIdx.x == 0) { s_bad = 0; s_malformed = 0xffffffffu; }
+    __syncthreads();
+    uint32_t bad = 0, malformed = 0xffffffffu;
+    for (uint32_t b = threadIdx.x; b < nb; b += blockDim.x) {
+        const uint32_t e = a.blk_end[b];
+        if (e == 0xffffffffu) malformed = min(malformed, b);
+        if (b + 1 < nb && e != a.blk_start[b + 1]) bad = 1;
+    }
+    if (bad) s_bad = 1;
+    if (malformed != 0xffffffffu) atomicMin(&s_malformed, malformed);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     uint32_t fixups = 0;
-    if (bad) {
+    if (s_bad) {
         a.meta->frame_bad = 1;
+        s_malformed = 0xffffffffu;  // re-derived below: bad speculation also ends walks with the malformed mark
         for (uint32_t b = 0; b + 1 < nb; b++) {
             uint32_t e = a.blk_end[b];
-            if (e == 0xffffffffu) break;
+            if (e == 0xffffffffu) { s_malformed = b; break; }
             if (e != a.blk_start[b + 1]) {
                 uint32_t limit = b + 2 < nb ? a.blk.uoff[b + 2] : u_end;
                 uint32_t n = 0;
@@ -855,13 +863,13 @@ __global__ void __launch_bounds__(32) k_frame_fix(FrameArgs a) {
                 fixups++;
             }
         }
+        if (s_malformed == 0xffffffffu && nb && a.blk_end[nb - 1] == 0xffffffffu) s_malformed = nb - 1;
     }
     a.meta->n_fixups = fixups;
     uint32_t carry = 0;
     if (nb) {
         uint32_t e = a.blk_end[nb - 1];
-        for (uint32_t b = 0; b < nb; b++)
-            if (a.blk_end[b] == 0xffffffffu) { set_err(a.meta, WERR_RECORD, b); e = u_end; break; }
+        if (s_malformed != 0xffffffffu) { set_err(a.meta, WERR_RECORD, s_malformed); e = u_end; }
         if (e < u_end) carry = u_end - e;
         if (carry > U_PREFIX) { set_err(a.meta, WERR_CARRY, carry); carry = 0; }
     } else if (!a.meta->range_start) {

@@ -493,7 +493,7 @@ struct Pipeline {
             uint32_t fgrid = std::max(1u, (m.n_blocks + 127) / 128);
             k_frame_walk<false><<<fgrid, 128, 0, s_main>>>(fa);
             launched("k_frame_walk<count>", s_main);
-            k_frame_fix<<<1, 32, 0, s_main>>>(fa);
+            k_frame_fix<<<1, 1024, 0, s_main>>>(fa);
             launched("k_frame_fix", s_main);
             k_excl_scan<<<1, 1024, 0, s_main>>>(fa.blk_nrec, fa.rec_base, &dmeta(bi)->n_blocks, 0, 0, &dmeta(bi)->n_records);
             launched("k_excl_scan(records)", s_main);

@@ -10,6 +10,6 @@ CMD="python tools/profile_target.py"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'k_inflate|k_frame_walk|k_count_reads' -c 6 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_inflate_batched|k_frame_walk|k_count_reads|k_scan' -c 8 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/plain_$TAG.log gpurun_out/ncu_launch_$TAG.log gpurun_out/ncu_full_$TAG.log
 ls -la gpurun_out
