@@ -146,6 +146,8 @@ def main():
     if world != args.gpus and world > 1:
         args.gpus = world
     threads = os.cpu_count() or 1
+    # one rank per GPU shares the host cores: split the file-staging threads between the ranks
+    os.environ.setdefault("MBF_BAM_READ_THREADS", str(max(2, min(16, threads // max(1, world)))))
 
     if args.impl == "reference" and rank != 0:
         return 0
