@@ -76,6 +76,14 @@ int32_t mbfbam_tid(const mbfbam_reader* r, const char* name); /* -1 if absent */
 int mbfbam_preload(mbfbam_reader* r, int32_t device, char* err, size_t errlen);
 void mbfbam_drop_preload(mbfbam_reader* r);
 
+/* Optional: map the file and page-lock the mapping (cudaHostRegister), so that the streamed path
+ * copies host -> device straight from the page cache instead of through pread + pinned staging
+ * buffers.  Pays off when one reader serves several calls (the count_reads_* suite on one BAM).
+ * Returns MBFBAM_ERR_UNSUPPORTED when the platform refuses to register the mapping; the reader keeps
+ * working through the staging path. */
+int mbfbam_pin_file(mbfbam_reader* r, char* err, size_t errlen);
+void mbfbam_unpin_file(mbfbam_reader* r);
+
 /* Per-call measurements (all optional output; zeroed by the library first). */
 typedef struct mbfbam_stats {
     uint64_t n_records;          /* BAM records framed (all refs in the scanned ranges) */

@@ -102,6 +102,7 @@ struct Source {
     virtual uint64_t size() const = 0;
     virtual void read(uint64_t off, size_t n, uint8_t* dst) const = 0;
     virtual const uint8_t* resident(int device) const { return nullptr; }  // device copy of the whole file
+    virtual const uint8_t* host_pinned() const { return nullptr; }         // page-locked host copy / mapping
 };
 struct FileSource : Source {
     const Reader* r;
@@ -109,6 +110,7 @@ struct FileSource : Source {
     uint64_t size() const override { return r->file_size; }
     void read(uint64_t off, size_t n, uint8_t* dst) const override { r->pread_exact(dst, off, n); }
     const uint8_t* resident(int device) const override { return r->preload_device == device ? r->preload_ptr : nullptr; }
+    const uint8_t* host_pinned() const override { return r->map_registered ? r->map_ptr : nullptr; }
 };
 struct MemSource : Source {
     const uint8_t* p;
@@ -315,7 +317,6 @@ struct Pipeline {
         if (res) {
             w.c_ptr = res + win_off;
         } else {
-            w.h_c.ensure((size_t)W + 65536 + 256);
             w.d_c.ensure((size_t)W + 65536 + 256);
             stage_window(w, win_off, (size_t)avail);
             st.h2d_bytes += avail;
@@ -377,8 +378,15 @@ struct Pipeline {
     // from the page cache runs at 2-4 GB/s per thread, far below PCIe); every piece is copied to the
     // device as soon as it and its predecessors have landed, so reading and H2D overlap.
     void stage_window(WinBufs& w, uint64_t win_off, size_t avail) {
-        uint8_t* h = w.h_c.as<uint8_t>();
         uint8_t* d = w.d_c.as<uint8_t>();
+        if (const uint8_t* hp = src->host_pinned()) {
+            // the file mapping is page-locked: DMA straight out of the page cache
+            CK(cudaMemcpyAsync(d, hp + win_off, avail, cudaMemcpyHostToDevice, s_front));
+            CK(cudaMemsetAsync(d + avail, 0, 128, s_front));
+            return;
+        }
+        w.h_c.ensure((size_t)W + 65536 + 256);
+        uint8_t* h = w.h_c.as<uint8_t>();
         const size_t PIECE = 8u << 20;
         const size_t n_pieces = (avail + PIECE - 1) / PIECE;
         int n_threads = (int)env_u32("MBF_BAM_READ_THREADS", std::min(16u, std::max(2u, std::thread::hardware_concurrency())));
@@ -873,6 +881,7 @@ int mbfbam_open(const char* bam_path, const char* bai_path, mbfbam_reader** out,
 
 void mbfbam_close(mbfbam_reader* r) {
     if (!r) return;
+    mbfbam_unpin_file(r);
     if (r->r.preload_device >= 0) cudaSetDevice(r->r.preload_device);
     delete r;
 }
@@ -908,6 +917,40 @@ int mbfbam_preload(mbfbam_reader* r, int32_t device, char* err, size_t errlen) {
         r->r.preload_device = device;
         r->r.preload_ptr = (uint8_t*)r->preload.p;
     });
+}
+
+int mbfbam_pin_file(mbfbam_reader* r, char* err, size_t errlen) {
+    return guarded(err, errlen, [&] {
+        std::lock_guard<std::mutex> lk(g_mu);
+        Reader& rd = r->r;
+        if (rd.map_registered) return;
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
+        if (!rd.map_ptr) {
+            void* p = mmap(nullptr, (size_t)rd.file_size, PROT_READ, MAP_SHARED | MAP_POPULATE, rd.fd, 0);
+            if (p == MAP_FAILED) throw Error(MBFBAM_ERR_IO, "Could not read bam: mmap failed for " + rd.path);
+            rd.map_ptr = (uint8_t*)p;
+            rd.map_len = (size_t)rd.file_size;
+        }
+        cudaError_t e = cudaHostRegister(rd.map_ptr, rd.map_len, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            munmap(rd.map_ptr, rd.map_len);
+            rd.map_ptr = nullptr;
+            rd.map_len = 0;
+            throw Error(MBFBAM_ERR_UNSUPPORTED, std::string("cannot page-lock the file mapping: ") + cudaGetErrorString(e));
+        }
+        rd.map_registered = true;
+    });
+}
+
+void mbfbam_unpin_file(mbfbam_reader* r) {
+    Reader& rd = r->r;
+    if (rd.map_registered) cudaHostUnregister(rd.map_ptr);
+    rd.map_registered = false;
+    if (rd.map_ptr) munmap(rd.map_ptr, rd.map_len);
+    rd.map_ptr = nullptr;
+    rd.map_len = 0;
 }
 
 void mbfbam_drop_preload(mbfbam_reader* r) {

@@ -151,6 +151,18 @@ struct PyReader {
         if (rc) value_error(err);
     }
     void drop_preload() { mbfbam_drop_preload(r); }
+    bool pin_file() {
+        char err[512] = {0};
+        int rc;
+        {
+            py::gil_scoped_release rel;
+            rc = mbfbam_pin_file(r, err, sizeof err);
+        }
+        if (rc == MBFBAM_ERR_UNSUPPORTED) return false;
+        if (rc) value_error(err);
+        return true;
+    }
+    void unpin_file() { mbfbam_unpin_file(r); }
 
     std::vector<std::pair<std::string, uint32_t>> targets() const {
         std::vector<std::pair<std::string, uint32_t>> v;
@@ -461,6 +473,8 @@ PYBIND11_MODULE(mbf_bam, m) {
         .def("set_shard", &PyReader::set_shard)
         .def("preload", &PyReader::preload)
         .def("drop_preload", &PyReader::drop_preload)
+        .def("pin_file", &PyReader::pin_file, "page-lock a mapping of the file; False if the platform refuses")
+        .def("unpin_file", &PyReader::unpin_file)
         .def("targets", &PyReader::targets)
         .def("chunks", &PyReader::chunks, py::arg("gene_intervals") = py::none())
         .def("plan", &PyReader::plan, py::arg("gene_intervals"), py::arg("shard_index") = 0, py::arg("shard_count") = 1)

@@ -12,6 +12,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -52,6 +53,10 @@ struct Reader {
     // optional device-resident copy of the whole file (mbfbam_preload)
     int preload_device = -1;
     uint8_t* preload_ptr = nullptr;
+    // optional page-locked mapping of the file (mbfbam_pin_file): H2D copies then read the page cache directly
+    uint8_t* map_ptr = nullptr;
+    size_t map_len = 0;
+    bool map_registered = false;
 
     ~Reader() {
         if (fd >= 0) ::close(fd);

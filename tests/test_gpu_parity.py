@@ -251,3 +251,15 @@ def test_alternate_inflate_kernels_agree(mb, tmp_path, monkeypatch):
     for d in ("0", "1", "2", "208"):
         monkeypatch.setenv("MBF_BAM_INFLATE_D", d)
         assert mb.inflate_buffer(data) == want, d
+
+
+def test_pinned_file_mapping_gives_same_result(mb, tmp_path):
+    path, contigs, recs, iv, giv = make_case(tmp_path, 18, n_reads=30_000, random_seq=True)
+    rd = mb.Reader(path)
+    a = rd.count_reads(1, iv, giv)
+    if not rd.pin_file():
+        pytest.skip("platform refuses to page-lock a file mapping")
+    b = rd.count_reads(1, iv, giv)
+    rd.unpin_file()
+    c = rd.count_reads(1, iv, giv)
+    assert a == b == c == c_oracle.count_reads_stranded(path, None, iv, giv)
