@@ -926,20 +926,26 @@ int mbfbam_pin_file(mbfbam_reader* r, char* err, size_t errlen) {
         if (rd.map_registered) return;
         int n = 0;
         if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
-        if (!rd.map_ptr) {
-            void* p = mmap(nullptr, (size_t)rd.file_size, PROT_READ, MAP_SHARED | MAP_POPULATE, rd.fd, 0);
-            if (p == MAP_FAILED) throw Error(MBFBAM_ERR_IO, "Could not read bam: mmap failed for " + rd.path);
+        // attempt 1: shared read-only mapping registered read-only; attempt 2: private (copy-on-write, never
+        // written) mapping registered with the default flags
+        std::string why;
+        for (int attempt = 0; attempt < 2 && !rd.map_registered; attempt++) {
+            void* p = attempt == 0 ? mmap(nullptr, (size_t)rd.file_size, PROT_READ, MAP_SHARED | MAP_POPULATE, rd.fd, 0)
+                                   : mmap(nullptr, (size_t)rd.file_size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_POPULATE, rd.fd, 0);
+            if (p == MAP_FAILED) { why = "mmap failed"; continue; }
+            cudaError_t e = cudaHostRegister(p, (size_t)rd.file_size,
+                                             attempt == 0 ? (cudaHostRegisterPortable | cudaHostRegisterReadOnly) : cudaHostRegisterPortable);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                why = cudaGetErrorString(e);
+                munmap(p, (size_t)rd.file_size);
+                continue;
+            }
             rd.map_ptr = (uint8_t*)p;
             rd.map_len = (size_t)rd.file_size;
+            rd.map_registered = true;
         }
-        cudaError_t e = cudaHostRegister(rd.map_ptr, rd.map_len, cudaHostRegisterPortable | cudaHostRegisterReadOnly);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            munmap(rd.map_ptr, rd.map_len);
-            rd.map_ptr = nullptr;
-            rd.map_len = 0;
-            throw Error(MBFBAM_ERR_UNSUPPORTED, std::string("cannot page-lock the file mapping: ") + cudaGetErrorString(e));
-        }
+        if (!rd.map_registered) throw Error(MBFBAM_ERR_UNSUPPORTED, "cannot page-lock the file mapping: " + why);
         rd.map_registered = true;
     });
 }

@@ -11,6 +11,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -158,7 +159,10 @@ struct PyReader {
             py::gil_scoped_release rel;
             rc = mbfbam_pin_file(r, err, sizeof err);
         }
-        if (rc == MBFBAM_ERR_UNSUPPORTED) return false;
+        if (rc == MBFBAM_ERR_UNSUPPORTED) {
+            if (getenv("MBF_BAM_TRACE")) fprintf(stderr, "[mbfbam] pin_file: %s\n", err);
+            return false;
+        }
         if (rc) value_error(err);
         return true;
     }
