@@ -10,8 +10,9 @@ One "step" = one complete count_reads_stranded job over the whole file.
           dense counts -> (NCCL all-reduce when N > 1).
   e2e   : reads/s through the public API from HOST memory (page cache): pread -> pinned -> H2D ->
           kernels -> D2H -> Python dicts.
-  roofline : k_inflate, algorithmic bytes (compressed read once + uncompressed written once) over its
-          CUDA-event time, against the measured HBM copy bandwidth.
+  roofline : k_tokens_bf (pass 1 of the two-pass inflate, the longest kernel): algorithmic bytes
+          (compressed stream read once + one 4-byte token written per DEFLATE symbol) over its CUDA-event
+          time on the launching stream, against the measured HBM copy bandwidth.
   cpu_baseline : the CPU restatement of the reference (oracle/, zlib + pthreads, one task per chunk like
           rayon in counters.rs:217-259) on all host cores over a bounded sample of the same file.
 """
@@ -29,9 +30,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "aligned reads/sec counted end-to-end from BAM"
 UNIT = "reads/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of k_inflate_batched divided by its algorithmic bytes (C + U),
-# from the ncu --set full capture summarised in profiles/r01z_ncu_full_summary.txt (789 MB + 830 MB vs 1086 MB)
-K1_TRAFFIC_RATIO_NCU = 1.49
+# dram__bytes_read.sum + dram__bytes_write.sum of k_tokens_bf<8> divided by its algorithmic bytes (C + 4 T),
+# from the ncu --set full capture summarised in profiles/r01y_ncu_two_pass_summary.txt
+K1_TRAFFIC_RATIO_NCU = 1.07
+K1_NCU_PROFILE = "profiles/r01y_ncu_two_pass_summary.txt"
 
 
 def env_int(name, default):
@@ -300,12 +302,12 @@ def main():
     d2h = gsum(statistics.mean(s["d2h_bytes"] for s in e2e_sts))
     # roofline of the dominant kernel on rank 0's shard
     st0 = val_sts[-1]
-    ms_infl = statistics.mean(s["ms_gpu_inflate"] for s in val_sts)
-    alg_bytes = st0["compressed_bytes"] + st0["uncompressed_bytes"]
+    ms_infl = statistics.mean(s["ms_gpu_tokens"] for s in val_sts)
+    alg_bytes = st0["compressed_bytes"] + 4 * st0["n_tokens"]
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (ms_infl / 1e3) / 1e9 if ms_infl > 0 else 0.0
     stage_ms = {k: statistics.mean(s[k] for s in val_sts) for k in
-                ("ms_gpu_scan", "ms_gpu_inflate", "ms_gpu_frame", "ms_gpu_count", "ms_gpu_all", "ms_total")}
+                ("ms_gpu_scan", "ms_gpu_inflate", "ms_gpu_tokens", "ms_gpu_frame", "ms_gpu_count", "ms_gpu_all", "ms_total")}
 
     if rank != 0:
         if dist is not None:
@@ -336,14 +338,16 @@ def main():
             "value": n_records * args.steps / pin_total, "unit": UNIT, "ms_per_step": 1000 * pin_total / args.steps,
             "note": "file mapping page-locked once per reader (mbfbam_pin_file); H2D straight from the page cache"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "k_inflate_batched", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": "k_tokens_bf<8>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None,
                      "traffic": int(alg_bytes * K1_TRAFFIC_RATIO_NCU / max(1, st0["n_windows"])),
-                     "traffic_note": "per launch; dram bytes / algorithmic bytes = %.2f measured with ncu (profiles/r01z_ncu_full_summary.txt)" % K1_TRAFFIC_RATIO_NCU,
+                     "traffic_note": "per launch; dram bytes / algorithmic bytes = %.2f measured with ncu (%s)" % (
+                         K1_TRAFFIC_RATIO_NCU, K1_NCU_PROFILE),
                      "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes),
                      "algorithmic_bytes_per_launch": int(alg_bytes / max(1, st0["n_windows"])),
                      "launches_per_step": int(st0["n_windows"]), "ms_per_step": ms_infl,
-                     "note": "K1 is bound by instruction issue (serial Huffman chain; smsp__issue_active 82 %), not by HBM"},
+                     "note": "DEFLATE symbol decode is a dependency chain: the kernel is latency/issue bound, not HBM bound "
+                             "(DESIGN.md, K1 roofline honesty); frac is small by construction"},
         "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "%d of %d chunks (%d reads, %.1f s wall), C restatement of the reference (zlib + pthreads)" % (
                              cpu_nck, n_chunks, cpu_nrec, cpu_dt)},

@@ -105,6 +105,8 @@ typedef struct mbfbam_stats {
     double ms_gpu_count;
     double ms_gpu_other;
     double ms_gpu_all;           /* first kernel start -> last kernel end               */
+    double ms_gpu_tokens;        /* pass 1 of the two-pass inflate (part of ms_gpu_inflate) */
+    uint64_t n_tokens;           /* DEFLATE symbols (literals + matches) decoded by pass 1  */
 } mbfbam_stats;
 
 typedef struct mbfbam_count_job {

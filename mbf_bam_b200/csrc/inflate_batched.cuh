@@ -73,11 +73,32 @@ __device__ __forceinline__ uint32_t d_entry(uint32_t sym, uint32_t codelen) {
 
 // Warp-cooperative table build.  lens[0..n) in shared memory.  IS_DIST selects the entry maker.
 // Returns 0 or an InflateError (uniform across the warp).
-template <bool IS_DIST>
+// second entry format (SIMT token decoder): [4:0] bits to consume (code + extra), [8:5] code length,
+// [25:10] base value, [31:30] kind.  extra = (window & ~(~0 << consume)) >> code length.  The two
+// special entries consume nothing.
+constexpr uint32_t E2_SLOW = K_SPECIAL, E2_INVALID = K_SPECIAL | 0x100u;
+__device__ __forceinline__ uint32_t ll_entry2(uint32_t sym, uint32_t codelen) {
+    if (sym < 256) return K_LIT | (sym << 10) | (codelen << 5) | codelen;
+    if (sym == 256) return K_EOB | (codelen << 5) | codelen;
+    sym -= 257;
+    if (sym >= 29) return E2_INVALID;
+    return K_LEN | ((uint32_t)MBF_TBL(LEN_BASE, sym) << 10) | (codelen << 5) | (codelen + (uint32_t)MBF_TBL(LEN_EXTRA, sym));
+}
+__device__ __forceinline__ uint32_t d_entry2(uint32_t sym, uint32_t codelen) {
+    if (sym >= 30) return E2_INVALID;
+    return ((uint32_t)MBF_TBL(DIST_BASE, sym) << 10) | (codelen << 5) | (codelen + (uint32_t)MBF_TBL(DIST_EXTRA, sym));
+}
+template <bool IS_DIST, int FMT>
+__device__ __forceinline__ uint32_t make_entry(uint32_t sym, uint32_t codelen) {
+    if (FMT == 2) return IS_DIST ? d_entry2(sym, codelen) : ll_entry2(sym, codelen);
+    return IS_DIST ? d_entry(sym, codelen) : ll_entry(sym, codelen);
+}
+
+template <bool IS_DIST, int FMT = 1>
 __device__ __forceinline__ int build_lut_warp(const uint8_t* lens, int n, int root, uint32_t* lut, uint16_t* sym_sorted,
                                                HuffDec* hd, uint32_t* run, int lane) {
     if (lane < 16) { hd->cnt[lane] = 0; run[lane] = 0; }
-    for (int i = lane; i < (1 << root); i += 32) lut[i] = E_INVALID;
+    for (int i = lane; i < (1 << root); i += 32) lut[i] = FMT == 2 ? E2_INVALID : E_INVALID;
     __syncwarp();
     for (int s = lane; s < n; s += 32) {
         const uint32_t l = lens[s];
@@ -121,10 +142,10 @@ __device__ __forceinline__ int build_lut_warp(const uint8_t* lens, int n, int ro
             const uint32_t code = hd->first[l] + rank;
             const uint32_t r = __brev(code) >> (32 - l);
             if (l <= (uint32_t)root) {
-                const uint32_t e = IS_DIST ? d_entry((uint32_t)s, l) : ll_entry((uint32_t)s, l);
+                const uint32_t e = make_entry<IS_DIST, FMT>((uint32_t)s, l);
                 for (uint32_t k = r; k < (1u << root); k += (1u << l)) lut[k] = e;
             } else {
-                lut[r & ((1u << root) - 1)] = E_SLOW;
+                lut[r & ((1u << root) - 1)] = FMT == 2 ? E2_SLOW : E_SLOW;
             }
         }
     }

@@ -60,6 +60,7 @@ struct WinMeta {
     uint32_t range_start;   // first window of a byte range: no carry, first record at first_rec_uoff
     uint32_t first_rec_uoff;
     unsigned long long outside;
+    unsigned long long n_tokens;  // DEFLATE symbols decoded by the token pass (statistics)
 };
 
 struct ChainState {

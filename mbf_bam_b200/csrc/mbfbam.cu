@@ -131,10 +131,11 @@ struct WinBufs {
     DevBuf mm_fp, mm_slot;
     uint32_t mm_cap = 0;
     const uint8_t* c_ptr = nullptr;  // device pointer of this window's bytes (d_c or a view of the preload)
+    bool two_pass = false;           // t[7] was recorded between the two passes of K1
     uint64_t win_off = 0;
     uint32_t scan_len = 0, avail = 0;
     cudaEvent_t ev_front = nullptr, ev_main = nullptr, ev_inf = nullptr;
-    cudaEvent_t t[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t t[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     WinMeta front_meta{};
     bool timed = false;
     bool in_flight = false;
@@ -155,7 +156,7 @@ struct Pipeline {
     WinBufs wb[2];
     DevBuf U[2];
     size_t U_cap = 0;    // data bytes (without prefix/slack)
-    DevBuf d_meta, d_chain, d_carry, d_tscratch, d_tok, d_ntok;
+    DevBuf d_meta, d_chain, d_carry, d_tscratch, d_tok[2], d_ntok[2];
     PinnedBuf h_meta_front, h_meta_main;
     int sm_count = 148;
     bool sync_debug = false;
@@ -218,7 +219,7 @@ struct Pipeline {
         src = s;
         kind = k;
         st = mbfbam_stats{};
-        uint64_t w = (uint64_t)env_u32("MBF_BAM_WINDOW_MB", 256) << 20;
+        uint64_t w = (uint64_t)env_u32("MBF_BAM_WINDOW_MB", 512) << 20;
         w = std::min<uint64_t>(std::max<uint64_t>(w, 1u << 20), 1024u << 20);
         uint64_t need = ((job_bytes + (1u << 20)) >> 20) << 20;
         W = (uint32_t)std::max<uint64_t>(1u << 20, std::min(w, need));
@@ -465,7 +466,8 @@ struct Pipeline {
         st.n_bgzf_blocks += m.n_blocks;
         st.uncompressed_bytes += m.u_total;
         st.n_windows++;
-        const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 1);
+        const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 308);
+        w.two_pass = false;
         cudaStream_t si = (mode_d == 0 || mode_d == 1) ? s_inf[bi] : s_inf[0];  // the two-pass kernels share one token buffer
         CK(cudaStreamWaitEvent(si, w.ev_front, 0));
         // U[bi] was last read by window k-2 (main stage + its second half); ev_reuse was recorded behind both
@@ -523,7 +525,8 @@ struct Pipeline {
     // K1 selection (MBF_BAM_INFLATE_D): 1 = batched warp-per-block kernel (production), 0 = single-lane
     // reference kernel, 2 / 216 / 208 = two-pass kernels with 32 / 16 / 8 decoders per warp
     void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks, cudaStream_t si) {
-        const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 1);
+        const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 308);
+        w.two_pass = false;
         switch (mode_d) {
             case 0: {
                 InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
@@ -537,33 +540,51 @@ struct Pipeline {
                 launched("k_inflate_batched", si);
                 break;
             }
-            case 2: case 216: case 208: {
-                // two-pass: SIMT token decode (DL blocks per warp), then one warp per block resolves LZ77
-                const int dl = mode_d == 216 ? 16 : mode_d == 208 ? 8 : 32;
-                d_tok.ensure((U_cap + 65536) * 4);
-                d_ntok.ensure((size_t)(cand_cap + 8) * 4);
-                d_tscratch.ensure((size_t)sm_count * 32 * 32 * sizeof(TokScratch));
-                TokenArgs ta{w.c_ptr, b.cpos, b.clen, b.isize, b.uoff, d_tok.as<uint32_t>(), d_ntok.as<uint32_t>(), U_PREFIX,
+            case 2: case 216: case 208: case 302: case 304: case 308: case 316: {
+                // two-pass: SIMT token decode (DL blocks per warp), then one warp per block resolves LZ77.
+                // 2xx = trip-interleaved state machine (first form), 3xx = branch-free trips.
+                const bool bf = mode_d >= 300;
+                const int dl = bf ? (int)mode_d - 300 : mode_d == 216 ? 16 : mode_d == 208 ? 8 : 32;
+                DevBuf& tokb = d_tok[bi];
+                DevBuf& ntokb = d_ntok[bi];
+                tokb.ensure((U_cap + 65536) * 4);
+                ntokb.ensure((size_t)(cand_cap + 8) * 4);
+                d_tscratch.ensure((size_t)2 * sm_count * 32 * 32 * sizeof(TokScratch));
+                TokenArgs ta{w.c_ptr, b.cpos, b.clen, b.isize, b.uoff, tokb.as<uint32_t>(), ntokb.as<uint32_t>(), U_PREFIX,
                              &dmeta(bi)->n_blocks, &dmeta(bi)->inflate_next, &dmeta(bi)->err, &dmeta(bi)->err_info,
-                             d_tscratch.as<TokScratch>()};
+                             d_tscratch.as<TokScratch>() + (size_t)bi * sm_count * 32 * 32,
+                             &dmeta(bi)->n_tokens};
                 auto launch_tokens = [&](auto kernel, int smem) {
                     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                    const int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
+                    int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
+                    // leaving room beside the persistent decoders lets the other window's resolve pass run
+                    // concurrently (it is issue bound, the decoders are latency bound)
+                    const uint32_t cap = env_u32("MBF_BAM_TOKENS_PER_SM", 0);
+                    if (cap) per_sm = std::min<int>(per_sm, (int)cap);
                     uint32_t grid = std::min<uint32_t>((n_blocks + dl - 1) / dl, (uint32_t)(sm_count * per_sm));
                     kernel<<<grid, 32, smem, si>>>(ta);
                 };
-                if (dl == 32) launch_tokens(k_inflate_tokens<32>, (int)sizeof(TokensShared<32>));
+                if (bf) {
+                    if (dl == 16) launch_tokens(k_tokens_bf<16>, (int)sizeof(TokensShared32<16>));
+                    else if (dl == 8) launch_tokens(k_tokens_bf<8>, (int)sizeof(TokensShared32<8>));
+                    else if (dl == 4) launch_tokens(k_tokens_bf<4>, (int)sizeof(TokensShared32<4>));
+                    else launch_tokens(k_tokens_bf<2>, (int)sizeof(TokensShared32<2>));
+                } else if (dl == 32) launch_tokens(k_inflate_tokens<32>, (int)sizeof(TokensShared<32>));
                 else if (dl == 16) launch_tokens(k_inflate_tokens<16>, (int)sizeof(TokensShared<16>));
                 else launch_tokens(k_inflate_tokens<8>, (int)sizeof(TokensShared<8>));
-                launched("k_inflate_tokens", si);
-                ResolveArgs ra{d_tok.as<uint32_t>(), d_ntok.as<uint32_t>(), b.isize, b.uoff, U_PREFIX, U[bi].as<uint8_t>(),
+                launched(bf ? "k_tokens_bf" : "k_inflate_tokens", si);
+                CK(cudaEventRecord(w.t[7], si));
+                w.two_pass = true;
+                ResolveArgs ra{tokb.as<uint32_t>(), ntokb.as<uint32_t>(), b.isize, b.uoff, U_PREFIX, U[bi].as<uint8_t>(),
                                &dmeta(bi)->n_blocks, &dmeta(bi)->err, &dmeta(bi)->err_info};
-                k_lz_resolve<<<n_blocks, 32, 0, si>>>(ra);
+                const uint32_t rgrid = (n_blocks + RESOLVE_WARPS - 1) / RESOLVE_WARPS;
+                if (env_u32("MBF_BAM_RESOLVE_RING", 2048) == 1024) k_lz_resolve<1024><<<rgrid, 32 * RESOLVE_WARPS, 0, si>>>(ra);
+                else k_lz_resolve<2048><<<rgrid, 32 * RESOLVE_WARPS, 0, si>>>(ra);
                 launched("k_lz_resolve", si);
                 break;
             }
             default:
-                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 0, 1, 2, 216 or 208");
+                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 0, 1, 2, 216, 208, 302, 304, 308 or 316");
         }
     }
 
@@ -668,6 +689,7 @@ struct Pipeline {
         if (m.err) throw Error(MBFBAM_ERR_FORMAT, err_text(m));
         st.n_records += m.n_records;
         st.n_fixups += m.n_fixups;
+        st.n_tokens += m.n_tokens;
         if (kind == JOB_COUNT) {
             st.n_records_owned += m.owned_records;
             if (m.mm_count > w.mm_cap) {
@@ -706,6 +728,7 @@ struct Pipeline {
             float ms = 0;
             cudaEventElapsedTime(&ms, w.t[0], w.t[1]); st.ms_gpu_scan += ms;
             cudaEventElapsedTime(&ms, w.t[2], w.t[3]); st.ms_gpu_inflate += ms;
+            if (w.two_pass) { cudaEventElapsedTime(&ms, w.t[2], w.t[7]); st.ms_gpu_tokens += ms; }
             cudaEventElapsedTime(&ms, w.t[6], w.t[4]); st.ms_gpu_frame += ms;
             cudaEventElapsedTime(&ms, w.t[4], w.t[5]); st.ms_gpu_count += ms;
             w.timed = false;

@@ -112,6 +112,8 @@ py::dict stats_dict(const mbfbam_stats& s) {
     d["ms_gpu_frame"] = s.ms_gpu_frame;
     d["ms_gpu_count"] = s.ms_gpu_count;
     d["ms_gpu_other"] = s.ms_gpu_other;
+    d["ms_gpu_tokens"] = s.ms_gpu_tokens;
+    d["n_tokens"] = s.n_tokens;
     d["ms_gpu_all"] = s.ms_gpu_all;
     return d;
 }
