@@ -31,8 +31,17 @@ struct Flat {
     std::vector<uint64_t> offs{0};
     std::vector<uint32_t> st, en, ge;
     std::vector<int8_t> sd;
-    std::vector<std::vector<std::string>> gene_ids;
+    // the caller's gene id objects (strong references: the GIL is released while the GPU works); they
+    // become the keys of the result dicts, so no string is copied or hashed again
+    std::vector<std::vector<PyObject*>> gene_ids;
     mbfbam_intervals c{};
+    Flat() = default;
+    Flat(const Flat&) = delete;
+    Flat& operator=(const Flat&) = delete;
+    ~Flat() {
+        for (auto& v : gene_ids)
+            for (PyObject* o : v) Py_DECREF(o);
+    }
 };
 
 [[noreturn]] void value_error(const std::string& m) {
@@ -42,39 +51,58 @@ struct Flat {
 
 // src/lib.rs:118-134 py_intervals_to_trees + src/count_reads/mod.rs:27-45 build_tree
 void flatten(const py::dict& d, Flat& f) {
-    try {
-        for (auto item : d) {
-            f.names.push_back(py::cast<std::string>(item.first));
-            if (!py::isinstance<py::list>(item.second)) value_error("Python error: interval value is not a list");
-            py::list lst = py::reinterpret_borrow<py::list>(item.second);
-            f.n_genes.push_back((uint32_t)lst.size());
-            f.gene_ids.emplace_back();
-            uint32_t gene_no = 0;
-            for (auto e : lst) {
-                if (!py::isinstance<py::tuple>(e)) value_error("Python error: interval entry is not a tuple");
-                py::tuple t = py::reinterpret_borrow<py::tuple>(e);
-                if (t.size() < 4) value_error("Python error: interval entry needs (gene_id, strand, starts, stops)");
-                f.gene_ids.back().push_back(py::cast<std::string>(t[0]));
-                long strand = py::cast<long>(t[1]);
-                if (strand < -128 || strand > 127) value_error("Python error: strand does not fit i8");
-                if (!py::isinstance<py::list>(t[2]) || !py::isinstance<py::list>(t[3]))
-                    value_error("Python error: starts/stops must be lists");
-                py::list s = py::reinterpret_borrow<py::list>(t[2]), e2 = py::reinterpret_borrow<py::list>(t[3]);
-                size_t n = std::min(s.size(), e2.size());  // zip() truncates (mod.rs:38)
-                for (size_t i = 0; i < n; i++) {
-                    long long a = py::cast<long long>(s[i]), b = py::cast<long long>(e2[i]);
-                    if (a < 0 || b < 0 || a > 0xffffffffLL || b > 0xffffffffLL) value_error("Python error: coordinate does not fit u32");
-                    f.st.push_back((uint32_t)a);
-                    f.en.push_back((uint32_t)b);
-                    f.ge.push_back(gene_no);
-                    f.sd.push_back((int8_t)strand);
-                }
-                gene_no++;
-            }
-            f.offs.push_back(f.st.size());
+    // plain CPython calls: this runs once per count call over ~10^5 small objects, and the generic
+    // pybind11 casts cost about a microsecond each
+    auto as_ll = [](PyObject* o, long long& out) {
+        out = PyLong_AsLongLong(o);
+        if (out == -1 && PyErr_Occurred()) {
+            PyErr_Clear();
+            value_error("Python error: interval coordinate/strand is not an integer");
         }
-    } catch (py::cast_error& e) {
-        value_error(std::string("Python error: ") + e.what());
+    };
+    PyObject *key, *value;
+    Py_ssize_t pos = 0;
+    while (PyDict_Next(d.ptr(), &pos, &key, &value)) {
+        Py_ssize_t klen = 0;
+        const char* kp = PyUnicode_Check(key) ? PyUnicode_AsUTF8AndSize(key, &klen) : nullptr;
+        if (!kp) {
+            PyErr_Clear();
+            value_error("Python error: interval key is not a str");
+        }
+        f.names.emplace_back(kp, (size_t)klen);
+        if (!PyList_Check(value)) value_error("Python error: interval value is not a list");
+        const Py_ssize_t ng = PyList_GET_SIZE(value);
+        f.n_genes.push_back((uint32_t)ng);
+        f.gene_ids.emplace_back();
+        auto& ids = f.gene_ids.back();
+        ids.reserve((size_t)ng);
+        for (Py_ssize_t g = 0; g < ng; g++) {
+            PyObject* t = PyList_GET_ITEM(value, g);
+            if (!PyTuple_Check(t)) value_error("Python error: interval entry is not a tuple");
+            if (PyTuple_GET_SIZE(t) < 4) value_error("Python error: interval entry needs (gene_id, strand, starts, stops)");
+            PyObject* id = PyTuple_GET_ITEM(t, 0);
+            if (!PyUnicode_Check(id)) value_error("Python error: gene id is not a str");
+            Py_INCREF(id);
+            ids.push_back(id);
+            long long strand;
+            as_ll(PyTuple_GET_ITEM(t, 1), strand);
+            if (strand < -128 || strand > 127) value_error("Python error: strand does not fit i8");
+            PyObject* s = PyTuple_GET_ITEM(t, 2);
+            PyObject* e = PyTuple_GET_ITEM(t, 3);
+            if (!PyList_Check(s) || !PyList_Check(e)) value_error("Python error: starts/stops must be lists");
+            const Py_ssize_t n = std::min(PyList_GET_SIZE(s), PyList_GET_SIZE(e));  // zip() truncates (mod.rs:38)
+            for (Py_ssize_t i = 0; i < n; i++) {
+                long long a, b;
+                as_ll(PyList_GET_ITEM(s, i), a);
+                as_ll(PyList_GET_ITEM(e, i), b);
+                if (a < 0 || b < 0 || a > 0xffffffffLL || b > 0xffffffffLL) value_error("Python error: coordinate does not fit u32");
+                f.st.push_back((uint32_t)a);
+                f.en.push_back((uint32_t)b);
+                f.ge.push_back((uint32_t)g);
+                f.sd.push_back((int8_t)strand);
+            }
+        }
+        f.offs.push_back(f.st.size());
     }
     for (auto& n : f.names) f.name_ptrs.push_back(n.c_str());
     f.c.n_contigs = (int32_t)f.names.size();
@@ -85,6 +113,35 @@ void flatten(const py::dict& d, Flat& f) {
     f.c.iv_end = f.en.data();
     f.c.iv_gene = f.ge.data();
     f.c.iv_strand = f.sd.data();
+}
+
+// result dict helpers (keys are the caller's own str objects or small "_name" strings)
+inline PyObject* to_py(uint64_t v) { return PyLong_FromUnsignedLongLong(v); }
+inline PyObject* to_py(double v) { return PyFloat_FromDouble(v); }
+inline bool from_py(PyObject* o, uint64_t& v) { v = PyLong_AsUnsignedLongLong(o); return !(v == (uint64_t)-1 && PyErr_Occurred()); }
+inline bool from_py(PyObject* o, double& v) { v = PyFloat_AsDouble(o); return !(v == -1.0 && PyErr_Occurred()); }
+
+template <class T>
+void dict_add(PyObject* d, PyObject* key, T v) {  // d[key] = d.get(key, 0) + v
+    PyObject* old = PyDict_GetItemWithError(d, key);  // borrowed
+    if (old) {
+        T o;
+        if (!from_py(old, o)) throw py::error_already_set();
+        v += o;
+    } else if (PyErr_Occurred()) {
+        throw py::error_already_set();
+    }
+    PyObject* nv = to_py(v);
+    if (!nv || PyDict_SetItem(d, key, nv) != 0) {
+        Py_XDECREF(nv);
+        throw py::error_already_set();
+    }
+    Py_DECREF(nv);
+}
+template <class T>
+void dict_add(PyObject* d, const std::string& key, T v) {
+    py::str k(key);
+    dict_add<T>(d, k.ptr(), v);
 }
 
 int env_int(const char* name, int dflt) {
@@ -256,7 +313,6 @@ struct PyReader {
     // counters.rs:236-254 summed over chunks: per contig, `insert` keeps the LAST gene_no of a duplicated id
     static py::dict assemble_unstranded(const Raw& raw) {
         py::dict out;
-        std::map<std::string, uint64_t> acc;
         size_t base = 0;
         uint64_t total_all = 0;
         bool any = false;
@@ -264,54 +320,66 @@ struct PyReader {
             const auto& ids = raw.iv.gene_ids[c];
             if (raw.scanned[c]) {
                 any = true;
-                std::map<std::string, uint64_t> last;
+                py::dict last;  // insert semantics within one contig
                 uint64_t tot = 0;
                 for (size_t g = 0; g < ids.size(); g++) {
-                    last[ids[g]] = raw.fwd[base + g];
+                    PyObject* v = to_py(raw.fwd[base + g]);
+                    if (!v || PyDict_SetItem(last.ptr(), ids[g], v) != 0) {
+                        Py_XDECREF(v);
+                        throw py::error_already_set();
+                    }
+                    Py_DECREF(v);
                     tot += raw.fwd[base + g];
                 }
-                for (auto& kv : last) acc[kv.first] += kv.second;
-                acc["_" + raw.iv.names[c]] += tot;
+                PyObject *k, *v;
+                Py_ssize_t pos = 0;
+                while (PyDict_Next(last.ptr(), &pos, &k, &v)) {
+                    uint64_t x;
+                    if (!from_py(v, x)) throw py::error_already_set();
+                    dict_add<uint64_t>(out.ptr(), k, x);
+                }
+                dict_add<uint64_t>(out.ptr(), "_" + raw.iv.names[c], tot);
                 total_all += tot;
             }
             base += ids.size();
         }
         if (any) {
-            acc["_total"] += total_all;
-            acc["_outside"] += raw.outside;
+            dict_add<uint64_t>(out.ptr(), std::string("_total"), total_all);
+            dict_add<uint64_t>(out.ptr(), std::string("_outside"), raw.outside);
         }
-        for (auto& kv : acc) out[py::str(kv.first)] = py::int_(kv.second);
         return out;
     }
 
     // counters.rs:262-273 (+= per gene id), :309-314 (_outside only in the forward dict)
     template <class T>
     static py::tuple assemble_dual(const Raw& raw, const std::vector<T>& f, const std::vector<T>& v) {
-        std::map<std::string, T> a, b;
+        py::dict da, db;
         size_t base = 0;
         bool any = false;
+        T all_a = 0, all_b = 0;
         for (size_t c = 0; c < raw.iv.names.size(); c++) {
             const auto& ids = raw.iv.gene_ids[c];
             if (raw.scanned[c]) {
                 any = true;
                 T ta = 0, tb = 0;
                 for (size_t g = 0; g < ids.size(); g++) {
-                    a[ids[g]] += f[base + g];
-                    b[ids[g]] += v[base + g];
+                    dict_add<T>(da.ptr(), ids[g], f[base + g]);
+                    dict_add<T>(db.ptr(), ids[g], v[base + g]);
                     ta += f[base + g];
                     tb += v[base + g];
                 }
-                a["_" + raw.iv.names[c]] += ta;
-                b["_" + raw.iv.names[c]] += tb;
-                a["_total"] += ta;
-                b["_total"] += tb;
+                dict_add<T>(da.ptr(), "_" + raw.iv.names[c], ta);
+                dict_add<T>(db.ptr(), "_" + raw.iv.names[c], tb);
+                all_a += ta;
+                all_b += tb;
             }
             base += ids.size();
         }
-        py::dict da, db;
-        for (auto& kv : a) da[py::str(kv.first)] = py::cast(kv.second);
-        for (auto& kv : b) db[py::str(kv.first)] = py::cast(kv.second);
-        if (any) da["_outside"] = py::int_(raw.outside);
+        if (any) {
+            dict_add<T>(da.ptr(), std::string("_total"), all_a);
+            dict_add<T>(db.ptr(), std::string("_total"), all_b);
+            da["_outside"] = py::int_(raw.outside);
+        }
         return py::make_tuple(da, db);
     }
 
