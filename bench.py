@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 METRIC = "aligned reads/sec counted end-to-end from BAM"
 UNIT = "reads/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of k_tokens_bf<8> divided by its algorithmic bytes (C + 4 T),
-# from the ncu --set full capture summarised in profiles/r01y_ncu_two_pass_summary.txt
-K1_TRAFFIC_RATIO_NCU = 1.07
-K1_NCU_PROFILE = "profiles/r01y_ncu_two_pass_summary.txt"
+# from the ncu --set full capture summarised in profiles/r01tp_ncu_full_summary.txt
+K1_TRAFFIC_RATIO_NCU = 0.99
+K1_NCU_PROFILE = "profiles/r01tp_ncu_full_summary.txt"
 
 
 def env_int(name, default):

@@ -153,65 +153,6 @@ __device__ __forceinline__ int build_lut_warp(const uint8_t* lens, int n, int ro
     return 0;
 }
 
-// Same cooperative build for 16-bit LUTs in the (symbol << 4 | length) format of inflate_core.cuh
-// (LUT_SLOW / LUT_INVALID markers).  Used by the SIMT token decoder, whose per-lane tables must be small.
-__device__ __forceinline__ int build_lut16_warp(const uint8_t* lens, int n, int root, uint16_t* lut, uint16_t* sym_sorted,
-                                                HuffDec* hd, uint32_t* run, int lane) {
-    if (lane < 16) { hd->cnt[lane] = 0; run[lane] = 0; }
-    for (int i = lane; i < (1 << root); i += 32) lut[i] = LUT_INVALID;
-    __syncwarp();
-    for (int s = lane; s < n; s += 32) {
-        const uint32_t l = lens[s];
-        if (l) atomicAdd(&run[l], 1u);
-    }
-    __syncwarp();
-    if (lane == 0) {
-        int left = 1, max = 0, bad = 0;
-        uint32_t code = 0, off = 0;
-        for (int len = 1; len <= 15; len++) {
-            const uint32_t c = run[len];
-            hd->cnt[len] = (uint16_t)c;
-            if (c) max = len;
-            left = (left << 1) - (int)c;
-            if (left < 0) bad = 1;
-            hd->first[len] = (uint16_t)code;
-            hd->offs[len] = (uint16_t)off;
-            code = (code + c) << 1;
-            off += c;
-        }
-        if (max == 0) bad = 0;
-        else if (left > 0 && max != 1) bad = 1;
-        hd->cnt[0] = (uint16_t)bad;
-    }
-    __syncwarp();
-    if (hd->cnt[0]) return INF_BAD_CODES;
-    if (lane < 16) run[lane] = 0;
-    __syncwarp();
-    for (int base = 0; base < n; base += 32) {
-        const int s = base + lane;
-        const uint32_t l = s < n ? lens[s] : 0u;
-        const unsigned peers = __match_any_sync(0xffffffffu, l);
-        uint32_t rank = 0;
-        if (l) rank = run[l] + __popc(peers & ((1u << lane) - 1));
-        __syncwarp();
-        if (l && lane == __ffs(peers) - 1) run[l] += __popc(peers);
-        __syncwarp();
-        if (l) {
-            sym_sorted[hd->offs[l] + rank] = (uint16_t)s;
-            const uint32_t code = hd->first[l] + rank;
-            const uint32_t r = __brev(code) >> (32 - l);
-            if (l <= (uint32_t)root) {
-                const uint16_t e = (uint16_t)(((uint32_t)s << 4) | l);
-                for (uint32_t k = r; k < (1u << root); k += (1u << l)) lut[k] = e;
-            } else {
-                lut[r & ((1u << root) - 1)] = LUT_SLOW;
-            }
-        }
-    }
-    __syncwarp();
-    return 0;
-}
-
 // codes longer than the LUT root (lane 0 only): canonical search, then the entry of that symbol
 template <bool IS_DIST>
 __device__ __forceinline__ uint32_t slow_entry(const HuffDec* hd, const uint16_t* sym, uint32_t bits15, int root) {

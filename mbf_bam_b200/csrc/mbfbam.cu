@@ -522,8 +522,8 @@ struct Pipeline {
         w.timed = true;
     }
 
-    // K1 selection (MBF_BAM_INFLATE_D): 1 = batched warp-per-block kernel (production), 0 = single-lane
-    // reference kernel, 2 / 216 / 208 = two-pass kernels with 32 / 16 / 8 decoders per warp
+    // K1 selection (MBF_BAM_INFLATE_D): 308 = two-pass, 8 decoders per warp (production; 302/304/316 =
+    // 2/4/16 decoders), 1 = one-pass warp-per-block kernel, 0 = single-lane reference kernel
     void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks, cudaStream_t si) {
         const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 308);
         w.two_pass = false;
@@ -540,11 +540,10 @@ struct Pipeline {
                 launched("k_inflate_batched", si);
                 break;
             }
-            case 2: case 216: case 208: case 302: case 304: case 308: case 316: {
-                // two-pass: SIMT token decode (DL blocks per warp), then one warp per block resolves LZ77.
-                // 2xx = trip-interleaved state machine (first form), 3xx = branch-free trips.
-                const bool bf = mode_d >= 300;
-                const int dl = bf ? (int)mode_d - 300 : mode_d == 216 ? 16 : mode_d == 208 ? 8 : 32;
+            case 302: case 304: case 308: case 316: {
+                // two-pass: SIMT token decode (DL = mode - 300 decoders per warp), then one warp per block
+                // resolves LZ77
+                const int dl = (int)mode_d - 300;
                 DevBuf& tokb = d_tok[bi];
                 DevBuf& ntokb = d_ntok[bi];
                 tokb.ensure((U_cap + 65536) * 4);
@@ -564,15 +563,11 @@ struct Pipeline {
                     uint32_t grid = std::min<uint32_t>((n_blocks + dl - 1) / dl, (uint32_t)(sm_count * per_sm));
                     kernel<<<grid, 32, smem, si>>>(ta);
                 };
-                if (bf) {
-                    if (dl == 16) launch_tokens(k_tokens_bf<16>, (int)sizeof(TokensShared32<16>));
-                    else if (dl == 8) launch_tokens(k_tokens_bf<8>, (int)sizeof(TokensShared32<8>));
-                    else if (dl == 4) launch_tokens(k_tokens_bf<4>, (int)sizeof(TokensShared32<4>));
-                    else launch_tokens(k_tokens_bf<2>, (int)sizeof(TokensShared32<2>));
-                } else if (dl == 32) launch_tokens(k_inflate_tokens<32>, (int)sizeof(TokensShared<32>));
-                else if (dl == 16) launch_tokens(k_inflate_tokens<16>, (int)sizeof(TokensShared<16>));
-                else launch_tokens(k_inflate_tokens<8>, (int)sizeof(TokensShared<8>));
-                launched(bf ? "k_tokens_bf" : "k_inflate_tokens", si);
+                if (dl == 16) launch_tokens(k_tokens_bf<16>, (int)sizeof(TokensShared32<16>));
+                else if (dl == 8) launch_tokens(k_tokens_bf<8>, (int)sizeof(TokensShared32<8>));
+                else if (dl == 4) launch_tokens(k_tokens_bf<4>, (int)sizeof(TokensShared32<4>));
+                else launch_tokens(k_tokens_bf<2>, (int)sizeof(TokensShared32<2>));
+                launched("k_tokens_bf", si);
                 CK(cudaEventRecord(w.t[7], si));
                 w.two_pass = true;
                 ResolveArgs ra{tokb.as<uint32_t>(), ntokb.as<uint32_t>(), b.isize, b.uoff, U_PREFIX, U[bi].as<uint8_t>(),
@@ -584,7 +579,7 @@ struct Pipeline {
                 break;
             }
             default:
-                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 0, 1, 2, 216, 208, 302, 304, 308 or 316");
+                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 0, 1, 302, 304, 308 or 316");
         }
     }
 

@@ -248,7 +248,7 @@ def test_alternate_inflate_kernels_agree(mb, tmp_path, monkeypatch):
     path, *_ = make_case(tmp_path, 17, n_reads=30_000, random_seq=True)
     data = open(path, "rb").read()
     want = b"".join(p for _, _, p in bamio.iter_bgzf_blocks(data))
-    for d in ("0", "1", "2", "208", "304", "308", "316"):
+    for d in ("0", "1", "302", "304", "308", "316"):
         monkeypatch.setenv("MBF_BAM_INFLATE_D", d)
         assert mb.inflate_buffer(data) == want, d
 
