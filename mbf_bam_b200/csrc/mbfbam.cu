@@ -736,16 +736,21 @@ struct Pipeline {
     void run(const std::vector<ByteRange>& ranges) {
         struct Win { uint64_t off; uint32_t scan_len; uint64_t src_end; int range_start; uint64_t range_off; uint32_t first_uoff; };
         std::vector<Win> wins;
+        // Streamed jobs ramp the window size up (W/8, then x1.5 per window until W): the bytes of window k+1
+        // are staged while the GPU works on window k, so a window must not take longer to stage than its
+        // predecessor takes to process -- a full-size second window would leave the GPU idle for ~10 ms.
+        const bool ramp = !src->resident(device);
+        uint64_t cur_w = ramp ? std::max<uint64_t>(W / 8, 1u << 20) : W;
         for (const ByteRange& r : ranges) {
             uint64_t pos = r.cbeg;
             bool first = true;
             while (pos < r.cend) {
                 uint64_t base = pos & ~(uint64_t)15;
-                // the very first window is a quarter of the others so that the GPU starts early
-                uint64_t scan_end = std::min<uint64_t>(r.cend, base + (wins.empty() && !src->resident(device) ? std::max<uint32_t>(W / 4, 1u << 20) : W));
+                uint64_t scan_end = std::min<uint64_t>(r.cend, base + cur_w);
                 wins.push_back({base, (uint32_t)(scan_end - base), src->size(), first ? 1 : 0, r.cbeg, first ? r.first_uoff : 0u});
                 first = false;
                 pos = scan_end;
+                cur_w = std::min<uint64_t>(W, cur_w + cur_w / 2);
             }
         }
         double t0 = now_ms();
