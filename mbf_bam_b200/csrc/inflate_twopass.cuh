@@ -10,10 +10,10 @@
 //           is ONE straight-line instruction sequence whatever the symbols are; it emits a 32-bit token
 //           (literal byte | length + distance) to HBM.  Everything rare -- end of block, headers, stored
 //           blocks, table builds (by all 32 lanes), codes longer than the LUT root -- happens outside it.
-//   pass 2  k_lz_resolve  one warp per block turns tokens into bytes: 32 tokens per batch, warp scan for
-//           the output offsets, literals stored at once, independent matches copied one per lane
-//           (16 bytes per step; sources within 1.5 KB from the shared-memory ring, older ones from
-//           L2/HBM), dependent matches in order with 32 lanes each.
+//   pass 2  k_lz_resolve  one warp per block turns tokens into bytes: batches of up to 32 matches / 512
+//           bytes (tokens read 32 at a time, warp scan for the output offsets, literals stored at once),
+//           independent matches copied one per lane (16 bytes per step; sources within 1.5 KB from the
+//           shared-memory ring, older ones from L2/HBM), dependent matches in order with 32 lanes each.
 //
 // Tokens of block b live at tok[uoff[b] - U_PREFIX ...] (a token yields >= 1 byte, so ISIZE bounds the
 // count); ntok[b] is written by pass 1.
@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(32 * RESOLVE_WARPS) k_lz_resolve(ResolveArgs a
     constexpr uint32_t BATCH_NEAR = RING - BATCH_MAX_OUT;
     constexpr uint32_t RINGB = RING;
     __shared__ __align__(16) uint8_t rings[RESOLVE_WARPS][RING];
+    __shared__ uint2 queues[RESOLVE_WARPS][32];  // (len << 16 | dist - 1, output offset in the batch) per match
     uint8_t* const ring = rings[threadIdx.x >> 5];
     const uint32_t b = blockIdx.x * RESOLVE_WARPS + (threadIdx.x >> 5);
     if (b >= *a.n_blocks) return;
@@ -416,38 +417,65 @@ __global__ void __launch_bounds__(32 * RESOLVE_WARPS) k_lz_resolve(ResolveArgs a
     const uint32_t nt = a.ntok[b];
     uint8_t* const U = a.U;
     const uint32_t s_ring = smem_addr(ring);
+    const uint32_t s_q = smem_addr(queues[threadIdx.x >> 5]);
+    const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t opos = ostart, flushed = ostart;
     bool bad = false;
     for (uint32_t t0 = 0; t0 < nt;) {
-        // ---- next batch: as many of the next 32 tokens as fit BATCH_MAX_OUT bytes
-        const uint32_t ti = t0 + lane;
-        const uint32_t e = ti < nt ? __ldg(tk + ti) : 0u;
-        if (ti + 32 < nt) asm volatile("prefetch.global.L1 [%0];" ::"l"(tk + ti + 32));  // next batch starts at most 32 on
-        const bool is_match = (e >> 31) != 0;
-        const uint32_t mylen = ti < nt ? (is_match ? ((e >> 16) & 0x1ffu) : 1u) : 0u;
-        uint32_t incl = mylen;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += y;
-        }
-        const unsigned fits = __ballot_sync(0xffffffffu, mylen != 0 && incl <= BATCH_MAX_OUT);
-        const uint32_t k = (uint32_t)__popc(fits);  // tokens taken (prefix property: incl is monotone)
-        const uint32_t acc = __shfl_sync(0xffffffffu, incl, k ? k - 1 : 0);
-        const bool mine = (uint32_t)lane < k;
-        const uint32_t off = incl - mylen;
-        if (k == 0 || opos + acc > oend) { bad = true; break; }
         // ---- older output to HBM first (far matches read it back through L2)
         {
             const uint32_t upto = min(opos & ~15u, oend);
             ring_flush_w<RINGB_MASK>(ring, U, flushed, upto, lane);
             if (upto > flushed) flushed = upto;
         }
-        if (mine && !is_match) sts_u8(s_ring + ((opos + off) & RINGB_MASK), e & 0xffu);
+        // ---- build a batch: tokens in rounds of 32 until 32 matches or BATCH_MAX_OUT bytes are collected.
+        // Literals go straight into the ring, matches into the queue (one per lane for the copy passes:
+        // a batch of 32 TOKENS would leave 60 % of the lanes without a match).
+        uint32_t nm = 0, acc = 0;
+        for (bool more = true; more;) {
+            const uint32_t ti = t0 + lane;
+            const bool valid = ti < nt;
+            const uint32_t e = valid ? __ldg(tk + ti) : 0u;
+            if (ti + 32 < nt) asm volatile("prefetch.global.L1 [%0];" ::"l"(tk + ti + 32));
+            const bool is_match = (e >> 31) != 0;
+            const uint32_t mylen = valid ? (is_match ? ((e >> 16) & 0x1ffu) : 1u) : 0u;
+            uint32_t incl = mylen;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += y;
+            }
+            const unsigned mb = __ballot_sync(0xffffffffu, valid && is_match);
+            const uint32_t midx = nm + (uint32_t)__popc(mb & lt_mask);
+            const bool fit = valid && acc + incl <= BATCH_MAX_OUT && (!is_match || midx < 32u);
+            const unsigned fb = __ballot_sync(0xffffffffu, fit);
+            const uint32_t k = fb == 0xffffffffu ? 32u : (uint32_t)__ffs(~fb) - 1u;  // leading tokens that fit
+            const uint32_t off = acc + incl - mylen;
+            if ((uint32_t)lane < k) {
+                if (is_match) {
+                    sts_u32(s_q + 8u * midx, (mylen << 16) | (e & 0x7fffu));
+                    sts_u32(s_q + 8u * midx + 4u, off);
+                } else {
+                    sts_u8(s_ring + ((opos + off) & RINGB_MASK), e & 0xffu);
+                }
+            }
+            if (k) {
+                acc += __shfl_sync(0xffffffffu, incl, (int)k - 1);
+                nm += (uint32_t)__popc(k == 32u ? mb : mb & ((1u << k) - 1u));
+                t0 += k;
+            }
+            more = k == 32u && t0 < nt && nm < 32u && acc < BATCH_MAX_OUT;
+        }
+        if (acc == 0 || opos + acc > oend) { bad = true; break; }
         __syncwarp();
         // ---- pass 1: one whole match per lane when it reads nothing of this batch
-        const uint32_t len = mine && is_match ? mylen : 0u;
-        const uint32_t dist = (e & 0x7fffu) + 1u;
+        uint32_t len = 0, dist = 1, off = 0;
+        if ((uint32_t)lane < nm) {
+            const uint32_t m = lds_u32(s_q + 8u * lane);
+            off = lds_u32(s_q + 8u * lane + 4u);
+            len = m >> 16;
+            dist = (m & 0x7fffu) + 1u;
+        }
         const bool dep = len != 0 && dist < off + len;
         if (len != 0 && dist > opos + off - ostart) bad = true;
         if (__any_sync(0xffffffffu, bad)) { bad = true; break; }
@@ -503,7 +531,6 @@ __global__ void __launch_bounds__(32 * RESOLVE_WARPS) k_lz_resolve(ResolveArgs a
             __syncwarp();
         }
         opos += acc;
-        t0 += k;
     }
     __syncwarp();
     if (!bad) {
