@@ -476,7 +476,8 @@ __global__ void __launch_bounds__(32 * RESOLVE_WARPS) k_lz_resolve(ResolveArgs a
             len = m >> 16;
             dist = (m & 0x7fffu) + 1u;
         }
-        const bool dep = len != 0 && dist < off + len;
+        // long matches would keep one lane busy for many steps while 31 wait: they take the 32-lane route
+        const bool dep = len != 0 && (dist < off + len || len > 32u);
         if (len != 0 && dist > opos + off - ostart) bad = true;
         if (__any_sync(0xffffffffu, bad)) { bad = true; break; }
         const uint32_t dst = opos + off, src = dst - dist;
@@ -512,7 +513,8 @@ __global__ void __launch_bounds__(32 * RESOLVE_WARPS) k_lz_resolve(ResolveArgs a
             }
         }
         __syncwarp();
-        // ---- pass 2: matches that read this batch's own output (or overlap themselves), in order
+        // ---- pass 2: matches that read this batch's own output (or overlap themselves) and long ones, in
+        // order, 32 lanes each
         unsigned mm = __ballot_sync(0xffffffffu, dep);
         while (mm) {
             const int j = __ffs(mm) - 1;
@@ -521,7 +523,13 @@ __global__ void __launch_bounds__(32 * RESOLVE_WARPS) k_lz_resolve(ResolveArgs a
             const uint32_t dj = __shfl_sync(0xffffffffu, dist, j);
             const uint32_t dstj = opos + __shfl_sync(0xffffffffu, off, j);
             const uint32_t sj = dstj - dj;
-            if (dj >= lj) {
+            if (dj > BATCH_NEAR) {  // source already flushed and possibly gone from the ring (dj > lj here)
+                for (uint32_t i = lane; i < lj; i += 32) {
+                    uint32_t v;
+                    asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(U + sj + i));
+                    sts_u8(s_ring + ((dstj + i) & RINGB_MASK), v);
+                }
+            } else if (dj >= lj) {
                 for (uint32_t i = lane; i < lj; i += 32)
                     sts_u8(s_ring + ((dstj + i) & RINGB_MASK), lds_u8(s_ring + ((sj + i) & RINGB_MASK)));
             } else {

@@ -64,6 +64,31 @@ def test_inflate_random_and_text(mb, tmp_path):
     assert mb.inflate_buffer(p.read_bytes()) == payload
 
 
+def test_inflate_long_matches_near_far_and_overlapping(mb, tmp_path, monkeypatch):
+    """Long matches (up to 258 bytes) whose source is in the output ring, far behind it (already flushed), or
+    overlaps the destination (run-length style): the three routes of the LZ77 pass, for every inflate kernel."""
+    rng = random.Random(19)
+    a = bytes(rng.getrandbits(8) for _ in range(5000))
+    b = bytes(rng.getrandbits(8) for _ in range(700))
+    parts = [a, b, a[:3000], bytes(rng.getrandbits(8) for _ in range(40)), b * 3, a[1000:4000],
+             b"xy" * 400, b"q" * 700, a[::-1][:2500], a[200:4900]]
+    for _ in range(200):
+        o = rng.randrange(0, 4500)
+        parts.append(a[o:o + rng.randrange(3, 400)])
+        parts.append(bytes(rng.getrandbits(8) for _ in range(rng.randrange(0, 6))))
+    payload = b"".join(parts)
+    assert 40_000 < len(payload) < 65_000  # a single BGZF block: distances up to 32 KiB stay possible
+    p = tmp_path / "m.bgzf"
+    with open(p, "wb") as fh:
+        w = bamio.BgzfWriter(fh, level=9)
+        w.write(payload, atomic=False)
+        w.close()
+    data = p.read_bytes()
+    for d in ("308", "304", "1", "0"):
+        monkeypatch.setenv("MBF_BAM_INFLATE_D", d)
+        assert mb.inflate_buffer(data) == payload, d
+
+
 def test_inflate_many_windows(mb, tmp_path, monkeypatch):
     monkeypatch.setenv("MBF_BAM_WINDOW_MB", "1")
     rng = random.Random(6)
