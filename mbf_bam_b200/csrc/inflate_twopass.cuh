@@ -140,8 +140,8 @@ struct TokensShared32 {
 
 enum { B_HUFF = 0, B_DONE = 1, B_IDLE = 2, B_HEADER = 3, B_BUILD = 4, B_FIN = 5 };
 
-template <int DL>
-__global__ void __launch_bounds__(32, 24) k_tokens_bf(TokenArgs a) {
+template <int DL, bool PIPE>
+__global__ void __launch_bounds__(32, 16) k_tokens_bf(TokenArgs a) {
     extern __shared__ __align__(16) uint8_t tk_smem[];
     TokensShared32<DL>& S = *reinterpret_cast<TokensShared32<DL>*>(tk_smem);
     const int lane = threadIdx.x;
@@ -178,7 +178,24 @@ __global__ void __launch_bounds__(32, 24) k_tokens_bf(TokenArgs a) {
         // of a trip leads to code that reads the read-ahead register, so nothing waits for its load.
         const unsigned hm = __ballot_sync(0xffffffffu, st == B_HUFF);
         if (st == B_HUFF) {
-            bool leave;
+            // values, token, store of one symbol: nothing here feeds the bit position
+            auto emit_token = [&](uint32_t e, uint32_t w, uint32_t d, uint32_t w2, bool emit) {
+                const bool is_match = (e >> 30) == 1u;
+                const uint32_t val = ((e >> 10) & 0xffffu) + ((w & ~(0xffffffffu << (e & 31u))) >> ((e >> 5) & 15u));
+                const uint32_t dist = ((d >> 10) & 0xffffu) + ((w2 & ~(0xffffffffu << (d & 31u))) >> ((d >> 5) & 15u));
+                const uint32_t token = is_match ? (0x80000000u | (val << 16) | ((dist - 1u) & 0x7fffu)) : val;
+                const uint32_t nout = out_bytes + (is_match ? val : 1u);
+                const bool ok = emit && nout <= isize_b;  // all predicated: no branch region in the common path
+                if (ok) __stcg(tk + ntok, token);         // L2 only: the small L1 beside 220 KB of tables is for the input
+                ntok += ok ? 1u : 0u;
+                out_bytes = ok ? nout : out_bytes;
+                err = (emit && !ok) ? (int)INF_OUTPUT_OVERRUN : err;
+            };
+            // Software pipelined by one trip: the token of trip i-1 is computed and stored in the same basic
+            // block as the two table lookups of trip i, so the (in-order) warp has independent instructions
+            // to issue while the lookups and the bit-position chain wait for their operands.
+            uint32_t pe = 0, pw = 0, pd = 0, pw2 = 0;
+            bool pemit = false, leave;
             do {
                 // ------------------------------------------------------------ one symbol, straight line
                 const uint32_t w = br.window();
@@ -188,6 +205,7 @@ __global__ void __launch_bounds__(32, 24) k_tokens_bf(TokenArgs a) {
                 // distance lookup in every trip; a literal reads its zero word instead (consumes nothing)
                 const bool m0 = (e >> 30) == 1u;
                 uint32_t d = lds_u32((m0 ? s_d : s_zero) + ((w2 << 2) & (m0 ? ((1u << D_ROOT3) - 1) << 2 : 0u)));
+                if (PIPE) emit_token(pe, pw, pd, pw2, pemit);
                 bool emit = true;
                 if ((e | d) >> 31) {
                     // ---- rare: end of block, code longer than the LUT root, invalid code
@@ -201,7 +219,7 @@ __global__ void __launch_bounds__(32, 24) k_tokens_bf(TokenArgs a) {
                     }
                     const uint32_t k2 = e >> 30;
                     if (k2 == 3u) {
-                        err = INF_BAD_SYMBOL;
+                        err = err ? err : (int)INF_BAD_SYMBOL;
                         emit = false;
                     } else if (k2 == 2u) {
                         st = bfinal ? B_FIN : B_HEADER;
@@ -209,26 +227,21 @@ __global__ void __launch_bounds__(32, 24) k_tokens_bf(TokenArgs a) {
                     } else if (k2 == 1u && d >= K_SPECIAL) {
                         d = d == E2_SLOW ? slow_entry_s<true>(s_dhd, s_dsym, w2 & 0x7fffu, D_ROOT3) : E2_INVALID;
                         if (d >= K_SPECIAL) {
-                            err = INF_BAD_DISTANCE;
+                            err = err ? err : (int)INF_BAD_DISTANCE;
                             emit = false;
                         }
                     }
                 }
                 br.bo = bo1 + (d & 31u);  // <= 79
                 br.refill();              // a second step, if ever needed, is made in the rare section below
-                // ---- off the critical path: values, token, store
-                const bool is_match = (e >> 30) == 1u;
-                const uint32_t val = ((e >> 10) & 0xffffu) + ((w & ~(0xffffffffu << (e & 31u))) >> ((e >> 5) & 15u));
-                const uint32_t dist = ((d >> 10) & 0xffffu) + ((w2 & ~(0xffffffffu << (d & 31u))) >> ((d >> 5) & 15u));
-                const uint32_t token = is_match ? (0x80000000u | (val << 16) | ((dist - 1u) & 0x7fffu)) : val;
-                const uint32_t nout = out_bytes + (is_match ? val : 1u);
-                const bool ok = emit && nout <= isize_b;  // all predicated: no branch region in the common path
-                if (ok) __stcg(tk + ntok, token);  // L2 only: the small L1 left beside 220 KB of tables is for the input stream
-                ntok += ok ? 1u : 0u;
-                out_bytes = ok ? nout : out_bytes;
-                err = (emit && !ok) ? (int)INF_OUTPUT_OVERRUN : err;
+                if (PIPE) {
+                    pe = e; pw = w; pd = d; pw2 = w2; pemit = emit;
+                } else {
+                    emit_token(e, w, d, w2, emit);
+                }
                 leave = st != B_HUFF || err != 0 || br.bo >= 32u;
             } while (!__any_sync(hm, leave));
+            if (PIPE) emit_token(pe, pw, pd, pw2, pemit);  // the last trip's token
         }
         __syncwarp();
         if (err) {

@@ -466,9 +466,8 @@ struct Pipeline {
         st.n_bgzf_blocks += m.n_blocks;
         st.uncompressed_bytes += m.u_total;
         st.n_windows++;
-        const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 308);
         w.two_pass = false;
-        cudaStream_t si = (mode_d == 0 || mode_d == 1) ? s_inf[bi] : s_inf[0];  // the two-pass kernels share one token buffer
+        cudaStream_t si = s_inf[bi];  // alternating streams: every per-window buffer of K1 exists twice
         CK(cudaStreamWaitEvent(si, w.ev_front, 0));
         // U[bi] was last read by window k-2 (main stage + its second half); ev_reuse was recorded behind both
         // in the previous iteration of run()
@@ -563,10 +562,12 @@ struct Pipeline {
                     uint32_t grid = std::min<uint32_t>((n_blocks + dl - 1) / dl, (uint32_t)(sm_count * per_sm));
                     kernel<<<grid, 32, smem, si>>>(ta);
                 };
-                if (dl == 16) launch_tokens(k_tokens_bf<16>, (int)sizeof(TokensShared32<16>));
-                else if (dl == 8) launch_tokens(k_tokens_bf<8>, (int)sizeof(TokensShared32<8>));
-                else if (dl == 4) launch_tokens(k_tokens_bf<4>, (int)sizeof(TokensShared32<4>));
-                else launch_tokens(k_tokens_bf<2>, (int)sizeof(TokensShared32<2>));
+                const bool pipe = env_u32("MBF_BAM_TOKENS_PIPE", 1) != 0;  // 0: token emitted in its own trip
+                if (dl == 16) launch_tokens(k_tokens_bf<16, true>, (int)sizeof(TokensShared32<16>));
+                else if (dl == 8 && pipe) launch_tokens(k_tokens_bf<8, true>, (int)sizeof(TokensShared32<8>));
+                else if (dl == 8) launch_tokens(k_tokens_bf<8, false>, (int)sizeof(TokensShared32<8>));
+                else if (dl == 4) launch_tokens(k_tokens_bf<4, true>, (int)sizeof(TokensShared32<4>));
+                else launch_tokens(k_tokens_bf<2, true>, (int)sizeof(TokensShared32<2>));
                 launched("k_tokens_bf", si);
                 CK(cudaEventRecord(w.t[7], si));
                 w.two_pass = true;
