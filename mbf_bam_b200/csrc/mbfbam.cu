@@ -239,7 +239,7 @@ struct Pipeline {
             wbi.in_flight = wbi.timed = false;
             if (mm_env) wbi.mm_cap = 0;  // tests force a tiny key buffer
         }
-        ensure_U((size_t)W * 4);
+        ensure_U(std::min<size_t>((size_t)W * 4, (size_t)3 << 30));
         mode = 0;
         cc = CountCtx{};
         ic = IntronCtx{};
@@ -555,9 +555,11 @@ struct Pipeline {
                 auto launch_tokens = [&](auto kernel, int smem) {
                     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
                     int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
-                    // leaving room beside the persistent decoders lets the other window's resolve pass run
-                    // concurrently (it is issue bound, the decoders are latency bound)
-                    const uint32_t cap = env_u32("MBF_BAM_TOKENS_PER_SM", 0);
+                    // The persistent decoders take about 4/5 of what shared memory allows (9 of 11 CTAs per SM
+                    // with 8 decoders per warp): the rest is room for the other window's resolve pass, scan and
+                    // count kernels to run beside them (the decoders are latency bound and leave issue slots
+                    // free).  Measured on the 50M-read bench: 11 -> 112 ms, 10 -> 110 ms, 9 -> 108 ms per job.
+                    const uint32_t cap = env_u32("MBF_BAM_TOKENS_PER_SM", (uint32_t)std::max(1, per_sm * 9 / 11));
                     if (cap) per_sm = std::min<int>(per_sm, (int)cap);
                     uint32_t grid = std::min<uint32_t>((n_blocks + dl - 1) / dl, (uint32_t)(sm_count * per_sm));
                     kernel<<<grid, 32, smem, si>>>(ta);
@@ -736,40 +738,65 @@ struct Pipeline {
     // ---------------------------------------------------------------- driver
     void run(const std::vector<ByteRange>& ranges) {
         struct Win { uint64_t off; uint32_t scan_len; uint64_t src_end; int range_start; uint64_t range_off; uint32_t first_uoff; };
-        std::vector<Win> wins;
-        // Streamed jobs ramp the window size up (W/8, then x1.5 per window until W): the bytes of window k+1
-        // are staged while the GPU works on window k, so a window must not take longer to stage than its
-        // predecessor takes to process -- a full-size second window would leave the GPU idle for ~10 ms.
+        // Windows are planned one ahead, because their size depends on what the previous ones showed:
+        //  * every job starts with a W/8 window; the inflated size of a window must stay below 4 GiB (32-bit
+        //    offsets into U), so later windows are capped by the largest inflate ratio seen so far;
+        //  * streamed jobs grow x1.5 per window until W: the bytes of window k+1 are staged while the GPU
+        //    works on window k, so a window must not take longer to stage than its predecessor takes to
+        //    process (a full-size second window would leave the GPU idle for ~10 ms).
         const bool ramp = !src->resident(device);
-        uint64_t cur_w = ramp ? std::max<uint64_t>(W / 8, 1u << 20) : W;
-        for (const ByteRange& r : ranges) {
-            uint64_t pos = r.cbeg;
-            bool first = true;
-            while (pos < r.cend) {
-                uint64_t base = pos & ~(uint64_t)15;
-                uint64_t scan_end = std::min<uint64_t>(r.cend, base + cur_w);
-                wins.push_back({base, (uint32_t)(scan_end - base), src->size(), first ? 1 : 0, r.cbeg, first ? r.first_uoff : 0u});
-                first = false;
-                pos = scan_end;
-                cur_w = std::min<uint64_t>(W, cur_w + cur_w / 2);
+        size_t ri = 0;
+        uint64_t pos = ranges.empty() ? 0 : ranges[0].cbeg;
+        bool first_of_range = true;
+        auto next_win = [&](uint64_t cur_w, Win& out) -> bool {
+            while (ri < ranges.size() && pos >= ranges[ri].cend) {
+                ri++;
+                if (ri < ranges.size()) { pos = ranges[ri].cbeg; first_of_range = true; }
             }
-        }
+            if (ri >= ranges.size()) return false;
+            const ByteRange& r = ranges[ri];
+            uint64_t base = pos & ~(uint64_t)15;
+            uint64_t scan_end = std::min<uint64_t>(r.cend, base + cur_w);
+            out = {base, (uint32_t)(scan_end - base), src->size(), first_of_range ? 1 : 0, r.cbeg, first_of_range ? r.first_uoff : 0u};
+            first_of_range = false;
+            pos = scan_end;
+            return true;
+        };
+        uint64_t cur_w = std::max<uint64_t>(W / 8, 1u << 20);
+        double max_ratio = 1.0;
+        // inflated bytes a window may have (MBF_BAM_U_LIMIT_MB exists so that tests can reach the cap)
+        const uint64_t u_limit = (uint64_t)std::min<uint32_t>(env_u32("MBF_BAM_U_LIMIT_MB", 3276), 3276) << 20;
+        Win wk{}, wn{};
+        bool have = next_win(cur_w, wk);
         double t0 = now_ms();
-        if (!wins.empty()) {
-            const Win& w0 = wins[0];
-            stage_front(0, w0.off, w0.scan_len, w0.src_end, w0.range_start, w0.range_off, w0.first_uoff);
+        if (have) {
+            stage_front(0, wk.off, wk.scan_len, wk.src_end, wk.range_start, wk.range_off, wk.first_uoff);
             scan_front(0);
         }
         const bool trace = env_u32("MBF_BAM_TRACE", 0) != 0;
-        for (size_t k = 0; k < wins.size(); k++) {
+        for (size_t k = 0; have; k++) {
             int bi = (int)(k & 1);
             double ta = now_ms();
-            issue_inflate(bi);    // waits for window k's block table; may overlap the tail of window k-1's K1
+            // The host must never wait for the GPU while bytes remain to be staged (the staging rate bounds a
+            // streamed job): from the second window on, window k+1 is staged BEFORE the blocking wait for
+            // window k's block table.  Window 0's K1 is launched first so that the GPU starts at once.
+            if (k == 0) {
+                issue_inflate(bi);
+                if (wk.scan_len) max_ratio = std::max(max_ratio, (double)wb[bi].front_meta.u_total / (double)wk.scan_len);
+            }
             double tb = now_ms();
-            if (k + 1 < wins.size()) {
+            // size of the next window (ratios of the windows whose block tables the host has seen)
+            uint64_t cap = (uint64_t)((double)u_limit / (max_ratio * 1.25));
+            cap = std::max<uint64_t>(cap & ~(uint64_t)0xfffff, 1u << 20);
+            cur_w = std::min<uint64_t>(std::min<uint64_t>(W, cap), ramp ? cur_w + cur_w / 2 : W);
+            const bool have_next = next_win(cur_w, wn);
+            if (have_next) {
                 // bytes of window k+1 (host read + H2D) while the GPU works on windows k-1 / k
-                const Win& wn = wins[k + 1];
                 stage_front(bi ^ 1, wn.off, wn.scan_len, wn.src_end, wn.range_start, wn.range_off, wn.first_uoff);
+            }
+            if (k > 0) {
+                issue_inflate(bi);  // waits for window k's block table; may overlap the tail of window k-1's K1
+                if (wk.scan_len) max_ratio = std::max(max_ratio, (double)wb[bi].front_meta.u_total / (double)wk.scan_len);
             }
             double tc = now_ms();
             finish_main(bi ^ 1);  // second half of window k-1 (must precede window k's carry copy)
@@ -777,10 +804,12 @@ struct Pipeline {
             CK(cudaEventRecord(ev_reuse, s_main));
             double td = now_ms();
             issue_main(bi);
-            if (k + 1 < wins.size()) scan_front(bi ^ 1);
+            if (have_next) scan_front(bi ^ 1);
             if (trace)
                 fprintf(stderr, "[mbfbam] win %zu t=%.2f issue_inflate %.2f ms, stage_next %.2f ms, finish_prev %.2f ms, rest %.2f ms (scan_len %u)\n",
-                        k, ta - t0, tb - ta, tc - tb, td - tc, now_ms() - td, wins[k].scan_len);
+                        k, ta - t0, tb - ta, tc - tb, td - tc, now_ms() - td, wk.scan_len);
+            wk = wn;
+            have = have_next;
         }
         finish_main(0);
         finish_main(1);

@@ -104,6 +104,25 @@ def test_inflate_many_windows(mb, tmp_path, monkeypatch):
     assert mb.last_stats()["n_windows"] >= 3
 
 
+def test_window_size_follows_inflate_ratio(mb, tmp_path, monkeypatch):
+    """Windows are capped so that their inflated size stays below the 32-bit offset limit; with the limit
+    lowered to 4 MiB the file must be cut into more windows and still inflate to the same bytes."""
+    rng = random.Random(21)
+    payload = b"".join(b"%x\t" % rng.getrandbits(24) for _ in range(2_000_000))
+    p = tmp_path / "c.bgzf"
+    with open(p, "wb") as fh:
+        w = bamio.BgzfWriter(fh, level=6)
+        w.write(payload, atomic=False)
+        w.close()
+    data = p.read_bytes()
+    monkeypatch.setenv("MBF_BAM_WINDOW_MB", "16")
+    assert mb.inflate_buffer(data) == payload
+    n_free = mb.last_stats()["n_windows"]
+    monkeypatch.setenv("MBF_BAM_U_LIMIT_MB", "4")
+    assert mb.inflate_buffer(data) == payload
+    assert mb.last_stats()["n_windows"] > n_free
+
+
 def test_inflate_rejects_corruption(mb, tmp_path):
     path, *_ = make_case(tmp_path, 13, n_reads=3000)
     data = bytearray(open(path, "rb").read())
