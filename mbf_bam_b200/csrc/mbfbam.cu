@@ -788,7 +788,8 @@ struct Pipeline {
             // size of the next window (ratios of the windows whose block tables the host has seen)
             uint64_t cap = (uint64_t)((double)u_limit / (max_ratio * 1.25));
             cap = std::max<uint64_t>(cap & ~(uint64_t)0xfffff, 1u << 20);
-            cur_w = std::min<uint64_t>(std::min<uint64_t>(W, cap), ramp ? cur_w + cur_w / 2 : W);
+            const uint64_t grow_pct = env_u32("MBF_BAM_RAMP_PCT", 150);
+            cur_w = std::min<uint64_t>(std::min<uint64_t>(W, cap), ramp ? cur_w * grow_pct / 100 : W);
             const bool have_next = next_win(cur_w, wn);
             if (have_next) {
                 // bytes of window k+1 (host read + H2D) while the GPU works on windows k-1 / k
