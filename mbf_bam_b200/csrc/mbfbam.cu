@@ -762,7 +762,7 @@ struct Pipeline {
             pos = scan_end;
             return true;
         };
-        uint64_t cur_w = std::max<uint64_t>(W / 8, 1u << 20);
+        uint64_t cur_w = std::max<uint64_t>(W / std::max<uint32_t>(1, env_u32("MBF_BAM_FIRST_WINDOW_DIV", 8)), 1u << 20);
         double max_ratio = 1.0;
         // inflated bytes a window may have (MBF_BAM_U_LIMIT_MB exists so that tests can reach the cap)
         const uint64_t u_limit = (uint64_t)std::min<uint32_t>(env_u32("MBF_BAM_U_LIMIT_MB", 3276), 3276) << 20;
