@@ -38,7 +38,30 @@ struct RefIndex {
     bool has_reads = false;
     uint64_t voff_beg = 0, voff_end = 0;           // over all real bins
     std::vector<uint64_t> ioffset;                 // 16 kb linear index
-    std::vector<std::pair<uint32_t, std::pair<uint64_t, uint64_t>>> bins;  // bin -> (min beg, max end)
+    // bin -> (min beg, max end).  Filled at open only when the index lacks the samtools metadata pseudo-bin;
+    // otherwise on first use (voff_upper of a range that ends inside the contig), from the mapped index.
+    mutable std::vector<std::pair<uint32_t, std::pair<uint64_t, uint64_t>>> bins;
+    mutable bool bins_parsed = false;
+    const uint8_t* bins_raw = nullptr;             // first bin record of this reference in the mapped .bai
+    size_t bins_raw_len = 0;
+    int32_t n_bin = 0;
+};
+
+// the mapped .bai (kept for the life of the reader: a 50 M-read file has a 10 MB index, and walking all of
+// its chunk lists on every open costs more than everything else the open does)
+struct BaiMap {
+    const uint8_t* p = nullptr;
+    size_t n = 0;
+    int fd = -1;
+    BaiMap() = default;
+    BaiMap(const BaiMap&) = delete;
+    BaiMap& operator=(const BaiMap&) = delete;
+    ~BaiMap() {
+        if (p && n) munmap((void*)p, n);
+        if (fd >= 0) ::close(fd);
+    }
+    const uint8_t* data() const { return p; }
+    size_t size() const { return n; }
 };
 
 struct Reader {
@@ -159,19 +182,37 @@ struct Reader {
         }
     }
 
-    void parse_bai(const std::string& bp) {
-        // the index is mapped, not copied: a 50 M-read file has a 10 MB .bai and this runs on every open
-        struct Map {
-            const uint8_t* p = nullptr;
-            size_t n = 0;
-            int fd = -1;
-            ~Map() {
-                if (p && n) munmap((void*)p, n);
-                if (fd >= 0) ::close(fd);
+    BaiMap bai;
+
+    // (min chunk begin, max chunk end) of every real bin of one reference, from its raw records
+    static void parse_bins(const RefIndex& ri) {
+        if (ri.bins_parsed) return;
+        ri.bins.clear();
+        ri.bins.reserve((size_t)std::max(0, ri.n_bin));
+        const uint8_t* q = ri.bins_raw;
+        for (int32_t i = 0; i < ri.n_bin; i++) {  // bounds were checked when the index was walked at open
+            uint32_t bin;
+            int32_t n_chunk;
+            memcpy(&bin, q, 4);
+            memcpy(&n_chunk, q + 4, 4);
+            q += 8;
+            if (bin != 37450 && n_chunk > 0) {
+                uint64_t bmn = UINT64_MAX, bmx = 0;
+                for (int32_t c = 0; c < n_chunk; c++) {
+                    uint64_t be[2];
+                    memcpy(be, q + 16 * (size_t)c, 16);
+                    bmn = std::min(bmn, be[0]);
+                    bmx = std::max(bmx, be[1]);
+                }
+                ri.bins.push_back({bin, {bmn, bmx}});
             }
-            const uint8_t* data() const { return p; }
-            size_t size() const { return n; }
-        } d;
+            q += 16 * (size_t)n_chunk;
+        }
+        ri.bins_parsed = true;
+    }
+
+    void parse_bai(const std::string& bp) {
+        BaiMap& d = bai;
         d.fd = ::open(bp.c_str(), O_RDONLY);
         if (d.fd < 0) throw Error(MBFBAM_ERR_IO, "Could not read bam: no index " + bp);
         {
@@ -179,7 +220,7 @@ struct Reader {
             if (fstat(d.fd, &sb) != 0) throw Error(MBFBAM_ERR_IO, "Could not read bam: cannot stat index " + bp);
             d.n = (size_t)sb.st_size;
             if (d.n) {
-                void* m = mmap(nullptr, d.n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, d.fd, 0);
+                void* m = mmap(nullptr, d.n, PROT_READ, MAP_PRIVATE, d.fd, 0);
                 if (m == MAP_FAILED) {
                     d.n = 0;
                     throw Error(MBFBAM_ERR_IO, "Could not read bam: cannot map index " + bp);
@@ -201,41 +242,51 @@ struct Reader {
         idx.assign(names.size(), RefIndex());
         for (int32_t r = 0; r < n_ref; r++) {
             RefIndex ri;
-            int32_t n_bin;
-            take(&n_bin, 4);
-            if (n_bin > 0 && (size_t)n_bin * 8 <= d.size() - p) ri.bins.reserve((size_t)n_bin);
-            uint64_t mn = UINT64_MAX, mx = 0;
-            for (int32_t i = 0; i < n_bin; i++) {
+            take(&ri.n_bin, 4);
+            if (ri.n_bin < 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: bad index " + bp);
+            ri.bins_raw = d.data() + p;
+            // walk the bin headers only; the metadata pseudo-bin (37450, written by samtools/htslib) holds the
+            // virtual offsets of the reference's first and last record
+            bool meta = false, real = false;
+            for (int32_t i = 0; i < ri.n_bin; i++) {
                 uint32_t bin;
                 int32_t n_chunk;
                 take(&bin, 4);
                 take(&n_chunk, 4);
-                uint64_t bmn = UINT64_MAX, bmx = 0;
                 if (n_chunk < 0 || p + 16 * (size_t)n_chunk > d.size())
                     throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: truncated index " + bp);
-                if (bin != 37450) {
-                    const uint8_t* q = d.data() + p;  // one bounds check per bin: this loop sees every chunk of the index
-                    for (int32_t c = 0; c < n_chunk; c++, q += 16) {
+                if (bin == 37450) {
+                    if (n_chunk >= 1) {
                         uint64_t be[2];
-                        memcpy(be, q, 16);
-                        bmn = std::min(bmn, be[0]);
-                        bmx = std::max(bmx, be[1]);
+                        memcpy(be, d.data() + p, 16);
+                        ri.voff_beg = be[0];
+                        ri.voff_end = be[1];
+                        meta = true;
                     }
+                } else if (n_chunk > 0) {
+                    real = true;
                 }
                 p += 16 * (size_t)n_chunk;
-                if (bin != 37450 && n_chunk > 0) {
-                    ri.bins.push_back({bin, {bmn, bmx}});
-                    mn = std::min(mn, bmn);
-                    mx = std::max(mx, bmx);
-                }
             }
+            ri.bins_raw_len = (size_t)(d.data() + p - ri.bins_raw);
             int32_t n_intv;
             take(&n_intv, 4);
             ri.ioffset.resize((size_t)std::max(0, n_intv));
             if (n_intv > 0) take(ri.ioffset.data(), 8 * (size_t)n_intv);
-            ri.has_reads = mn != UINT64_MAX;
-            ri.voff_beg = ri.has_reads ? mn : 0;
-            ri.voff_end = mx;
+            if (meta && real && ri.voff_end > ri.voff_beg) {
+                ri.has_reads = true;
+            } else {
+                // no (usable) pseudo-bin: the offsets come from the chunk lists
+                parse_bins(ri);
+                uint64_t mn = UINT64_MAX, mx = 0;
+                for (const auto& b : ri.bins) {
+                    mn = std::min(mn, b.second.first);
+                    mx = std::max(mx, b.second.second);
+                }
+                ri.has_reads = mn != UINT64_MAX;
+                ri.voff_beg = ri.has_reads ? mn : 0;
+                ri.voff_end = mx;
+            }
             if ((size_t)r < idx.size()) idx[(size_t)r] = std::move(ri);
         }
     }
@@ -257,6 +308,7 @@ struct Reader {
         uint64_t mx = 0;
         static const uint32_t lvl_off[6] = {0, 1, 9, 73, 585, 4681};
         static const int lvl_shift[6] = {29, 26, 23, 20, 17, 14};
+        parse_bins(ri);
         for (const auto& b : ri.bins) {
             int l = 5;
             while (l > 0 && b.first < lvl_off[l]) l--;

@@ -77,6 +77,48 @@ def test_chunk_table_matches_oracle(built, tmp_path):
         assert [tuple(c) for c in rd.chunks(sub)] == c_oracle.chunks(path, None, sub)
 
 
+def _strip_pseudo_bins(bai: bytes) -> bytes:
+    """the same index without the samtools metadata bin 37450"""
+    import struct
+
+    out = bytearray(bai[:8])
+    p = 8
+    (n_ref,) = struct.unpack_from("<i", bai, 4)
+    for _ in range(n_ref):
+        (n_bin,) = struct.unpack_from("<i", bai, p)
+        p += 4
+        kept = []
+        for _ in range(n_bin):
+            b, n_chunk = struct.unpack_from("<Ii", bai, p)
+            rec = bai[p:p + 8 + 16 * n_chunk]
+            p += len(rec)
+            if b != 37450:
+                kept.append(rec)
+        out += struct.pack("<i", len(kept)) + b"".join(kept)
+        (n_intv,) = struct.unpack_from("<i", bai, p)
+        out += bai[p:p + 4 + 8 * n_intv]
+        p += 4 + 8 * n_intv
+    return bytes(out + bai[p:])
+
+
+def test_shard_plan_same_with_and_without_metadata_bin(built, tmp_path):
+    """Reference begin/end offsets come from the metadata pseudo-bin when the index has one and from the chunk
+    lists otherwise; the byte ranges planned from both must be identical (whole file and mid-contig cuts)."""
+    import mbf_bam_b200 as mb
+
+    path, contigs, recs, iv, giv = make_case(tmp_path, 31, n_reads=20_000, n_contigs=5)
+    bai = open(path + ".bai", "rb").read()
+    stripped = _strip_pseudo_bins(bai)
+    assert len(stripped) < len(bai)
+    alt = str(tmp_path / "nometa.bai")
+    open(alt, "wb").write(stripped)
+    a, b = mb.Reader(path), mb.Reader(path, alt)
+    for n in (1, 2, 3, 7):
+        for i in range(n):
+            assert a.plan(giv, i, n) == b.plan(giv, i, n), (i, n)
+    assert a.chunks(giv) == b.chunks(giv)
+
+
 def test_no_cpu_fallback(built, has_gpu, tmp_path):
     """Without a CUDA device every compute entry point must fail loudly."""
     if has_gpu:
