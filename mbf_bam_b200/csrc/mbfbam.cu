@@ -19,6 +19,7 @@
 #include <thread>
 #include <map>
 #include <memory>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -135,6 +136,7 @@ struct WinBufs {
     uint64_t win_off = 0;
     uint32_t scan_len = 0, avail = 0;
     cudaEvent_t ev_front = nullptr, ev_main = nullptr, ev_inf = nullptr;
+    cudaEvent_t ev_cfree = nullptr;  // the compressed bytes of this window are no longer read (pass 1 of K1 is done)
     cudaEvent_t t[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     WinMeta front_meta{};
     bool timed = false;
@@ -207,6 +209,7 @@ struct Pipeline {
             CK(cudaEventCreateWithFlags(&w.ev_front, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&w.ev_main, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&w.ev_inf, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&w.ev_cfree, cudaEventDisableTiming));
             for (auto& t : w.t) CK(cudaEventCreate(&t));
         }
     }
@@ -260,6 +263,7 @@ struct Pipeline {
             if (w.ev_front) cudaEventDestroy(w.ev_front);
             if (w.ev_main) cudaEventDestroy(w.ev_main);
             if (w.ev_inf) cudaEventDestroy(w.ev_inf);
+            if (w.ev_cfree) cudaEventDestroy(w.ev_cfree);
             for (auto& t : w.t) if (t) cudaEventDestroy(t);
         }
         if (ev_reuse) cudaEventDestroy(ev_reuse);
@@ -305,7 +309,7 @@ struct Pipeline {
     void stage_front(int bi, uint64_t win_off, uint32_t scan_len, uint64_t src_end, int range_start,
                      uint64_t range_off, uint32_t first_uoff) {
         WinBufs& w = wb[bi];
-        CK(cudaStreamWaitEvent(s_front, w.ev_inf, 0));
+        CK(cudaStreamWaitEvent(s_front, w.ev_cfree, 0));  // the previous user of this C buffer: pass 1 of window k-2
         uint64_t want = (uint64_t)scan_len + 65536 + 64;
         uint64_t avail = std::min<uint64_t>(want, src_end - win_off);
         w.win_off = win_off;
@@ -476,6 +480,7 @@ struct Pipeline {
         CK(cudaEventRecord(w.t[2], si));
         if (m.n_blocks) launch_inflate(w, b, bi, m.n_blocks, si);
         CK(cudaEventRecord(w.t[3], si));
+        if (!w.two_pass) CK(cudaEventRecord(w.ev_cfree, si));
         CK(cudaEventRecord(w.ev_inf, si));
     }
 
@@ -572,6 +577,7 @@ struct Pipeline {
                 else launch_tokens(k_tokens_bf<2, true>, (int)sizeof(TokensShared32<2>));
                 launched("k_tokens_bf", si);
                 CK(cudaEventRecord(w.t[7], si));
+                CK(cudaEventRecord(w.ev_cfree, si));  // pass 2 reads tokens only: the next H2D into this buffer may start
                 w.two_pass = true;
                 ResolveArgs ra{tokb.as<uint32_t>(), ntokb.as<uint32_t>(), b.isize, b.uoff, U_PREFIX, U[bi].as<uint8_t>(),
                                &dmeta(bi)->n_blocks, &dmeta(bi)->err, &dmeta(bi)->err_info};
@@ -762,6 +768,34 @@ struct Pipeline {
             pos = scan_end;
             return true;
         };
+        // one helper thread at a time; joined (and its exception rethrown) before anything depends on it, and
+        // on every way out of this function
+        struct Stager {
+            std::thread th;
+            std::exception_ptr err;
+            void start(std::function<void()> f, int dev) {
+                join();
+                th = std::thread([this, f, dev] {
+                    try {
+                        CK(cudaSetDevice(dev));  // the current device is per thread
+                        f();
+                    } catch (...) {
+                        err = std::current_exception();
+                    }
+                });
+            }
+            void join() {
+                if (th.joinable()) th.join();
+                if (err) {
+                    std::exception_ptr e = err;
+                    err = nullptr;
+                    std::rethrow_exception(e);
+                }
+            }
+            ~Stager() {
+                if (th.joinable()) th.join();
+            }
+        } stager;
         uint64_t cur_w = std::max<uint64_t>(W / std::max<uint32_t>(1, env_u32("MBF_BAM_FIRST_WINDOW_DIV", 8)), 1u << 20);
         double max_ratio = 1.0;
         // inflated bytes a window may have (MBF_BAM_U_LIMIT_MB exists so that tests can reach the cap)
@@ -792,8 +826,12 @@ struct Pipeline {
             cur_w = std::min<uint64_t>(std::min<uint64_t>(W, cap), ramp ? cur_w * grow_pct / 100 : W);
             const bool have_next = next_win(cur_w, wn);
             if (have_next) {
-                // bytes of window k+1 (host read + H2D) while the GPU works on windows k-1 / k
-                stage_front(bi ^ 1, wn.off, wn.scan_len, wn.src_end, wn.range_start, wn.range_off, wn.first_uoff);
+                // bytes of window k+1 (host read + H2D) while the GPU works on windows k-1 / k -- on a helper
+                // thread, so that this thread can launch K1 of window k the moment its block table is ready
+                // instead of after the 10 ms the host copy of 512 MiB takes
+                stager.start([this, bi, wn] {
+                    stage_front(bi ^ 1, wn.off, wn.scan_len, wn.src_end, wn.range_start, wn.range_off, wn.first_uoff);
+                }, device);
             }
             if (k > 0) {
                 issue_inflate(bi);  // waits for window k's block table; may overlap the tail of window k-1's K1
@@ -805,6 +843,7 @@ struct Pipeline {
             CK(cudaEventRecord(ev_reuse, s_main));
             double td = now_ms();
             issue_main(bi);
+            stager.join();  // window k+1's copies are queued on s_front: its scan may follow them
             if (have_next) scan_front(bi ^ 1);
             if (trace)
                 fprintf(stderr, "[mbfbam] win %zu t=%.2f issue_inflate %.2f ms, stage_next %.2f ms, finish_prev %.2f ms, rest %.2f ms (scan_len %u)\n",
