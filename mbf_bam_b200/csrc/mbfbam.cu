@@ -394,7 +394,7 @@ struct Pipeline {
         uint8_t* h = w.h_c.as<uint8_t>();
         const size_t PIECE = 8u << 20;
         const size_t n_pieces = (avail + PIECE - 1) / PIECE;
-        int n_threads = (int)env_u32("MBF_BAM_READ_THREADS", std::min(16u, std::max(2u, std::thread::hardware_concurrency())));
+        int n_threads = (int)env_u32("MBF_BAM_READ_THREADS", std::min(16u, std::max(2u, std::thread::hardware_concurrency() * 3 / 4)));
         n_threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, n_pieces));
         if (n_pieces <= 1 || n_threads <= 1) {
             src->read(win_off, avail, h);
