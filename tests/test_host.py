@@ -119,6 +119,59 @@ def test_shard_plan_same_with_and_without_metadata_bin(built, tmp_path):
     assert a.chunks(giv) == b.chunks(giv)
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_result_dict_assembly_matches_oracle(built, tmp_path, seed):
+    """Dense count vectors -> the reference's dict layout (counters.rs:236-254 `insert` per contig, :262-273 `+=`,
+    :309-314 `_outside` only forward): gene ids duplicated within and across contigs, ids that collide with the
+    special keys, unscanned contigs.  Host-only, so it runs without a GPU."""
+    import random
+
+    import numpy as np
+
+    import mbf_bam_b200 as mb
+    from oracle import c_oracle
+
+    rng = random.Random(seed)
+    path, contigs, recs, iv0, giv0 = make_case(tmp_path, 40 + seed, n_reads=200, n_contigs=4)
+    names = [c for c, _ in contigs]
+    pool = ["g%d" % i for i in range(12)] + ["_total", "_outside", "_" + names[0]]
+    iv = {c: [(rng.choice(pool), rng.choice([1, -1]), [10 * k], [10 * k + 5]) for k in range(rng.randrange(1, 9))]
+          for c in names}
+    G = sum(len(v) for v in iv.values())
+    fwd = np.array([rng.randrange(0, 1000) for _ in range(G)], dtype=np.uint64)
+    rev = np.array([rng.randrange(0, 1000) for _ in range(G)], dtype=np.uint64)
+    wf = np.array([rng.random() * 10 for _ in range(G)], dtype=np.float64)
+    wr = np.array([rng.random() * 10 for _ in range(G)], dtype=np.float64)
+    scanned = np.array([rng.random() < 0.8 for _ in names], dtype=np.uint8)
+    outside = rng.randrange(0, 10 ** 6)
+    rd = mb.Reader(path)
+    args = (iv, fwd.tobytes(), rev.tobytes(), wf.tobytes(), wr.tobytes(), scanned.tobytes(), outside)
+    r = dict(names=names, gene_ids=[[t[0] for t in iv[c]] for c in names], scanned=scanned, fwd=fwd, rev=rev,
+             wfwd=wf, wrev=wr, outside=outside)
+    assert rd.assemble(0, *args) == c_oracle._assemble_unstranded(r)
+    assert tuple(rd.assemble(1, *args)) == c_oracle._assemble_dual(r, "fwd", "rev", int)
+    got = rd.assemble(2, *args)
+    want = c_oracle._assemble_dual(r, "wfwd", "wrev", float)
+    for a, b in zip(got, want):
+        assert set(a) == set(b)
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-9 * max(1.0, abs(b[k])), k
+
+
+def test_interval_dict_errors_are_value_errors(built, tmp_path):
+    """Malformed interval dicts raise ValueError (lib.rs:118-134 extraction errors), never crash."""
+    import mbf_bam_b200 as mb
+
+    path, contigs, recs, iv, giv = make_case(tmp_path, 44, n_reads=200)
+    rd = mb.Reader(path)
+    c = contigs[0][0]
+    for bad in ({c: "nope"}, {c: [("g", 1, [1])]}, {c: [("g", 1, [1], 5)]}, {c: [("g", "x", [1], [2])]},
+                {c: [("g", 1, [-1], [2])]}, {c: [("g", 1, [1], [2 ** 33])]}, {c: [(5, 1, [1], [2])]}, {7: []},
+                {c: [("g", 300, [1], [2])]}, {c: [["g", 1, [1], [2]]]}):
+        with pytest.raises(ValueError):
+            rd.plan(bad, 0, 1)
+
+
 def test_no_cpu_fallback(built, has_gpu, tmp_path):
     """Without a CUDA device every compute entry point must fail loudly."""
     if has_gpu:
