@@ -1,14 +1,15 @@
 // sm_100a kernels of the read-counting path.  One "window" = a slice of the BGZF file resident
 // in HBM; per window the launch sequence is
-//   k_win_begin -> k_scan_count -> k_excl_scan -> k_scan_emit -> k_blocks_finalize -> k_excl_scan
-//   -> k_inflate -> k_carry_copy -> k_frame_walk<false> -> k_frame_fix -> k_excl_scan
-//   -> k_frame_walk<true> -> k_count_reads<MODE> | k_count_introns -> k_mm_insert
+//   k_win_begin -> k_scan<count> -> k_excl_scan -> k_scan<emit> -> k_blocks_finalize -> k_excl_scan
+//   -> k_tokens_bf -> k_lz_resolve   (inflate_twopass.cuh; or the one-pass k_inflate_batched / k_inflate)
+//   -> k_frame_walk<count> -> k_frame_fix -> k_excl_scan -> k_frame_walk<emit> -> k_carry_copy
+//   -> k_count_reads<MODE> | k_count_introns -> k_mm_insert
 // Everything reads its sizes from a device-resident WinMeta, so the host never has to wait for a
 // kernel before it can enqueue the next one (it reads WinMeta only for capacity decisions).
 //
 // Reference behaviour replaced (paths relative to the reference tree):
 //   k_scan_*/k_blocks_finalize  htslib bgzf block iteration under bam.fetch/read (counters.rs:40-41)
-//   k_inflate                   zlib inflate in htslib bgzf_read_block
+//   k_tokens_bf + k_lz_resolve  zlib inflate in htslib bgzf_read_block (also k_inflate_batched, k_inflate)
 //   k_frame_walk                htslib bam_read1 record framing
 //   k_count_reads               count_reads_in_region_{unstranded,stranded} (counters.rs:26-202),
 //                               BamRecordExtensions::blocks (bam_ext.rs:29-34), Record::aux(b"NH"),

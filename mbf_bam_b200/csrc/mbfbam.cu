@@ -3,12 +3,13 @@
 // Per job the host plans BGZF byte ranges from the BAI, then streams them through the GPU in
 // windows of W compressed bytes:
 //
-//   front stage (stream s_front):  H2D copy (or a view into the preloaded file) -> K0 block scan
-//                                  -> chain proof -> ISIZE scan -> WinMeta to the host
-//   main stage  (stream s_main):   K1 inflate -> K2 frame -> carry -> K3-5 count | K6 introns
+//   front stage (stream s_front):    host copy on a helper thread -> H2D (or a view into the preloaded
+//                                    file) -> K0 block scan -> chain proof -> ISIZE scan -> WinMeta to the host
+//   inflate     (streams s_inf[k%2]): K1 pass 1 (tokens) -> pass 2 (LZ77); consecutive windows alternate streams
+//   main stage  (stream s_main):     K2 frame -> carry -> K3-5 count | K6 introns
 //
-// Window k+1's front stage runs while window k's main stage is executing.  All per-window device
-// arrays are double buffered.  The host reads WinMeta only to size buffers (U, record offsets, the
+// Window k+1's front stage and window k+1's K1 run while window k's K1 / main stage are executing.  All
+// per-window device arrays are double buffered.  The host reads WinMeta only to size buffers (U, record offsets, the
 // multi-mapper set, the intron map); it never touches alignment data.
 #include <cuda_runtime.h>
 #include <stdarg.h>
