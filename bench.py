@@ -277,7 +277,9 @@ def main():
     # ---- same with the file mapping page-locked once per reader (mbfbam_pin_file): extra information only
     pin_total = None
     try:
-        if rd.pin_file():
+        # single-GPU runs only: with N ranks every rank would page-lock the whole N x 3 GB file for a figure that
+        # is extra information
+        if dist is None and rd.pin_file():
             pinned_mode[0] = True
             pin_total, _, pin_last, _ = timed(False, args.steps, 1)
             pinned_mode[0] = False
