@@ -46,8 +46,10 @@ struct TokenArgs {
     unsigned long long* n_tokens;  // statistics (may be null)
 };
 
+// first error wins; the failed member gets an empty token list, so pass 2 never walks stale tokens for it
 __device__ __forceinline__ void tok_err(const TokenArgs& a, uint32_t code, uint32_t info) {
     if (atomicCAS(a.err, 0u, code) == 0u) *a.err_info = info;
+    a.ntok[info] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -252,9 +254,9 @@ __global__ void __launch_bounds__(32, 16) k_tokens_bf(TokenArgs a) {
         // ---------------------------------------------------------------- rare work, lane by lane
         while (br.bo >= 32u) br.refill();  // a trip that consumed more than 32 bits
         if (st == B_FIN) {
+            a.ntok[b] = ntok;
             if (out_bytes != isize_b) tok_err(a, WERR_INFLATE + (uint32_t)INF_SIZE_MISMATCH, b);
             else if (br.bytes_consumed(mis) > clen_b) tok_err(a, WERR_INFLATE + (uint32_t)INF_INPUT_OVERRUN, b);
-            a.ntok[b] = ntok;
             if (a.n_tokens) atomicAdd(a.n_tokens, (unsigned long long)ntok);
             st = B_IDLE;
         }
