@@ -12,9 +12,9 @@ namespace mbf {
 struct LinearOut {
     uint8_t* base;
     uint32_t pos, cap;
-    bool want_flush() const { return pos + 258 > cap; }  // treat "no room" as an error upstream
-    void put(uint8_t b) { base[pos++] = b; }
-    bool copy(uint32_t dist, uint32_t len) {
+    MBF_HD bool want_flush() const { return pos + 258 > cap; }  // treat "no room" as an error upstream
+    MBF_HD void put(uint8_t b) { base[pos++] = b; }
+    MBF_HD bool copy(uint32_t dist, uint32_t len) {
         if (dist > pos) return false;
         for (uint32_t i = 0; i < len; i++) base[pos + i] = base[pos - dist + i];
         pos += len;
