@@ -134,6 +134,26 @@ def test_inflate_rejects_corruption(mb, tmp_path):
         mb.inflate_buffer(bytes(data))
 
 
+def test_read_error_on_the_staging_thread_is_a_value_error(mb, tmp_path, monkeypatch):
+    """The bytes of window k+1 are read on a helper thread: a file that shrinks under the reader must surface as
+    ValueError from the call, and the reader/pipeline must stay usable afterwards."""
+    monkeypatch.setenv("MBF_BAM_WINDOW_MB", "4")  # windows of 1, 1.5, 2.25 MiB: all but the first go through the helper thread
+    path, contigs, recs, iv, giv = make_case(tmp_path, 23, n_reads=60_000, random_seq=True)
+    size = os.path.getsize(path)
+    assert size > 3 * (1 << 20)
+    want = c_oracle.count_reads_stranded(path, None, iv, giv)
+    rd = mb.Reader(path)
+    assert tuple(rd.count_reads(1, iv, giv)) == want
+    data = open(path, "rb").read()
+    with open(path, "r+b") as fh:
+        fh.truncate(size // 2)
+    with pytest.raises(ValueError, match="Could not read bam"):
+        rd.count_reads(1, iv, giv)
+    with open(path, "wb") as fh:
+        fh.write(data)
+    assert tuple(rd.count_reads(1, iv, giv)) == want
+
+
 # ------------------------------------------------------------------------------------------------ K3
 @pytest.mark.parametrize("g", GOLDEN, ids=lambda g: "%d_%s" % (g["index"], g["cigar"]))
 def test_cigar_golden_on_device(mb, g):
