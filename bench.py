@@ -112,9 +112,36 @@ def ensure_bam(workdir, reads_total, rank, world, barrier):
     intervals, gene_intervals, genes = model.make_gene_model(c["contigs"], c["n_genes"], c["seed"], gene_mode=False,
                                                              span=c["span"], mean_exons=4.6)
     level = env_int("MBF_BENCH_LEVEL", 6)
-    path = os.path.join(workdir, "cfg2_%dM_l%d.bam" % (reads_total // 1_000_000, level))
+    name = "cfg2_%dM_l%d.bam" % (reads_total // 1_000_000, level)
+
+    def complete(p):
+        return os.path.exists(p) and os.path.exists(p + ".bai") and os.path.exists(p + ".ok")
+
+    # Where the synthetic file lives: the given directory, else the first of /tmp, /dev/shm, the repo with room for
+    # it (N x 3.2 GB at N GPUs).  Rank 0 decides and leaves a note; the other ranks read it after the barrier.
+    note = os.path.join("/tmp", "mbf_bench_%s.where" % name)
+    if rank == 0:
+        cands = [workdir] if workdir else ["/tmp/mbf_bench", "/dev/shm/mbf_bench", os.path.join(ROOT, ".bench")]
+        need = int(reads_total * 70 * 1.1)
+        chosen = next((d for d in cands if complete(os.path.join(d, name))), None)
+        if chosen is None:
+            for d in cands:
+                try:
+                    os.makedirs(d, exist_ok=True)
+                    sv = os.statvfs(d)
+                    if sv.f_bavail * sv.f_frsize >= need:
+                        chosen = d
+                        break
+                except OSError:
+                    continue
+        if chosen is None:
+            chosen = cands[0]
+        with open(note, "w") as fh:
+            fh.write(chosen)
+        workdir = chosen
     t_gen = 0.0
-    if rank == 0 and not (os.path.exists(path) and os.path.exists(path + ".bai") and os.path.exists(path + ".ok")):
+    path = os.path.join(workdir or "/tmp/mbf_bench", name)
+    if rank == 0 and not complete(path):
         os.makedirs(workdir, exist_ok=True)
         t0 = time.time()
         info = model.generate_bam(path, c["contigs"], genes, reads_total, c["seed"], readlen=c["readlen"], level=level,
@@ -122,6 +149,8 @@ def ensure_bam(workdir, reads_total, rank, world, barrier):
         t_gen = time.time() - t0
         open(path + ".ok", "w").write(json.dumps(info))
     barrier()
+    if rank != 0:
+        path = os.path.join(open(note).read().strip(), name)
     info = json.load(open(path + ".ok"))
     return path, intervals, gene_intervals, info, t_gen
 
@@ -142,7 +171,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=env_int("MBF_BENCH_READS", 50_000_000), help="reads per GPU")
-    ap.add_argument("--workdir", default=os.environ.get("MBF_BENCH_DIR", "/tmp/mbf_bench"))
+    ap.add_argument("--workdir", default=os.environ.get("MBF_BENCH_DIR"),
+                    help="directory of the synthetic BAM (default: /tmp, /dev/shm or the repo, whichever has room)")
     args = ap.parse_args()
     rank, world, local = dist_env()
     if world != args.gpus and world > 1:
