@@ -69,6 +69,7 @@ int32_t mbfbam_n_targets(const mbfbam_reader* r);
 const char* mbfbam_target_name(const mbfbam_reader* r, int32_t tid);
 uint32_t mbfbam_target_len(const mbfbam_reader* r, int32_t tid);
 int32_t mbfbam_tid(const mbfbam_reader* r, const char* name); /* -1 if absent */
+uint64_t mbfbam_file_size(const mbfbam_reader* r);
 
 /* Optional: copy the compressed BGZF byte ranges of the whole file into HBM of
  * `device` once, so later count calls on that device start from device-resident
@@ -76,13 +77,20 @@ int32_t mbfbam_tid(const mbfbam_reader* r, const char* name); /* -1 if absent */
 int mbfbam_preload(mbfbam_reader* r, int32_t device, char* err, size_t errlen);
 void mbfbam_drop_preload(mbfbam_reader* r);
 
-/* Optional: map the file and page-lock the mapping (cudaHostRegister), so that the streamed path
- * copies host -> device straight from the page cache instead of through pread + pinned staging
- * buffers.  Pays off when one reader serves several calls (the count_reads_* suite on one BAM).
- * Returns MBFBAM_ERR_UNSUPPORTED when the platform refuses to register the mapping; the reader keeps
- * working through the staging path. */
+/* Host side of the ingest (replaces the hFILE reads under htslib's bgzf_read_block).  The library keeps a
+ * process-wide cache of private file mappings keyed by (device, inode, size, mtime); jobs copy out of the
+ * mapping into pinned staging buffers with a few threads.  Once MBF_BAM_PIN_AFTER (default 3; "never")
+ * jobs have streamed a file, the byte ranges a job touches are page-locked (cudaHostRegister, 64 MiB
+ * segments, at most MBF_BAM_PIN_MAX_MB, default half of RAM) and later jobs DMA straight out of the page
+ * cache.  mbfbam_pin_file page-locks the whole file now (MBFBAM_ERR_UNSUPPORTED when the platform refuses;
+ * the reader keeps working through the staging path); mbfbam_unpin_file releases the page locks of this
+ * file (no job may be running on it); mbfbam_host_cache_clear drops every cached mapping. */
 int mbfbam_pin_file(mbfbam_reader* r, char* err, size_t errlen);
 void mbfbam_unpin_file(mbfbam_reader* r);
+void mbfbam_host_cache_clear(void);
+/* The library keeps one pipeline (streams, device and pinned buffers, sized by the largest job so far) per
+ * device between calls; this frees the one of `device` (it is rebuilt by the next job). */
+void mbfbam_release_device(int32_t device);
 
 /* Per-call measurements (all optional output; zeroed by the library first). */
 typedef struct mbfbam_stats {
@@ -104,20 +112,28 @@ typedef struct mbfbam_stats {
     double ms_gpu_frame;
     double ms_gpu_count;
     double ms_gpu_other;
-    double ms_gpu_all;           /* first kernel start -> last kernel end               */
+    double ms_gpu_all;           /* first copy/kernel start -> last kernel end (CUDA events) */
     double ms_gpu_tokens;        /* pass 1 of the two-pass inflate (part of ms_gpu_inflate) */
     uint64_t n_tokens;           /* DEFLATE symbols (literals + matches) decoded by pass 1  */
+    uint64_t h2d_pinned_bytes;   /* part of h2d_bytes that went by DMA from the page-locked file mapping */
+    uint64_t n_devices;          /* devices that worked on the call                     */
+    uint64_t n_retries;          /* job restarts with smaller windows (inflate ratio jump) */
+    double ms_pin;               /* time spent page-locking file segments in this call  */
 } mbfbam_stats;
+/* With several devices the additive fields are summed and the times are the maximum over devices. */
 
 typedef struct mbfbam_count_job {
     const mbfbam_intervals* intervals;      /* overlap targets (`intervals` argument)        */
     const mbfbam_intervals* gene_intervals; /* chunk edges only (`gene_intervals` argument)  */
     int32_t mode;                           /* MBFBAM_MODE_*                                  */
     int32_t each_read_counts_once;          /* lib.rs:143,152 (default false)                 */
-    int32_t device;                         /* CUDA ordinal                                   */
+    int32_t device;                         /* CUDA ordinal (used when n_devices == 0)        */
     int32_t shard_index;                    /* this call owns chunks of shard i of n ...      */
     int32_t shard_count;                    /* ... (1 => everything); see DESIGN.md (e)       */
-    int32_t reserved;
+    int32_t n_devices;                      /* > 0: fan out over devices[0..n_devices) from this one call:    */
+    const int32_t* devices;                 /* the shard is cut into n_devices chunk ranges, one pipeline per  */
+                                            /* device on its own thread, dense results summed on the host --   */
+                                            /* the rayon pool of counters.rs:217-259 at GPU granularity        */
 } mbfbam_count_job;
 
 /* Results are dense and caller-allocated; gene slot = gene_base[c] + gene_no where
@@ -125,7 +141,9 @@ typedef struct mbfbam_count_job {
  *   fwd/rev : u64[n_total]   (rev may be NULL for unstranded; weighted leaves them 0)
  *   wfwd/wrev: f64[n_total]  (weighted mode only, may be NULL otherwise)
  *   scanned : u8[intervals->n_contigs] 1 if the contig was scanned (in gene_intervals ∩ header)
- *   outside : reads in an owned chunk that hit no interval (counters.rs:95-97)            */
+ *   outside : reads in an owned chunk that hit no interval (counters.rs:95-97)
+ * each_read_counts_once != 0 (counters.rs:83-92,173-182): a read counts only for the first hit of its first
+ * block that has one, "first" in the iteration order of bio's IntervalTree (restated in reader.hpp). */
 typedef struct mbfbam_counts {
     uint64_t* fwd;
     uint64_t* rev;
@@ -158,6 +176,11 @@ typedef struct mbfbam_introns {
 int mbfbam_count_introns(mbfbam_reader* r, int32_t device, int32_t shard_index,
                          int32_t shard_count, mbfbam_introns* out, mbfbam_stats* stats,
                          char* err, size_t errlen);
+/* Same over several devices from one call (introns.rs:66-87 is a rayon map/reduce over chunks);
+ * every (tid, start, stop) appears once in the result. */
+int mbfbam_count_introns_multi(mbfbam_reader* r, const int32_t* devices, int32_t n_devices,
+                               int32_t shard_index, int32_t shard_count, mbfbam_introns* out,
+                               mbfbam_stats* stats, char* err, size_t errlen);
 void mbfbam_free_introns(mbfbam_introns* x);
 
 /* ChunkedGenome (src/count_reads/chunked_genome.rs:17-43,72-119): writes up to `cap`

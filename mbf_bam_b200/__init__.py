@@ -21,6 +21,8 @@ try:
         count_reads_unstranded,
         count_reads_weighted,
         device_count,
+        host_cache_clear,
+        release_device,
         inflate_buffer,
         last_stats,
     )

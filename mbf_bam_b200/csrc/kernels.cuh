@@ -41,6 +41,7 @@ enum WinErr : uint32_t {
     WERR_NH_TYPE = 105,     // NH tag present but not an integer type
     WERR_AUX = 106,         // malformed aux area
     WERR_CAPACITY = 107,    // a device buffer was too small (host retries with a larger one)
+    WERR_USIZE = 108,       // the window's blocks inflate past the 32-bit offset range (host retries with smaller windows)
     WERR_INFLATE = 200,     // + InflateError
 };
 
@@ -95,11 +96,14 @@ __device__ __forceinline__ uint32_t ldu32_cg(const uint8_t* p) {
 __device__ __forceinline__ uint32_t ldu16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 
 // ---------------------------------------------------------------------------------------------
-// generic single-CTA exclusive scan of u32 (n read from device memory); writes total to *total_out
+// generic single-CTA exclusive scan of u32 (n read from device memory); writes total to *total_out.
+// The running sum is kept in 64 bits; with `ovf_meta` a total above `limit` is reported as WERR_USIZE
+// (err_info = total in MiB) instead of wrapping silently.
 __global__ void __launch_bounds__(1024) k_excl_scan(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr,
-                                                     uint32_t n_direct, uint32_t add, uint32_t* total_out) {
+                                                     uint32_t n_direct, uint32_t add, uint32_t* total_out,
+                                                     WinMeta* ovf_meta, unsigned long long limit) {
     __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry_s;
+    __shared__ unsigned long long carry_s;
     const uint32_t n = n_ptr ? *n_ptr : n_direct;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = add;
@@ -125,14 +129,22 @@ __global__ void __launch_bounds__(1024) k_excl_scan(const uint32_t* in, uint32_t
             warp_sums[lane] = s;
         }
         __syncthreads();
-        uint32_t c = carry_s;
-        uint32_t prefix = c + (wid ? warp_sums[wid - 1] : 0) + x - v;
+        const unsigned long long c = carry_s;  // a tile of 1024 values < 2^22 each cannot wrap 32 bits
+        uint32_t prefix = (uint32_t)c + (wid ? warp_sums[wid - 1] : 0) + x - v;
         if (i < n) out[i] = prefix;
         __syncthreads();
         if (threadIdx.x == 1023) carry_s = c + warp_sums[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0 && total_out) *total_out = carry_s - add;
+    if (threadIdx.x == 0) {
+        const unsigned long long total = carry_s - add;
+        if (ovf_meta && total > limit) {
+            set_err(ovf_meta, WERR_USIZE, (uint32_t)(total >> 20));
+            if (total_out) *total_out = 0;
+        } else if (total_out) {
+            *total_out = (uint32_t)total;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -999,6 +1011,7 @@ struct CountCtx {
     const uint32_t* iv_end;
     const uint32_t* iv_pmax;         // prefix max of iv_end (start-sorted order)
     const uint32_t* iv_gene;         // global gene slot | strand bit in bit 31 (1 = gene strand == +1)
+    const uint32_t* iv_rank;         // each_read_counts_once: rank in bio's find() order (reader.hpp); else null
     const uint32_t* slot_chunk_off;  // range into chunk_stop
     const uint32_t* chunk_stop;      // ascending per slot
     uint32_t chunk_lo, chunk_hi;     // owned global chunk ids
@@ -1135,24 +1148,35 @@ __device__ __forceinline__ bool rec_view(const uint8_t* U, uint32_t off, RecView
 
 // Enumerate the (gene|strandbit) of every interval overlapped by every aligned block, in a fixed order.
 // cb(gene_word) returns false to stop.  `filter_stop`: unstranded block filter (counters.rs:52).
+// each_read_counts_once (c.iv_rank != null; counters.rs:83-92,173-182): only the first hit of the first
+// block that has one counts -- "first" in bio's iteration order, i.e. the overlapping interval of least rank.
 template <class CB>
 __device__ __forceinline__ void enumerate_hits(const CountCtx& c, const RecView& v, uint32_t iv_lo, uint32_t iv_hi,
                                                bool use_filter, uint32_t chunk_stop, CB&& cb) {
-    bool go = true;
+    const bool once = c.iv_rank != nullptr;
     cigar_walk(v.cigar, v.n_cig, v.upos,
                [&](uint32_t b0, uint32_t b1) {
                    if (use_filter && b0 >= chunk_stop) return true;
                    uint32_t hi = lower_bound_u32(c.iv_start, iv_lo, iv_hi, b1);  // start < b1 below hi
+                   uint32_t best_rank = 0xffffffffu, best_gw = 0;
                    for (uint32_t k = hi; k-- > iv_lo;) {
                        if (__ldg(c.iv_pmax + k) <= b0) break;
                        if (b0 < __ldg(c.iv_end + k)) {
-                           if (!cb(__ldg(c.iv_gene + k))) { go = false; return false; }
+                           if (once) {
+                               const uint32_t rk = __ldg(c.iv_rank + k);
+                               if (rk < best_rank) { best_rank = rk; best_gw = __ldg(c.iv_gene + k); }
+                           } else if (!cb(__ldg(c.iv_gene + k))) {
+                               return false;
+                           }
                        }
+                   }
+                   if (once && best_rank != 0xffffffffu) {
+                       cb(best_gw);
+                       return false;  // the read is spent
                    }
                    return true;
                },
                [](uint32_t, uint32_t) {});
-    (void)go;
 }
 
 constexpr int SEEN_K = 6;

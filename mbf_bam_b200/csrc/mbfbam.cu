@@ -27,6 +27,7 @@
 
 #include "kernels.cuh"
 #include "reader.hpp"
+#include "hostmap.hpp"
 
 using namespace mbf;
 
@@ -61,6 +62,14 @@ uint32_t env_u32(const char* name, uint32_t dflt) {
     return (uint32_t)strtoul(v, nullptr, 10);
 }
 
+// A window inflated to more than 32-bit offsets can address (the planner sizes windows from the largest
+// inflate ratio seen so far; a sudden, much more compressible stretch defeats it).  The job is started
+// again with windows planned for `ratio`.
+struct RetryJob : Error {
+    double ratio;
+    RetryJob(const std::string& m, double r) : Error(MBFBAM_ERR_UNSUPPORTED, m), ratio(r) {}
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -85,7 +94,7 @@ struct PinnedBuf {
         if (n <= cap) return;
         if (p) CK(cudaFreeHost(p));
         p = nullptr;
-        CK(cudaMallocHost(&p, n));
+        CK(cudaHostAlloc(&p, n, cudaHostAllocPortable));
         cap = n;
     }
     template <class T> T* as() const { return (T*)p; }
@@ -104,15 +113,31 @@ struct Source {
     virtual uint64_t size() const = 0;
     virtual void read(uint64_t off, size_t n, uint8_t* dst) const = 0;
     virtual const uint8_t* resident(int device) const { return nullptr; }  // device copy of the whole file
-    virtual const uint8_t* host_pinned() const { return nullptr; }         // page-locked host copy / mapping
+    // page-locked host bytes of [off, off+n) if all of it is page-locked (H2D straight from there)
+    virtual const uint8_t* host_pinned(uint64_t off, uint64_t n) const { return nullptr; }
 };
 struct FileSource : Source {
     const Reader* r;
-    explicit FileSource(const Reader* r_) : r(r_) {}
+    std::shared_ptr<FileMap> map;  // may be null: pread path
+    FileSource(const Reader* r_, std::shared_ptr<FileMap> m) : r(r_), map(std::move(m)) {}
     uint64_t size() const override { return r->file_size; }
-    void read(uint64_t off, size_t n, uint8_t* dst) const override { r->pread_exact(dst, off, n); }
+    // a mapping must not be read past the end of a file that shrank under us (SIGBUS): one fstat per piece
+    bool still_there(uint64_t end) const {
+        struct stat sb;
+        return fstat(r->fd, &sb) == 0 && (uint64_t)sb.st_size >= end;
+    }
+    void read(uint64_t off, size_t n, uint8_t* dst) const override {
+        if (map && off + n <= map->size) {
+            if (!still_there(off + n)) throw Error(MBFBAM_ERR_IO, "Could not read bam: short read on " + r->path);
+            memcpy(dst, map->p + off, n);  // hostmap.hpp: 1.7x the rate of pread
+        } else {
+            r->pread_exact(dst, off, n);
+        }
+    }
     const uint8_t* resident(int device) const override { return r->preload_device == device ? r->preload_ptr : nullptr; }
-    const uint8_t* host_pinned() const override { return r->map_registered ? r->map_ptr : nullptr; }
+    const uint8_t* host_pinned(uint64_t off, uint64_t n) const override {
+        return map && off + n <= map->size && map->seg_pinned(off, n) && still_there(off + n) ? map->p + off : nullptr;
+    }
 };
 struct MemSource : Source {
     const uint8_t* p;
@@ -155,19 +180,20 @@ struct Pipeline {
     uint32_t W;          // window size in compressed bytes
     uint32_t cand_cap;
     cudaStream_t s_front = nullptr, s_main = nullptr, s_inf[2] = {nullptr, nullptr};
-    cudaEvent_t ev_reuse = nullptr;
+    cudaEvent_t ev_reuse = nullptr, ev_job_begin = nullptr, ev_job_end = nullptr;
     WinBufs wb[2];
     DevBuf U[2];
-    size_t U_cap = 0;    // data bytes (without prefix/slack)
+    size_t U_cap[2] = {0, 0};  // data bytes (without prefix/slack); the two buffers grow independently
     DevBuf d_meta, d_chain, d_carry, d_tscratch, d_tok[2], d_ntok[2];
     PinnedBuf h_meta_front, h_meta_main;
     int sm_count = 148;
     bool sync_debug = false;
+    double ratio_hint = 1.0;  // inflate ratio the first windows are planned for (raised by a RetryJob)
 
     // ---- counting job state
     int mode = 0;
     CountCtx cc{};
-    DevBuf d_tid2slot, d_slot_iv_off, d_iv_start, d_iv_end, d_iv_pmax, d_iv_gene, d_slot_chunk_off, d_chunk_stop;
+    DevBuf d_tid2slot, d_slot_iv_off, d_iv_start, d_iv_end, d_iv_pmax, d_iv_gene, d_iv_rank, d_slot_chunk_off, d_chunk_stop;
     DevBuf d_counts, d_wspill;
     DevBuf d_set;
     uint64_t set_cap = 0, set_ub = 0;
@@ -200,6 +226,8 @@ struct Pipeline {
         CK(cudaStreamCreateWithPriority(&s_inf[0], cudaStreamNonBlocking, prio_lo));
         CK(cudaStreamCreateWithPriority(&s_inf[1], cudaStreamNonBlocking, prio_lo));
         CK(cudaEventCreateWithFlags(&ev_reuse, cudaEventDisableTiming));
+        CK(cudaEventCreate(&ev_job_begin));
+        CK(cudaEventCreate(&ev_job_end));
         d_meta.ensure(2 * sizeof(WinMeta));
         d_chain.ensure(sizeof(ChainState));
         d_carry.ensure(16);
@@ -220,6 +248,8 @@ struct Pipeline {
     // stream, so that small jobs do not allocate full-size windows.
     void begin_job(const Source* s, JobKind k, uint64_t job_bytes) {
         CK(cudaSetDevice(device));
+        // a previous job may have ended with an exception while work was still queued
+        for (cudaStream_t x : {s_front, s_inf[0], s_inf[1], s_main}) CK(cudaStreamSynchronize(x));
         src = s;
         kind = k;
         st = mbfbam_stats{};
@@ -229,6 +259,10 @@ struct Pipeline {
         W = (uint32_t)std::max<uint64_t>(1u << 20, std::min(w, need));
         cand_cap = W / 64 + 1024;
         sync_debug = env_u32("MBF_BAM_SYNC", 0) != 0;
+        {
+            const uint32_t hl = env_u32("MBF_BAM_U_HARD_LIMIT_MB", 0);
+            u_hard_limit = hl ? std::min<uint64_t>((uint64_t)hl << 20, U_DATA_LIMIT) : U_DATA_LIMIT;
+        }
         CK(cudaMemsetAsync(d_chain.p, 0, sizeof(ChainState), s_front));
         CK(cudaMemsetAsync(d_carry.p, 0, 16, s_main));
         uint32_t mm_env = env_u32("MBF_BAM_MM_CAP", 0);
@@ -243,7 +277,7 @@ struct Pipeline {
             wbi.in_flight = wbi.timed = false;
             if (mm_env) wbi.mm_cap = 0;  // tests force a tiny key buffer
         }
-        ensure_U(std::min<size_t>((size_t)W * 4, (size_t)3 << 30));
+        for (int i = 0; i < 2; i++) ensure_U(i, std::min<size_t>((size_t)W * 4, (size_t)3 << 30), false);
         mode = 0;
         cc = CountCtx{};
         ic = IntronCtx{};
@@ -268,6 +302,8 @@ struct Pipeline {
             for (auto& t : w.t) if (t) cudaEventDestroy(t);
         }
         if (ev_reuse) cudaEventDestroy(ev_reuse);
+        if (ev_job_begin) cudaEventDestroy(ev_job_begin);
+        if (ev_job_end) cudaEventDestroy(ev_job_end);
         for (auto& x : s_inf) if (x) cudaStreamDestroy(x);
         if (s_front) cudaStreamDestroy(s_front);
         if (s_main) cudaStreamDestroy(s_main);
@@ -285,23 +321,29 @@ struct Pipeline {
 
     WinMeta* dmeta(int i) { return d_meta.as<WinMeta>() + i; }
 
-    // (re)allocate both U buffers; preserves the carry prefix of buffer `keep` if >= 0
-    void ensure_U(size_t data_bytes, int keep = -1) {
-        if (data_bytes <= U_cap) return;
-        size_t cap = std::max(data_bytes, U_cap * 2);
-        if ((uint64_t)cap + U_PREFIX + 65536 > 0xffff0000ull) throw Error(MBFBAM_ERR_UNSUPPORTED, "window inflates past 4 GiB; lower MBF_BAM_WINDOW_MB");
+    // Largest inflated size of one window: 32-bit offsets into U (prefix + data + slack < 4 GiB).
+    static constexpr uint64_t U_DATA_LIMIT = 0xffff0000ull - U_PREFIX - 65536;
+    uint64_t u_hard_limit = U_DATA_LIMIT;  // MBF_BAM_U_HARD_LIMIT_MB lowers it so that tests can reach the retry
+
+    // Grow U[bi] (and what is sized from it: this parity's record offsets).  Only buffers of parity `bi` are
+    // touched: window k-1 (the other parity) may still have its second half outstanding (intron pass 2, the
+    // emit-only re-run after a key overflow), which reads U[bi^1] and wb[bi^1].rec_off.  The last users of
+    // U[bi] are window k-2's main stage (complete once s_main has drained: its second half was queued one
+    // iteration ago) and window k-1's carry copy INTO its prefix, which `keep_prefix` preserves.
+    void ensure_U(int bi, size_t data_bytes, bool keep_prefix) {
+        if (data_bytes <= U_cap[bi]) return;
+        if (data_bytes > U_DATA_LIMIT) throw RetryJob("window inflates past 4 GiB", 0.0);
+        size_t cap = std::min<size_t>(std::max(data_bytes, U_cap[bi] * 2), U_DATA_LIMIT);
         CK(cudaStreamSynchronize(s_inf[0]));
         CK(cudaStreamSynchronize(s_inf[1]));
         CK(cudaStreamSynchronize(s_main));
-        for (int i = 0; i < 2; i++) {
-            DevBuf nb;
-            nb.ensure(cap + U_PREFIX + 65536);
-            if (i == keep && U[i].p) CK(cudaMemcpy(nb.p, U[i].p, U_PREFIX, cudaMemcpyDeviceToDevice));
-            std::swap(U[i].p, nb.p);
-            std::swap(U[i].cap, nb.cap);
-        }
-        U_cap = cap;
-        for (auto& w : wb) w.rec_off.ensure((cap / 36 + 64) * 4);
+        DevBuf nb;
+        nb.ensure(cap + U_PREFIX + 65536);
+        if (keep_prefix && U[bi].p) CK(cudaMemcpy(nb.p, U[bi].p, U_PREFIX, cudaMemcpyDeviceToDevice));
+        std::swap(U[bi].p, nb.p);
+        std::swap(U[bi].cap, nb.cap);
+        U_cap[bi] = cap;
+        wb[bi].rec_off.ensure((cap / 36 + 64) * 4);
     }
 
     // ---------------------------------------------------------------- front stage
@@ -362,7 +404,7 @@ struct Pipeline {
             k_scan<false><<<ntile, SCAN_THREADS, 0, s_front>>>(a);
             launched("k_scan<count>", s_front);
         }
-        k_excl_scan<<<1, 1024, 0, s_front>>>(a.tile_count, a.tile_base, nullptr, ntile, 0, &dmeta(bi)->n_cand);
+        k_excl_scan<<<1, 1024, 0, s_front>>>(a.tile_count, a.tile_base, nullptr, ntile, 0, &dmeta(bi)->n_cand, nullptr, 0);
         launched("k_excl_scan(tiles)", s_front);
         if (ntile) {
             k_scan<true><<<ntile, SCAN_THREADS, 0, s_front>>>(a);
@@ -371,7 +413,8 @@ struct Pipeline {
         BlockArrays b{w.cpos.as<uint32_t>(), w.clen.as<uint32_t>(), w.isize.as<uint32_t>(), w.uoff.as<uint32_t>()};
         k_blocks_finalize<<<std::max(1u, std::min(64u, cand_cap / 256)), 256, 0, s_front>>>(a, b);
         launched("k_blocks_finalize", s_front);
-        k_excl_scan<<<1, 1024, 0, s_front>>>(b.isize, b.uoff, &dmeta(bi)->n_blocks, 0, U_PREFIX, &dmeta(bi)->u_total);
+        k_excl_scan<<<1, 1024, 0, s_front>>>(b.isize, b.uoff, &dmeta(bi)->n_blocks, 0, U_PREFIX, &dmeta(bi)->u_total, dmeta(bi),
+                                             u_hard_limit - 1024);
         launched("k_excl_scan(isize)", s_front);
         CK(cudaEventRecord(w.t[1], s_front));
         CK(cudaMemcpyAsync(h_meta_front.as<WinMeta>() + bi, dmeta(bi), sizeof(WinMeta), cudaMemcpyDeviceToHost, s_front));
@@ -380,22 +423,30 @@ struct Pipeline {
         w.in_flight = true;
     }
 
-    // Host bytes -> pinned staging -> HBM.  The window is cut into pieces read by a few threads (pread
-    // from the page cache runs at 2-4 GB/s per thread, far below PCIe); every piece is copied to the
-    // device as soon as it and its predecessors have landed, so reading and H2D overlap.
+    // Host bytes -> HBM.  Page-locked source (hostmap.hpp): one DMA per registration segment, no CPU copy.
+    // Otherwise the window is cut into pieces copied into a pinned staging buffer by a few threads (memcpy out of
+    // the file mapping runs at ~13 GB/s per thread, pread at ~8); every piece goes to the device as soon as it and
+    // its predecessors have landed, so the host copy and the H2D overlap.
+    int read_threads = 0;  // 0: derived from the core count
     void stage_window(WinBufs& w, uint64_t win_off, size_t avail) {
         uint8_t* d = w.d_c.as<uint8_t>();
-        if (const uint8_t* hp = src->host_pinned()) {
-            // the file mapping is page-locked: DMA straight out of the page cache
-            CK(cudaMemcpyAsync(d, hp + win_off, avail, cudaMemcpyHostToDevice, s_front));
+        if (const uint8_t* hp = src->host_pinned(win_off, avail)) {
+            for (size_t off = 0; off < avail;) {
+                const size_t seg_left = PIN_SEG - (size_t)((win_off + off) % PIN_SEG);
+                const size_t len = std::min(seg_left, avail - off);
+                CK(cudaMemcpyAsync(d + off, hp + off, len, cudaMemcpyHostToDevice, s_front));
+                off += len;
+            }
             CK(cudaMemsetAsync(d + avail, 0, 128, s_front));
+            st.h2d_pinned_bytes += avail;
             return;
         }
         w.h_c.ensure((size_t)W + 65536 + 256);
         uint8_t* h = w.h_c.as<uint8_t>();
         const size_t PIECE = 8u << 20;
         const size_t n_pieces = (avail + PIECE - 1) / PIECE;
-        int n_threads = (int)env_u32("MBF_BAM_READ_THREADS", std::min(16u, std::max(2u, std::thread::hardware_concurrency() * 3 / 4)));
+        int n_threads = read_threads > 0 ? read_threads
+                                         : (int)env_u32("MBF_BAM_READ_THREADS", std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2)));
         n_threads = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_threads, n_pieces));
         if (n_pieces <= 1 || n_threads <= 1) {
             src->read(win_off, avail, h);
@@ -410,7 +461,7 @@ struct Pipeline {
         std::string fail_msg;
         std::mutex fail_mu;
         std::vector<std::thread> th;
-        for (int t = 0; t < n_threads; t++)
+        for (int t = 0; t + 1 < n_threads; t++)  // the calling (staging helper) thread is the n-th copier
             th.emplace_back([&] {
                 for (;;) {
                     size_t i = next.fetch_add(1);
@@ -428,7 +479,20 @@ struct Pipeline {
             });
         cudaError_t cerr = cudaSuccess;
         for (size_t i = 0; i < n_pieces; i++) {
-            while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+            // while piece i is still being copied this thread copies pieces too instead of spinning
+            while (!done[i].load(std::memory_order_acquire)) {
+                size_t j = next.fetch_add(1);
+                if (j >= n_pieces) { std::this_thread::yield(); continue; }
+                size_t off = j * PIECE, len = std::min(PIECE, avail - off);
+                try {
+                    if (!failed.load()) src->read(win_off + off, len, h + off);
+                } catch (const std::exception& e) {
+                    std::lock_guard<std::mutex> lk(fail_mu);
+                    fail_msg = e.what();
+                    failed.store(1);
+                }
+                done[j].store(1, std::memory_order_release);
+            }
             size_t off = i * PIECE, len = std::min(PIECE, avail - off);
             if (i + 1 == n_pieces) {
                 memset(h + avail, 0, 128);
@@ -465,9 +529,11 @@ struct Pipeline {
         WinBufs& w = wb[bi];
         CK(cudaEventSynchronize(w.ev_front));
         WinMeta m = h_meta_front.as<WinMeta>()[bi];
+        if (m.err == WERR_USIZE)  // err_info = inflated size in MiB
+            throw RetryJob("window inflates past 4 GiB", ((double)m.err_info * 1048576.0) / (double)std::max<uint32_t>(1, w.scan_len));
         if (m.err) throw Error(MBFBAM_ERR_FORMAT, err_text(m));
         w.front_meta = m;
-        ensure_U((size_t)m.u_total + 1024, bi);
+        ensure_U(bi, (size_t)m.u_total + 1024, true);
         st.n_bgzf_blocks += m.n_blocks;
         st.uncompressed_bytes += m.u_total;
         st.n_windows++;
@@ -510,7 +576,7 @@ struct Pipeline {
             launched("k_frame_walk<count>", s_main);
             k_frame_fix<<<1, 1024, 0, s_main>>>(fa);
             launched("k_frame_fix", s_main);
-            k_excl_scan<<<1, 1024, 0, s_main>>>(fa.blk_nrec, fa.rec_base, &dmeta(bi)->n_blocks, 0, 0, &dmeta(bi)->n_records);
+            k_excl_scan<<<1, 1024, 0, s_main>>>(fa.blk_nrec, fa.rec_base, &dmeta(bi)->n_blocks, 0, 0, &dmeta(bi)->n_records, nullptr, 0);
             launched("k_excl_scan(records)", s_main);
             k_frame_walk<true><<<fgrid, 128, 0, s_main>>>(fa);
             launched("k_frame_walk<emit>", s_main);
@@ -551,7 +617,7 @@ struct Pipeline {
                 const int dl = (int)mode_d - 300;
                 DevBuf& tokb = d_tok[bi];
                 DevBuf& ntokb = d_ntok[bi];
-                tokb.ensure((U_cap + 65536) * 4);
+                tokb.ensure((U_cap[bi] + 65536) * 4);
                 ntokb.ensure((size_t)(cand_cap + 8) * 4);
                 d_tscratch.ensure((size_t)2 * sm_count * 32 * 32 * sizeof(TokScratch));
                 TokenArgs ta{w.c_ptr, b.cpos, b.clen, b.isize, b.uoff, tokb.as<uint32_t>(), ntokb.as<uint32_t>(), U_PREFIX,
@@ -751,7 +817,7 @@ struct Pipeline {
         //  * streamed jobs grow x1.5 per window until W: the bytes of window k+1 are staged while the GPU
         //    works on window k, so a window must not take longer to stage than its predecessor takes to
         //    process (a full-size second window would leave the GPU idle for ~10 ms).
-        const bool ramp = !src->resident(device);
+        const bool ramp = !src->resident(device) && !(ranges.size() && src->host_pinned(ranges[0].cbeg, 1));
         size_t ri = 0;
         uint64_t pos = ranges.empty() ? 0 : ranges[0].cbeg;
         bool first_of_range = true;
@@ -798,12 +864,14 @@ struct Pipeline {
             }
         } stager;
         uint64_t cur_w = std::max<uint64_t>(W / std::max<uint32_t>(1, env_u32("MBF_BAM_FIRST_WINDOW_DIV", 8)), 1u << 20);
-        double max_ratio = 1.0;
+        double max_ratio = std::max(1.0, ratio_hint);
         // inflated bytes a window may have (MBF_BAM_U_LIMIT_MB exists so that tests can reach the cap)
         const uint64_t u_limit = (uint64_t)std::min<uint32_t>(env_u32("MBF_BAM_U_LIMIT_MB", 3276), 3276) << 20;
+        cur_w = std::max<uint64_t>(1u << 20, std::min<uint64_t>(cur_w, (uint64_t)((double)u_limit / (max_ratio * 1.25)) & ~(uint64_t)0xfffff));
         Win wk{}, wn{};
         bool have = next_win(cur_w, wk);
         double t0 = now_ms();
+        CK(cudaEventRecord(ev_job_begin, s_front));
         if (have) {
             stage_front(0, wk.off, wk.scan_len, wk.src_end, wk.range_start, wk.range_off, wk.first_uoff);
             scan_front(0);
@@ -858,19 +926,33 @@ struct Pipeline {
         CK(cudaStreamSynchronize(s_inf[1]));
         CK(cudaStreamSynchronize(s_main));
         CK(cudaStreamSynchronize(s_front));
-        st.ms_gpu_all = now_ms() - t0;
+        CK(cudaEventRecord(ev_job_end, s_main));  // every stream has drained: this is the end of the device's work
+        CK(cudaEventSynchronize(ev_job_end));
+        float ms_all = 0;
+        CK(cudaEventElapsedTime(&ms_all, ev_job_begin, ev_job_end));
+        st.ms_gpu_all = ms_all;
     }
 };
 
-// one pipeline call at a time per process keeps the pinned/device footprint bounded
-std::mutex g_mu;
-
-// per-device pipeline cache (guarded by g_mu)
-Pipeline& get_pipeline(int device) {
-    static std::map<int, std::unique_ptr<Pipeline>> pipes;
-    auto it = pipes.find(device);
-    if (it == pipes.end()) it = pipes.emplace(device, std::unique_ptr<Pipeline>(new Pipeline(device))).first;
+// One Pipeline per device, created on first use and reused by every job on that device.  Jobs on one device
+// are serialised by the slot's mutex (a job owns the pipeline's streams and buffers); jobs on different
+// devices run concurrently -- that is how one call fans out over the GPUs of a box.
+struct DevSlot {
+    std::mutex mu;
+    std::unique_ptr<Pipeline> pipe;
+};
+DevSlot& dev_slot(int device) {
+    static std::mutex map_mu;
+    static std::map<int, std::unique_ptr<DevSlot>> slots;
+    std::lock_guard<std::mutex> lk(map_mu);
+    auto it = slots.find(device);
+    if (it == slots.end()) it = slots.emplace(device, std::unique_ptr<DevSlot>(new DevSlot())).first;
     return *it->second;
+}
+// caller holds slot.mu
+Pipeline& slot_pipeline(DevSlot& slot, int device) {
+    if (!slot.pipe) slot.pipe.reset(new Pipeline(device));
+    return *slot.pipe;
 }
 
 uint64_t range_bytes(const std::vector<ByteRange>& r) {
@@ -895,6 +977,35 @@ int guarded(char* err, size_t errlen, F&& f) {
         copy_err(err, errlen, e.what());
         return MBFBAM_ERR_CUDA;
     }
+}
+
+// f(k) for k in [0, n): on the calling thread when n == 1, else one thread each; the first exception is rethrown
+template <class F>
+void fan_out(size_t n, F&& f) {
+    if (n == 1) { f((size_t)0); return; }
+    std::vector<std::thread> th;
+    std::vector<std::exception_ptr> errs(n);
+    for (size_t k = 0; k < n; k++)
+        th.emplace_back([&, k] {
+            try { f(k); } catch (...) { errs[k] = std::current_exception(); }
+        });
+    for (auto& t : th) t.join();
+    for (auto& e : errs) if (e) std::rethrow_exception(e);
+}
+
+// sums the additive fields, keeps the largest of the times (devices work side by side)
+void merge_stats(mbfbam_stats& a, const mbfbam_stats& b) {
+    a.n_records += b.n_records; a.n_records_owned += b.n_records_owned; a.n_bgzf_blocks += b.n_bgzf_blocks;
+    a.compressed_bytes += b.compressed_bytes; a.uncompressed_bytes += b.uncompressed_bytes;
+    a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes; a.n_chunks += b.n_chunks;
+    a.n_kernel_launches += b.n_kernel_launches; a.n_windows += b.n_windows; a.n_mm_keys += b.n_mm_keys;
+    a.n_fixups += b.n_fixups; a.n_tokens += b.n_tokens; a.h2d_pinned_bytes += b.h2d_pinned_bytes;
+    a.n_devices += b.n_devices; a.n_retries += b.n_retries;
+    a.ms_total = std::max(a.ms_total, b.ms_total); a.ms_gpu_scan = std::max(a.ms_gpu_scan, b.ms_gpu_scan);
+    a.ms_gpu_inflate = std::max(a.ms_gpu_inflate, b.ms_gpu_inflate); a.ms_gpu_frame = std::max(a.ms_gpu_frame, b.ms_gpu_frame);
+    a.ms_gpu_count = std::max(a.ms_gpu_count, b.ms_gpu_count); a.ms_gpu_other = std::max(a.ms_gpu_other, b.ms_gpu_other);
+    a.ms_gpu_all = std::max(a.ms_gpu_all, b.ms_gpu_all); a.ms_gpu_tokens = std::max(a.ms_gpu_tokens, b.ms_gpu_tokens);
+    a.ms_pin = std::max(a.ms_pin, b.ms_pin);
 }
 
 struct ShardPlan {
@@ -947,12 +1058,265 @@ void plan_shard(const Reader& r, ShardPlan& p, int shard, int nshards) {
     for (auto& x : vr) add_range(p.ranges, x.first, x.second, r.file_size);
 }
 
+
+// Devices of a job: job devices[] if given, else the single `device`.
+std::vector<int> job_devices(const int32_t* devices, int32_t n_devices, int32_t device) {
+    std::vector<int> d;
+    if (devices && n_devices > 0) {
+        for (int i = 0; i < n_devices; i++) {
+            if (std::find(d.begin(), d.end(), (int)devices[i]) != d.end()) throw Error(MBFBAM_ERR_ARG, "device listed twice");
+            d.push_back(devices[i]);
+        }
+    } else {
+        d.push_back(device);
+    }
+    return d;
+}
+
+int pin_after_jobs() {  // a file's mapping is page-locked once this many jobs have streamed it (-1: never)
+    const char* v = getenv("MBF_BAM_PIN_AFTER");
+    if (!v || !*v) return 3;
+    if (!strcmp(v, "never")) return -1;
+    return atoi(v);
+}
+uint64_t pin_budget_bytes() {
+    const uint32_t mb = env_u32("MBF_BAM_PIN_MAX_MB", 0);
+    if (mb) return (uint64_t)mb << 20;
+    const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+    return pages > 0 && psz > 0 ? (uint64_t)pages * (uint64_t)psz / 2 : (8ull << 30);
+}
+
 }  // namespace
 
 struct mbfbam_reader {
     Reader r;
     DevBuf preload;
+    std::shared_ptr<FileMap> fmap;   // process-wide mapping of the file (null: pread path)
+    bool pin_now = false;            // mbfbam_pin_file was called: page-lock whatever a job touches
 };
+
+namespace {
+
+// Page-locks the byte ranges of a job when the policy says so; returns the ms spent.
+double maybe_pin(mbfbam_reader* rd, const std::vector<ByteRange>& ranges, uint64_t prior_jobs) {
+    if (!rd->fmap) return 0.0;
+    const int after = pin_after_jobs();
+    if (!(rd->pin_now || (after >= 0 && prior_jobs >= (uint64_t)after))) return 0.0;
+    double ms = 0.0;
+    const uint64_t budget = pin_budget_bytes();
+    for (const auto& r : ranges) ms += pin_range(*rd->fmap, r.cbeg, std::min<uint64_t>(r.cend + 65536 + 64, rd->fmap->size) - r.cbeg, budget);
+    return ms;
+}
+
+// runs `setup(p)` + p.run(ranges) with the retry a RetryJob asks for
+template <class S>
+void run_with_retry(Pipeline& p, const std::vector<ByteRange>& ranges, S&& setup) {
+    p.ratio_hint = 1.0;
+    for (int attempt = 0;; attempt++) {
+        try {
+            setup(p);
+            p.run(ranges);
+            p.st.n_retries = (uint64_t)attempt;
+            return;
+        } catch (const RetryJob& e) {
+            if (attempt >= 4) throw Error(MBFBAM_ERR_UNSUPPORTED, std::string("Could not read bam: ") + e.what() + " (after retries with smaller windows)");
+            p.ratio_hint = std::max(p.ratio_hint * 2.0, e.ratio * 1.3);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// count_reads: host tables shared by all devices of a job
+struct CountTables {
+    size_t G = 0;
+    std::vector<Chunk> chunks;
+    std::vector<int32_t> tid2slot;
+    std::vector<int> slot_iv;  // slot -> contig index in `intervals`
+    std::vector<uint32_t> slot_iv_off, ivs, ive, ivp, ivg, ivr, slot_chunk_off, chunk_stop;
+};
+
+void build_count_tables(const Reader& r, const mbfbam_count_job* job, CountTables& T) {
+    const mbfbam_intervals* iv = job->intervals;
+    const mbfbam_intervals* gv = job->gene_intervals;
+    std::vector<uint64_t> gene_base((size_t)iv->n_contigs + 1, 0);
+    for (int c = 0; c < iv->n_contigs; c++) gene_base[(size_t)c + 1] = gene_base[(size_t)c] + iv->n_genes[c];
+    T.G = (size_t)gene_base[(size_t)iv->n_contigs];
+    if (T.G >= (1ull << 31)) throw Error(MBFBAM_ERR_UNSUPPORTED, "too many genes");
+    std::map<std::string, int> iv_index;
+    for (int c = 0; c < iv->n_contigs; c++) iv_index.emplace(iv->contig_names[c], c);
+    // chunks over gene_intervals ∩ header (chunked_genome.rs:17-31); every such contig must be in `intervals`
+    T.chunks = make_chunks(r, gv);
+    T.tid2slot.assign(r.names.size(), -1);
+    for (const Chunk& c : T.chunks) {
+        if (T.tid2slot[(size_t)c.tid] >= 0) continue;
+        auto it = iv_index.find(r.names[(size_t)c.tid]);
+        if (it == iv_index.end())
+            throw Error(MBFBAM_ERR_ARG, "contig " + r.names[(size_t)c.tid] + " is in gene_intervals but not in intervals");
+        T.tid2slot[(size_t)c.tid] = (int32_t)T.slot_iv.size();
+        T.slot_iv.push_back(it->second);
+    }
+    // chunk_stop per slot, chunk ids global in chunk-table order (slots are created in that order too)
+    T.slot_chunk_off.assign(T.slot_iv.size() + 1, 0);
+    {
+        size_t i = 0;
+        for (size_t s = 0; s < T.slot_iv.size(); s++) {
+            T.slot_chunk_off[s] = (uint32_t)T.chunk_stop.size();
+            int32_t tid = T.chunks[i].tid;
+            while (i < T.chunks.size() && T.chunks[i].tid == tid) T.chunk_stop.push_back(T.chunks[i++].stop);
+        }
+        T.slot_chunk_off[T.slot_iv.size()] = (uint32_t)T.chunk_stop.size();
+    }
+    // flattened, start-sorted interval tables per slot
+    T.slot_iv_off.assign(T.slot_iv.size() + 1, 0);
+    for (size_t s = 0; s < T.slot_iv.size(); s++) {
+        int c = T.slot_iv[s];
+        SortedIntervals si = sort_intervals(iv, c, job->each_read_counts_once != 0);
+        T.slot_iv_off[s] = (uint32_t)T.ivs.size();
+        for (size_t k = 0; k < si.start.size(); k++) {
+            if (si.gene[k] >= iv->n_genes[c]) throw Error(MBFBAM_ERR_ARG, "gene index out of range");
+            T.ivs.push_back(si.start[k]);
+            T.ive.push_back(si.end[k]);
+            T.ivp.push_back(si.pmax[k]);
+            T.ivg.push_back((uint32_t)(gene_base[(size_t)c] + si.gene[k]) | (si.strand[k] == 1 ? 0x80000000u : 0u));
+            if (job->each_read_counts_once) T.ivr.push_back(si.rank[k]);
+        }
+    }
+    T.slot_iv_off[T.slot_iv.size()] = (uint32_t)T.ivs.size();
+}
+
+struct CountPart {
+    std::vector<unsigned long long> h;
+    std::vector<double> spill;
+    uint64_t outside = 0;
+    mbfbam_stats st{};
+};
+
+void count_on_device(mbfbam_reader* rd, const CountTables& T, const mbfbam_count_job* job, int device, int shard, int nshards,
+                     int read_threads, uint64_t prior_jobs, CountPart& out) {
+    const Reader& r = rd->r;
+    ShardPlan plan;
+    plan.chunks = T.chunks;
+    plan_shard(r, plan, shard, nshards);
+    const double ms_pin = maybe_pin(rd, plan.ranges, prior_jobs);
+    const size_t G = T.G;
+    const size_t n_words = (job->mode == MBFBAM_MODE_WEIGHTED ? (size_t)NH_DENSE * 2 : 2) * std::max<size_t>(G, 1);
+    FileSource src(&r, rd->fmap);
+    DevSlot& slot = dev_slot(device);
+    std::lock_guard<std::mutex> lk(slot.mu);
+    Pipeline& p = slot_pipeline(slot, device);
+    p.read_threads = read_threads;
+    run_with_retry(p, plan.ranges, [&](Pipeline& p) {
+        p.begin_job(&src, JOB_COUNT, range_bytes(plan.ranges));
+        p.mode = job->mode;
+        p.n_genes = G;
+        p.n_count_words = n_words;
+        p.d_counts.ensure(n_words * 8);
+        CK(cudaMemsetAsync(p.d_counts.p, 0, n_words * 8, p.s_main));
+        p.d_wspill.ensure(std::max<size_t>(G, 1) * 16);
+        CK(cudaMemsetAsync(p.d_wspill.p, 0, std::max<size_t>(G, 1) * 16, p.s_main));
+        p.d_set_size.ensure(8);
+        CK(cudaMemsetAsync(p.d_set_size.p, 0, 8, p.s_main));
+        CountCtx& c = p.cc;
+        c.tid2slot = upload(p.d_tid2slot, T.tid2slot, p.s_main);
+        c.n_ref = (int32_t)T.tid2slot.size();
+        c.slot_iv_off = upload(p.d_slot_iv_off, T.slot_iv_off, p.s_main);
+        c.iv_start = upload(p.d_iv_start, T.ivs, p.s_main);
+        c.iv_end = upload(p.d_iv_end, T.ive, p.s_main);
+        c.iv_pmax = upload(p.d_iv_pmax, T.ivp, p.s_main);
+        c.iv_gene = upload(p.d_iv_gene, T.ivg, p.s_main);
+        c.iv_rank = job->each_read_counts_once ? upload(p.d_iv_rank, T.ivr, p.s_main) : nullptr;
+        c.slot_chunk_off = upload(p.d_slot_chunk_off, T.slot_chunk_off, p.s_main);
+        c.chunk_stop = upload(p.d_chunk_stop, T.chunk_stop, p.s_main);
+        c.chunk_lo = (uint32_t)plan.lo;
+        c.chunk_hi = (uint32_t)plan.hi;
+        c.counts = p.d_counts.as<unsigned long long>();
+        c.wspill = p.d_wspill.as<double>();
+        c.n_genes = (uint32_t)G;
+        CK(cudaStreamSynchronize(p.s_main));  // the tables are read by kernels on other streams too
+        p.st.n_chunks = plan.hi - plan.lo;
+    });
+    out.h.resize(n_words);
+    CK(cudaMemcpy(out.h.data(), p.d_counts.p, n_words * 8, cudaMemcpyDeviceToHost));
+    p.st.d2h_bytes += n_words * 8;
+    if (job->mode == MBFBAM_MODE_WEIGHTED) {
+        out.spill.resize(2 * std::max<size_t>(G, 1));
+        CK(cudaMemcpy(out.spill.data(), p.d_wspill.p, out.spill.size() * 8, cudaMemcpyDeviceToHost));
+        p.st.d2h_bytes += out.spill.size() * 8;
+    }
+    out.outside = p.outside_total;
+    p.st.ms_pin = ms_pin;
+    p.st.n_devices = 1;
+    out.st = p.st;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct IntronEntry {
+    int32_t tid;
+    uint32_t start, stop;
+    uint64_t count;
+};
+struct IntronPart {
+    std::vector<IntronEntry> entries;
+    std::vector<uint8_t> seen;
+    mbfbam_stats st{};
+};
+
+void introns_on_device(mbfbam_reader* rd, const std::vector<Chunk>& chunks, const std::vector<uint32_t>& ref_chunk_off, int device,
+                       int shard, int nshards, int read_threads, uint64_t prior_jobs, IntronPart& out) {
+    const Reader& r = rd->r;
+    ShardPlan plan;
+    plan.chunks = chunks;
+    plan_shard(r, plan, shard, nshards);
+    const double ms_pin = maybe_pin(rd, plan.ranges, prior_jobs);
+    const size_t n_ref = r.names.size();
+    FileSource src(&r, rd->fmap);
+    DevSlot& slot = dev_slot(device);
+    std::lock_guard<std::mutex> lk(slot.mu);
+    Pipeline& p = slot_pipeline(slot, device);
+    p.read_threads = read_threads;
+    run_with_retry(p, plan.ranges, [&](Pipeline& p) {
+        p.begin_job(&src, JOB_INTRONS, range_bytes(plan.ranges));
+        p.d_hist.ensure(std::max<size_t>(1, n_ref) * HIST_DENSE * 8);
+        CK(cudaMemsetAsync(p.d_hist.p, 0, std::max<size_t>(1, n_ref) * HIST_DENSE * 8, p.s_main));
+        p.d_scalar.ensure(16);
+        p.ic.n_ref = (int32_t)n_ref;
+        p.ic.ref_chunk_off = upload(p.d_ref_chunk_off, ref_chunk_off, p.s_main);
+        p.ic.chunk_lo = (uint32_t)plan.lo;
+        p.ic.chunk_hi = (uint32_t)plan.hi;
+        p.ic.hist = p.d_hist.as<unsigned long long>();
+        CK(cudaStreamSynchronize(p.s_main));
+        p.ensure_map(1024);
+        p.st.n_chunks = plan.hi - plan.lo;
+    });
+    // pull the map and the dense histogram
+    std::vector<ulonglong2> slots((size_t)p.map_cap);
+    CK(cudaMemcpy(slots.data(), p.d_map.p, (size_t)p.map_cap * 16, cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> hist(std::max<size_t>(1, n_ref) * HIST_DENSE);
+    CK(cudaMemcpy(hist.data(), p.d_hist.p, hist.size() * 8, cudaMemcpyDeviceToHost));
+    p.st.d2h_bytes += (size_t)p.map_cap * 16 + hist.size() * 8;
+    for (const auto& s : slots) {
+        if (s.x == ~0ull && s.y == ~0ull) continue;
+        out.entries.push_back({(int32_t)(uint32_t)s.y, (uint32_t)s.x, (uint32_t)(s.x >> 32), s.y >> 32});
+    }
+    for (size_t t = 0; t < n_ref; t++)
+        for (int q = 0; q < HIST_DENSE; q++)
+            if (hist[t * HIST_DENSE + q]) out.entries.push_back({(int32_t)t, 0xffffffffu, 0xffffffffu - (uint32_t)q, hist[t * HIST_DENSE + q]});
+    // introns.rs:75-79: every chunk that was scanned inserts its contig key (possibly empty dict)
+    out.seen.assign(n_ref + 1, 0);
+    for (size_t i = plan.lo; i < plan.hi; i++) out.seen[(size_t)plan.chunks[i].tid] = 1;
+    p.st.ms_pin = ms_pin;
+    p.st.n_devices = 1;
+    out.st = p.st;
+}
+
+int default_read_threads(size_t n_devices) {
+    const uint32_t env = env_u32("MBF_BAM_READ_THREADS", 0);
+    if (env) return (int)env;
+    const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+    return (int)std::max<size_t>(2, std::min<size_t>(8, hw / 2 / std::max<size_t>(1, n_devices)));
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -969,15 +1333,16 @@ int mbfbam_open(const char* bam_path, const char* bai_path, mbfbam_reader** out,
     return guarded(err, errlen, [&] {
         std::unique_ptr<mbfbam_reader> h(new mbfbam_reader());
         h->r.open(bam_path, bai_path);
+        const char* stage = getenv("MBF_BAM_STAGE");  // "pread": never map the file
+        if (!(stage && !strcmp(stage, "pread"))) h->fmap = FileMapCache::get().lookup(h->r.fd);
         *out = h.release();
     });
 }
 
 void mbfbam_close(mbfbam_reader* r) {
     if (!r) return;
-    mbfbam_unpin_file(r);
     if (r->r.preload_device >= 0) cudaSetDevice(r->r.preload_device);
-    delete r;
+    delete r;  // the file mapping (and its page locks) stay in the process-wide cache
 }
 
 int32_t mbfbam_n_targets(const mbfbam_reader* r) { return (int32_t)r->r.names.size(); }
@@ -987,6 +1352,7 @@ const char* mbfbam_target_name(const mbfbam_reader* r, int32_t tid) {
 uint32_t mbfbam_target_len(const mbfbam_reader* r, int32_t tid) {
     return tid >= 0 && (size_t)tid < r->r.lens.size() ? r->r.lens[(size_t)tid] : 0;
 }
+uint64_t mbfbam_file_size(const mbfbam_reader* r) { return r->r.file_size; }
 int32_t mbfbam_tid(const mbfbam_reader* r, const char* name) {
     auto it = r->r.name2tid.find(name);
     return it == r->r.name2tid.end() ? -1 : it->second;
@@ -994,9 +1360,10 @@ int32_t mbfbam_tid(const mbfbam_reader* r, const char* name) {
 
 int mbfbam_preload(mbfbam_reader* r, int32_t device, char* err, size_t errlen) {
     return guarded(err, errlen, [&] {
-        std::lock_guard<std::mutex> lk(g_mu);
         int n = 0;
         if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) throw Error(MBFBAM_ERR_CUDA, "no such CUDA device");
+        DevSlot& slot = dev_slot(device);
+        std::lock_guard<std::mutex> lk(slot.mu);
         CK(cudaSetDevice(device));
         r->preload.ensure(r->r.file_size + 65536 + 4096);
         CK(cudaMemset((uint8_t*)r->preload.p + r->r.file_size, 0, 65536 + 4096));
@@ -1015,42 +1382,27 @@ int mbfbam_preload(mbfbam_reader* r, int32_t device, char* err, size_t errlen) {
 
 int mbfbam_pin_file(mbfbam_reader* r, char* err, size_t errlen) {
     return guarded(err, errlen, [&] {
-        std::lock_guard<std::mutex> lk(g_mu);
-        Reader& rd = r->r;
-        if (rd.map_registered) return;
         int n = 0;
         if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
-        // attempt 1: shared read-only mapping registered read-only; attempt 2: private (copy-on-write, never
-        // written) mapping registered with the default flags
-        std::string why;
-        for (int attempt = 0; attempt < 2 && !rd.map_registered; attempt++) {
-            void* p = attempt == 0 ? mmap(nullptr, (size_t)rd.file_size, PROT_READ, MAP_SHARED | MAP_POPULATE, rd.fd, 0)
-                                   : mmap(nullptr, (size_t)rd.file_size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_POPULATE, rd.fd, 0);
-            if (p == MAP_FAILED) { why = "mmap failed"; continue; }
-            cudaError_t e = cudaHostRegister(p, (size_t)rd.file_size,
-                                             attempt == 0 ? (cudaHostRegisterPortable | cudaHostRegisterReadOnly) : cudaHostRegisterPortable);
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                why = cudaGetErrorString(e);
-                munmap(p, (size_t)rd.file_size);
-                continue;
-            }
-            rd.map_ptr = (uint8_t*)p;
-            rd.map_len = (size_t)rd.file_size;
-            rd.map_registered = true;
-        }
-        if (!rd.map_registered) throw Error(MBFBAM_ERR_UNSUPPORTED, "cannot page-lock the file mapping: " + why);
-        rd.map_registered = true;
+        if (!r->fmap) throw Error(MBFBAM_ERR_UNSUPPORTED, "cannot page-lock the file mapping: the file is not mapped");
+        pin_range(*r->fmap, 0, r->fmap->size, pin_budget_bytes());
+        if (!r->fmap->seg_pinned(0, r->fmap->size))
+            throw Error(MBFBAM_ERR_UNSUPPORTED, "cannot page-lock the file mapping (refused by the platform or over MBF_BAM_PIN_MAX_MB)");
+        r->pin_now = true;
     });
 }
 
 void mbfbam_unpin_file(mbfbam_reader* r) {
-    Reader& rd = r->r;
-    if (rd.map_registered) cudaHostUnregister(rd.map_ptr);
-    rd.map_registered = false;
-    if (rd.map_ptr) munmap(rd.map_ptr, rd.map_len);
-    rd.map_ptr = nullptr;
-    rd.map_len = 0;
+    r->pin_now = false;
+    if (r->fmap) unpin_all(*r->fmap);
+}
+
+void mbfbam_host_cache_clear(void) { FileMapCache::get().clear(); }
+
+void mbfbam_release_device(int32_t device) {
+    DevSlot& slot = dev_slot(device);
+    std::lock_guard<std::mutex> lk(slot.mu);
+    slot.pipe.reset();
 }
 
 void mbfbam_drop_preload(mbfbam_reader* r) {
@@ -1100,105 +1452,46 @@ int mbfbam_count_reads(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_co
                        size_t errlen) {
     if (stats) memset(stats, 0, sizeof *stats);
     return guarded(err, errlen, [&] {
-        std::lock_guard<std::mutex> lk(g_mu);
-        double t0 = now_ms();
+        const double t0 = now_ms();
         const Reader& r = rd->r;
         const mbfbam_intervals* iv = job->intervals;
-        const mbfbam_intervals* gv = job->gene_intervals;
-        if (!iv || !gv || !out) throw Error(MBFBAM_ERR_ARG, "null argument");
+        if (!iv || !job->gene_intervals || !out) throw Error(MBFBAM_ERR_ARG, "null argument");
         if (job->mode < 0 || job->mode > 2) throw Error(MBFBAM_ERR_ARG, "bad mode");
-        if (job->each_read_counts_once)
-            throw Error(MBFBAM_ERR_UNSUPPORTED, "each_read_counts_once=True is not supported (it depends on bio's interval-tree iteration order)");
-        // gene slots
-        std::vector<uint64_t> gene_base((size_t)iv->n_contigs + 1, 0);
-        for (int c = 0; c < iv->n_contigs; c++) gene_base[(size_t)c + 1] = gene_base[(size_t)c] + iv->n_genes[c];
-        const size_t G = (size_t)gene_base[(size_t)iv->n_contigs];
-        if (G >= (1ull << 31)) throw Error(MBFBAM_ERR_UNSUPPORTED, "too many genes");
-        std::map<std::string, int> iv_index;
-        for (int c = 0; c < iv->n_contigs; c++) iv_index.emplace(iv->contig_names[c], c);
-        // chunks over gene_intervals ∩ header (chunked_genome.rs:17-31); every such contig must be in `intervals`
-        ShardPlan plan;
-        plan.chunks = make_chunks(r, gv);
-        std::vector<int32_t> tid2slot(r.names.size(), -1);
-        std::vector<int> slot_iv;  // slot -> contig index in iv
-        for (const Chunk& c : plan.chunks) {
-            if (tid2slot[(size_t)c.tid] >= 0) continue;
-            auto it = iv_index.find(r.names[(size_t)c.tid]);
-            if (it == iv_index.end())
-                throw Error(MBFBAM_ERR_ARG, "contig " + r.names[(size_t)c.tid] + " is in gene_intervals but not in intervals");
-            tid2slot[(size_t)c.tid] = (int32_t)slot_iv.size();
-            slot_iv.push_back(it->second);
-        }
+        if (job->each_read_counts_once && job->mode == MBFBAM_MODE_WEIGHTED)
+            throw Error(MBFBAM_ERR_UNSUPPORTED, "each_read_counts_once=True is not defined for count_reads_weighted");
+        int ndev_have = 0;
+        if (cudaGetDeviceCount(&ndev_have) != cudaSuccess || ndev_have == 0)
+            throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
+        const std::vector<int> devs = job_devices(job->devices, job->n_devices, job->device);
+        CountTables T;
+        build_count_tables(r, job, T);
         if (out->scanned) {
             memset(out->scanned, 0, (size_t)iv->n_contigs);
-            for (int c : slot_iv) out->scanned[c] = 1;
+            for (int c : T.slot_iv) out->scanned[c] = 1;
         }
-        // chunk_stop per slot, chunk ids global in plan.chunks order (slots are created in that order too)
-        std::vector<uint32_t> slot_chunk_off(slot_iv.size() + 1, 0), chunk_stop;
-        {
-            size_t i = 0;
-            for (size_t s = 0; s < slot_iv.size(); s++) {
-                slot_chunk_off[s] = (uint32_t)chunk_stop.size();
-                int32_t tid = plan.chunks[i].tid;
-                while (i < plan.chunks.size() && plan.chunks[i].tid == tid) chunk_stop.push_back(plan.chunks[i++].stop);
-            }
-            slot_chunk_off[slot_iv.size()] = (uint32_t)chunk_stop.size();
+        const int nsh = std::max(1, job->shard_count), sh = job->shard_index;
+        if (sh < 0 || sh >= nsh) throw Error(MBFBAM_ERR_ARG, "bad shard index/count");
+        const uint64_t prior = rd->fmap ? rd->fmap->jobs.fetch_add(1) : 0;
+        // the caller's shard is cut once more, one sub-shard per device (chunk ranges, like everything else)
+        std::vector<CountPart> parts(devs.size());
+        const int rt = default_read_threads(devs.size());
+        fan_out(devs.size(), [&](size_t k) {
+            count_on_device(rd, T, job, devs[k], sh * (int)devs.size() + (int)k, nsh * (int)devs.size(), rt, prior, parts[k]);
+        });
+        // gather on the host (dense vectors are summed; multi-mapper sets are chunk-local, so shards
+        // never share a set)
+        const size_t G = T.G;
+        std::vector<unsigned long long> h(parts[0].h.size(), 0);
+        std::vector<double> sp(2 * std::max<size_t>(G, 1), 0.0);
+        mbfbam_stats st{};
+        out->outside = 0;
+        for (const CountPart& pt : parts) {
+            for (size_t i = 0; i < h.size(); i++) h[i] += pt.h[i];
+            for (size_t i = 0; i < pt.spill.size(); i++) sp[i] += pt.spill[i];
+            out->outside += pt.outside;
+            merge_stats(st, pt.st);
         }
-        plan_shard(r, plan, job->shard_index, job->shard_count < 1 ? 1 : job->shard_count);
-        // flattened, start-sorted interval tables per slot
-        std::vector<uint32_t> slot_iv_off(slot_iv.size() + 1, 0), ivs, ive, ivp, ivg;
-        for (size_t s = 0; s < slot_iv.size(); s++) {
-            int c = slot_iv[s];
-            SortedIntervals si = sort_intervals(iv, c);
-            slot_iv_off[s] = (uint32_t)ivs.size();
-            for (size_t k = 0; k < si.start.size(); k++) {
-                if (si.gene[k] >= iv->n_genes[c]) throw Error(MBFBAM_ERR_ARG, "gene index out of range");
-                ivs.push_back(si.start[k]);
-                ive.push_back(si.end[k]);
-                ivp.push_back(si.pmax[k]);
-                ivg.push_back((uint32_t)(gene_base[(size_t)c] + si.gene[k]) | (si.strand[k] == 1 ? 0x80000000u : 0u));
-            }
-        }
-        slot_iv_off[slot_iv.size()] = (uint32_t)ivs.size();
-
-        FileSource src(&r);
-        Pipeline& p = get_pipeline(job->device);
-        p.begin_job(&src, JOB_COUNT, range_bytes(plan.ranges));
-        p.mode = job->mode;
-        p.n_genes = G;
-        p.n_count_words = (job->mode == MBFBAM_MODE_WEIGHTED ? (size_t)NH_DENSE * 2 : 2) * std::max<size_t>(G, 1);
-        p.d_counts.ensure(p.n_count_words * 8);
-        CK(cudaMemsetAsync(p.d_counts.p, 0, p.n_count_words * 8, p.s_main));
-        p.d_wspill.ensure(std::max<size_t>(G, 1) * 16);
-        CK(cudaMemsetAsync(p.d_wspill.p, 0, std::max<size_t>(G, 1) * 16, p.s_main));
-        p.d_set_size.ensure(8);
-        CK(cudaMemsetAsync(p.d_set_size.p, 0, 8, p.s_main));
-        CountCtx& c = p.cc;
-        c.tid2slot = upload(p.d_tid2slot, tid2slot, p.s_main);
-        c.n_ref = (int32_t)tid2slot.size();
-        c.slot_iv_off = upload(p.d_slot_iv_off, slot_iv_off, p.s_main);
-        c.iv_start = upload(p.d_iv_start, ivs, p.s_main);
-        c.iv_end = upload(p.d_iv_end, ive, p.s_main);
-        c.iv_pmax = upload(p.d_iv_pmax, ivp, p.s_main);
-        c.iv_gene = upload(p.d_iv_gene, ivg, p.s_main);
-        c.slot_chunk_off = upload(p.d_slot_chunk_off, slot_chunk_off, p.s_main);
-        c.chunk_stop = upload(p.d_chunk_stop, chunk_stop, p.s_main);
-        c.chunk_lo = (uint32_t)plan.lo;
-        c.chunk_hi = (uint32_t)plan.hi;
-        c.counts = p.d_counts.as<unsigned long long>();
-        c.wspill = p.d_wspill.as<double>();
-        c.n_genes = (uint32_t)G;
-        CK(cudaStreamSynchronize(p.s_main));  // uploads come from stack vectors
-        p.st.n_chunks = plan.hi - plan.lo;
-        p.run(plan.ranges);
-        // results
-        std::vector<unsigned long long> h(p.n_count_words);
-        CK(cudaMemcpy(h.data(), p.d_counts.p, p.n_count_words * 8, cudaMemcpyDeviceToHost));
-        p.st.d2h_bytes += p.n_count_words * 8;
         if (job->mode == MBFBAM_MODE_WEIGHTED) {
-            std::vector<double> sp(2 * std::max<size_t>(G, 1));
-            CK(cudaMemcpy(sp.data(), p.d_wspill.p, sp.size() * 8, cudaMemcpyDeviceToHost));
-            p.st.d2h_bytes += sp.size() * 8;
             for (size_t g = 0; g < G; g++) {
                 for (int b = 0; b < 2; b++) {
                     double acc = 0.0;
@@ -1219,82 +1512,76 @@ int mbfbam_count_reads(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_co
                 if (out->rev) out->rev[g] = h[G + g];
             }
         }
-        out->outside = p.outside_total;
-        p.st.ms_total = now_ms() - t0;
-        if (stats) *stats = p.st;
+        st.ms_total = now_ms() - t0;
+        if (stats) *stats = st;
     });
 }
 
-int mbfbam_count_introns(mbfbam_reader* rd, int32_t device, int32_t shard_index, int32_t shard_count, mbfbam_introns* out,
-                         mbfbam_stats* stats, char* err, size_t errlen) {
+int mbfbam_count_introns_multi(mbfbam_reader* rd, const int32_t* devices, int32_t n_devices, int32_t shard_index,
+                               int32_t shard_count, mbfbam_introns* out, mbfbam_stats* stats, char* err, size_t errlen) {
     if (stats) memset(stats, 0, sizeof *stats);
     if (out) memset(out, 0, sizeof *out);
     return guarded(err, errlen, [&] {
-        std::lock_guard<std::mutex> lk(g_mu);
-        double t0 = now_ms();
+        const double t0 = now_ms();
         const Reader& r = rd->r;
         if (!out) throw Error(MBFBAM_ERR_ARG, "null argument");
-        ShardPlan plan;
-        plan.chunks = make_chunks(r, nullptr);
+        int ndev_have = 0;
+        if (cudaGetDeviceCount(&ndev_have) != cudaSuccess || ndev_have == 0)
+            throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
+        const std::vector<int> devs = job_devices(devices, n_devices, 0);
+        std::vector<Chunk> chunks = make_chunks(r, nullptr);
         std::vector<uint32_t> ref_chunk_off(r.names.size() + 1, 0);
-        for (const Chunk& c : plan.chunks) ref_chunk_off[(size_t)c.tid + 1]++;
+        for (const Chunk& c : chunks) ref_chunk_off[(size_t)c.tid + 1]++;
         for (size_t i = 0; i < r.names.size(); i++) ref_chunk_off[i + 1] += ref_chunk_off[i];
-        plan_shard(r, plan, shard_index, shard_count < 1 ? 1 : shard_count);
-        FileSource src(&r);
-        Pipeline& p = get_pipeline(device);
-        p.begin_job(&src, JOB_INTRONS, range_bytes(plan.ranges));
+        const int nsh = std::max(1, shard_count), sh = shard_index;
+        if (sh < 0 || sh >= nsh) throw Error(MBFBAM_ERR_ARG, "bad shard index/count");
+        const uint64_t prior = rd->fmap ? rd->fmap->jobs.fetch_add(1) : 0;
+        std::vector<IntronPart> parts(devs.size());
+        const int rt = default_read_threads(devs.size());
+        fan_out(devs.size(), [&](size_t k) {
+            introns_on_device(rd, chunks, ref_chunk_off, devs[k], sh * (int)devs.size() + (int)k, nsh * (int)devs.size(), rt, prior, parts[k]);
+        });
+        // merge: a contig split between two devices can yield the same (tid, start, stop) twice (introns.rs:12-22
+        // adds such entries); the result holds every key once
         const size_t n_ref = r.names.size();
-        p.d_hist.ensure(std::max<size_t>(1, n_ref) * HIST_DENSE * 8);
-        CK(cudaMemsetAsync(p.d_hist.p, 0, std::max<size_t>(1, n_ref) * HIST_DENSE * 8, p.s_main));
-        p.d_scalar.ensure(16);
-        p.ic.n_ref = (int32_t)n_ref;
-        p.ic.ref_chunk_off = upload(p.d_ref_chunk_off, ref_chunk_off, p.s_main);
-        p.ic.chunk_lo = (uint32_t)plan.lo;
-        p.ic.chunk_hi = (uint32_t)plan.hi;
-        p.ic.hist = p.d_hist.as<unsigned long long>();
-        CK(cudaStreamSynchronize(p.s_main));
-        p.ensure_map(1024);
-        p.st.n_chunks = plan.hi - plan.lo;
-        p.run(plan.ranges);
-        // pull the map and the dense histogram
-        std::vector<ulonglong2> slots((size_t)p.map_cap);
-        CK(cudaMemcpy(slots.data(), p.d_map.p, (size_t)p.map_cap * 16, cudaMemcpyDeviceToHost));
-        std::vector<unsigned long long> hist(std::max<size_t>(1, n_ref) * HIST_DENSE);
-        CK(cudaMemcpy(hist.data(), p.d_hist.p, hist.size() * 8, cudaMemcpyDeviceToHost));
-        p.st.d2h_bytes += (size_t)p.map_cap * 16 + hist.size() * 8;
+        std::vector<IntronEntry> all;
+        mbfbam_stats st{};
+        out->contig_seen = (uint8_t*)calloc(n_ref + 1, 1);
+        for (const IntronPart& pt : parts) {
+            all.insert(all.end(), pt.entries.begin(), pt.entries.end());
+            for (size_t t = 0; t < n_ref; t++) out->contig_seen[t] |= pt.seen[t];
+            merge_stats(st, pt.st);
+        }
+        std::sort(all.begin(), all.end(), [](const IntronEntry& a, const IntronEntry& b) {
+            if (a.tid != b.tid) return a.tid < b.tid;
+            if (a.start != b.start) return a.start < b.start;
+            return a.stop < b.stop;
+        });
         size_t n = 0;
-        for (const auto& s : slots) if (!(s.x == ~0ull && s.y == ~0ull)) n++;
-        for (auto v : hist) if (v) n++;
+        for (size_t i = 0; i < all.size(); i++) {
+            if (n && all[n - 1].tid == all[i].tid && all[n - 1].start == all[i].start && all[n - 1].stop == all[i].stop) all[n - 1].count += all[i].count;
+            else all[n++] = all[i];
+        }
         out->tid = (int32_t*)malloc((n + 1) * 4);
         out->start = (uint32_t*)malloc((n + 1) * 4);
         out->stop = (uint32_t*)malloc((n + 1) * 4);
         out->count = (uint64_t*)malloc((n + 1) * 8);
         out->n_targets = (int32_t)n_ref;
-        out->contig_seen = (uint8_t*)calloc(n_ref + 1, 1);
-        size_t k = 0;
-        for (const auto& s : slots) {
-            if (s.x == ~0ull && s.y == ~0ull) continue;
-            out->tid[k] = (int32_t)(uint32_t)s.y;
-            out->start[k] = (uint32_t)s.x;
-            out->stop[k] = (uint32_t)(s.x >> 32);
-            out->count[k] = s.y >> 32;
-            k++;
+        for (size_t k = 0; k < n; k++) {
+            out->tid[k] = all[k].tid;
+            out->start[k] = all[k].start;
+            out->stop[k] = all[k].stop;
+            out->count[k] = all[k].count;
         }
-        for (size_t t = 0; t < n_ref; t++)
-            for (int q = 0; q < HIST_DENSE; q++)
-                if (hist[t * HIST_DENSE + q]) {
-                    out->tid[k] = (int32_t)t;
-                    out->start[k] = 0xffffffffu;
-                    out->stop[k] = 0xffffffffu - (uint32_t)q;
-                    out->count[k] = hist[t * HIST_DENSE + q];
-                    k++;
-                }
-        out->n = k;
-        // introns.rs:75-79: every chunk that was scanned inserts its contig key (possibly empty dict)
-        for (size_t i = plan.lo; i < plan.hi; i++) out->contig_seen[(size_t)plan.chunks[i].tid] = 1;
-        p.st.ms_total = now_ms() - t0;
-        if (stats) *stats = p.st;
+        out->n = n;
+        st.ms_total = now_ms() - t0;
+        if (stats) *stats = st;
     });
+}
+
+int mbfbam_count_introns(mbfbam_reader* rd, int32_t device, int32_t shard_index, int32_t shard_count, mbfbam_introns* out,
+                         mbfbam_stats* stats, char* err, size_t errlen) {
+    return mbfbam_count_introns_multi(rd, &device, 1, shard_index, shard_count, out, stats, err, errlen);
 }
 
 void mbfbam_free_introns(mbfbam_introns* x) {
@@ -1311,16 +1598,22 @@ int mbfbam_inflate_buffer(const uint8_t* bgzf, uint64_t n, uint8_t* out, uint64_
                           mbfbam_stats* stats, char* err, size_t errlen) {
     if (stats) memset(stats, 0, sizeof *stats);
     return guarded(err, errlen, [&] {
-        std::lock_guard<std::mutex> lk(g_mu);
         double t0 = now_ms();
         MemSource src(bgzf, n);
-        Pipeline& p = get_pipeline(device);
-        p.begin_job(&src, JOB_INFLATE, n);
-        p.out_host = out;
-        p.out_cap = out_cap;
+        int ndev_have = 0;
+        if (cudaGetDeviceCount(&ndev_have) != cudaSuccess || ndev_have == 0)
+            throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
+        DevSlot& slot = dev_slot(device);
+        std::lock_guard<std::mutex> lk(slot.mu);
+        Pipeline& p = slot_pipeline(slot, device);
+        p.read_threads = 0;
         std::vector<ByteRange> ranges;
         if (n) ranges.push_back({0, n, 0});
-        p.run(ranges);
+        run_with_retry(p, ranges, [&](Pipeline& p) {
+            p.begin_job(&src, JOB_INFLATE, n);
+            p.out_host = out;
+            p.out_cap = out_cap;
+        });
         if (out_len) *out_len = p.out_len;
         p.st.ms_total = now_ms() - t0;
         if (stats) *stats = p.st;

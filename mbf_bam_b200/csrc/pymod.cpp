@@ -144,10 +144,6 @@ void dict_add(PyObject* d, const std::string& key, T v) {
     dict_add<T>(d, k.ptr(), v);
 }
 
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
 
 py::dict stats_dict(const mbfbam_stats& s) {
     py::dict d;
@@ -172,13 +168,48 @@ py::dict stats_dict(const mbfbam_stats& s) {
     d["ms_gpu_tokens"] = s.ms_gpu_tokens;
     d["n_tokens"] = s.n_tokens;
     d["ms_gpu_all"] = s.ms_gpu_all;
+    d["h2d_pinned_bytes"] = s.h2d_pinned_bytes;
+    d["n_devices"] = s.n_devices;
+    d["n_retries"] = s.n_retries;
+    d["ms_pin"] = s.ms_pin;
+    return d;
+}
+
+// Devices a call fans out over when the caller did not say (Reader.set_devices): MBF_BAM_DEVICES ("all" or a
+// comma list); else, inside a torchrun/torch.distributed job (LOCAL_RANK set), this rank's GPU only; else every
+// visible GPU, but no more than one per 256 MiB of file (a small file is not worth eight pipelines).
+std::vector<int32_t> default_devices(uint64_t file_bytes) {
+    std::vector<int32_t> d;
+    const int n = mbfbam_device_count();
+    const char* v = getenv("MBF_BAM_DEVICES");
+    if (v && *v && strcmp(v, "all") != 0) {
+        for (const char* p = v; *p;) {
+            char* e = nullptr;
+            long x = strtol(p, &e, 10);
+            if (e == p) break;
+            d.push_back((int32_t)x);
+            p = *e == ',' ? e + 1 : e;
+        }
+        if (!d.empty()) return d;
+    }
+    const char* lr = getenv("LOCAL_RANK");
+    if (!(v && *v) && lr && *lr) {
+        d.push_back((int32_t)atoi(lr));
+        return d;
+    }
+    const uint64_t per = 256ull << 20;
+    int want = (int)std::min<uint64_t>((uint64_t)std::max(1, n), std::max<uint64_t>(1, (file_bytes + per - 1) / per));
+    if (v && !strcmp(v, "all")) want = std::max(1, n);
+    for (int i = 0; i < want; i++) d.push_back(i);
     return d;
 }
 
 struct PyReader {
     mbfbam_reader* r = nullptr;
     mbfbam_stats last{};
-    int device = 0, shard_index = 0, shard_count = 1;
+    std::vector<int32_t> devices;
+    int shard_index = 0, shard_count = 1;
+    uint64_t file_bytes = 0;
 
     PyReader(const std::string& filename, py::object index_filename) {
         char err[512] = {0};
@@ -189,24 +220,30 @@ struct PyReader {
             ip = idx.c_str();
         }
         if (mbfbam_open(filename.c_str(), ip, &r, err, sizeof err)) value_error(err);
-        device = env_int("MBF_BAM_DEVICE", 0);
-        const char* sh = getenv("MBF_BAM_SHARD");  // "i/n"
-        if (sh && strchr(sh, '/')) {
-            shard_index = atoi(sh);
-            shard_count = atoi(strchr(sh, '/') + 1);
-        }
+        file_bytes = mbfbam_file_size(r);
+        devices = default_devices(file_bytes);
     }
     ~PyReader() { mbfbam_close(r); }
 
-    void set_device(int d) { device = d; }
-    void set_shard(int i, int n) { shard_index = i; shard_count = n; }
+    void set_device(int d) { devices.assign(1, d); }
+    void set_devices(std::vector<int32_t> d) {
+        if (d.empty()) value_error("set_devices: empty device list");
+        devices = std::move(d);
+    }
+    std::vector<int32_t> get_devices() const { return devices; }
+    // explicit sharding for one-process-per-GPU jobs (mbf_bam_b200.dist); never read from the environment
+    void set_shard(int i, int n) {
+        if (n < 1 || i < 0 || i >= n) value_error("set_shard: need 0 <= index < count");
+        shard_index = i;
+        shard_count = n;
+    }
 
     void preload() {
         char err[512] = {0};
         int rc;
         {
             py::gil_scoped_release rel;
-            rc = mbfbam_preload(r, device, err, sizeof err);
+            rc = mbfbam_preload(r, devices[0], err, sizeof err);
         }
         if (rc) value_error(err);
     }
@@ -291,7 +328,9 @@ struct PyReader {
         job.gene_intervals = &gv.c;
         job.mode = mode;
         job.each_read_counts_once = once ? 1 : 0;
-        job.device = device;
+        job.device = devices[0];
+        job.n_devices = (int32_t)devices.size();
+        job.devices = devices.data();
         job.shard_index = shard_index;
         job.shard_count = shard_count;
         mbfbam_counts out{};
@@ -393,9 +432,9 @@ struct PyReader {
 
     // dense vectors (bytes of u64 / f64) for the one-process-per-GPU merge: the caller all-reduces them
     // and calls assemble()
-    py::tuple count_reads_raw(int mode, const py::dict& intervals, const py::dict& gene_intervals) {
+    py::tuple count_reads_raw(int mode, const py::dict& intervals, const py::dict& gene_intervals, py::object once) {
         Raw raw;
-        run(mode, intervals, gene_intervals, false, raw);
+        run(mode, intervals, gene_intervals, !once.is_none() && py::cast<bool>(once), raw);
         size_t G = raw.fwd.size() - 1;
         auto b = [](const void* p, size_t n) { return py::bytes((const char*)p, n); };
         return py::make_tuple(b(raw.fwd.data(), G * 8), b(raw.rev.data(), G * 8), b(raw.wfwd.data(), G * 8),
@@ -430,7 +469,7 @@ struct PyReader {
         int rc;
         {
             py::gil_scoped_release rel;
-            rc = mbfbam_count_introns(r, device, shard_index, shard_count, &res, &last, err, sizeof err);
+            rc = mbfbam_count_introns_multi(r, devices.data(), (int32_t)devices.size(), shard_index, shard_count, &res, &last, err, sizeof err);
         }
         if (rc) {
             mbfbam_free_introns(&res);
@@ -501,6 +540,9 @@ PYBIND11_MODULE(mbf_bam, m) {
           py::arg("filename"), py::arg("index_filename") = py::none(), "python wrapper for py_count_introns (reference src/lib.rs:216)");
     m.def("last_stats", []() { return stats_dict(g_last_stats); }, "measurements of the most recent module-level call");
     m.def("device_count", []() { return mbfbam_device_count(); });
+    m.def("release_device", [](int device) { mbfbam_release_device(device); }, py::arg("device") = 0,
+          "free the cached pipeline (device + pinned buffers) of a device");
+    m.def("host_cache_clear", []() { mbfbam_host_cache_clear(); }, "drop the process-wide file mappings and their page locks");
 
     m.def("inflate_buffer", [](py::bytes data, int device) {
         std::string s = data;
@@ -544,7 +586,10 @@ PYBIND11_MODULE(mbf_bam, m) {
     py::class_<PyReader>(m, "Reader", "open BAM + BAI once (reference src/bam_ext.rs:6 open_bam), run several jobs")
         .def(py::init<const std::string&, py::object>(), py::arg("filename"), py::arg("index_filename") = py::none())
         .def("set_device", &PyReader::set_device)
-        .def("set_shard", &PyReader::set_shard)
+        .def("set_devices", &PyReader::set_devices, "CUDA ordinals one call fans out over (default: see default_devices)")
+        .def("devices", &PyReader::get_devices)
+        .def("set_shard", &PyReader::set_shard, py::arg("index"), py::arg("count"),
+             "this reader counts only shard `index` of `count` chunk-range shards (one-process-per-GPU jobs)")
         .def("preload", &PyReader::preload)
         .def("drop_preload", &PyReader::drop_preload)
         .def("pin_file", &PyReader::pin_file, "page-lock a mapping of the file; False if the platform refuses")
@@ -554,7 +599,8 @@ PYBIND11_MODULE(mbf_bam, m) {
         .def("plan", &PyReader::plan, py::arg("gene_intervals"), py::arg("shard_index") = 0, py::arg("shard_count") = 1)
         .def("count_reads", &PyReader::count_reads, py::arg("mode"), py::arg("intervals"), py::arg("gene_intervals"),
              py::arg("each_read_counts_once") = py::none())
-        .def("count_reads_raw", &PyReader::count_reads_raw)
+        .def("count_reads_raw", &PyReader::count_reads_raw, py::arg("mode"), py::arg("intervals"), py::arg("gene_intervals"),
+             py::arg("each_read_counts_once") = py::none())
         .def("assemble", &PyReader::assemble)
         .def("count_introns", &PyReader::count_introns)
         .def("stats", &PyReader::stats);

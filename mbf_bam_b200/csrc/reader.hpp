@@ -76,10 +76,6 @@ struct Reader {
     // optional device-resident copy of the whole file (mbfbam_preload)
     int preload_device = -1;
     uint8_t* preload_ptr = nullptr;
-    // optional page-locked mapping of the file (mbfbam_pin_file): H2D copies then read the page cache directly
-    uint8_t* map_ptr = nullptr;
-    size_t map_len = 0;
-    bool map_registered = false;
 
     ~Reader() {
         if (fd >= 0) ::close(fd);
@@ -328,9 +324,89 @@ struct Chunk {
 struct SortedIntervals {
     std::vector<uint32_t> start, end, pmax, gene;  // gene = local gene_no
     std::vector<int8_t> strand;
+    std::vector<uint32_t> rank;  // position in bio's find() iteration order (only when asked for)
 };
 
-inline SortedIntervals sort_intervals(const mbfbam_intervals* iv, int c) {
+// bio 0.25 IntervalTree (Cargo.lock:100-101; source not vendored, restated from SURVEY.md App. B.2): an AVL tree
+// keyed on interval.start -- insert descends LEFT when new.start <= node.start, else right, then repairs on the
+// way up with the usual single/double rotations -- whose find() iterator pops a node, pushes its left child,
+// then its right child, and yields the node: hits come in the order node, right subtree, left subtree.
+// Pruning skips whole subtrees but never reorders, so every interval has a static rank in that traversal and
+// "the first hit" (each_read_counts_once, reference src/count_reads/counters.rs:83-92,173-182) is the
+// overlapping interval of minimum rank.  Returns rank[i] for the i-th inserted interval.
+inline std::vector<uint32_t> bio_tree_ranks(const uint32_t* starts, size_t n) {
+    struct Node { int32_t l = -1, r = -1, h = 1; };
+    std::vector<Node> nd(n);
+    auto height = [&](int32_t x) { return x < 0 ? 0 : nd[(size_t)x].h; };
+    auto update = [&](int32_t x) { nd[(size_t)x].h = 1 + std::max(height(nd[(size_t)x].l), height(nd[(size_t)x].r)); };
+    auto rot_right = [&](int32_t x) {  // returns the new subtree root
+        int32_t y = nd[(size_t)x].l;
+        nd[(size_t)x].l = nd[(size_t)y].r;
+        nd[(size_t)y].r = x;
+        update(x);
+        update(y);
+        return y;
+    };
+    auto rot_left = [&](int32_t x) {
+        int32_t y = nd[(size_t)x].r;
+        nd[(size_t)x].r = nd[(size_t)y].l;
+        nd[(size_t)y].l = x;
+        update(x);
+        update(y);
+        return y;
+    };
+    auto repair = [&](int32_t x) {
+        const int lh = height(nd[(size_t)x].l), rh = height(nd[(size_t)x].r);
+        if (std::abs(lh - rh) <= 1) { update(x); return x; }
+        if (rh > lh) {
+            int32_t r = nd[(size_t)x].r;
+            if (height(nd[(size_t)r].l) > height(nd[(size_t)r].r)) nd[(size_t)x].r = rot_right(r);
+            return rot_left(x);
+        }
+        int32_t l = nd[(size_t)x].l;
+        if (height(nd[(size_t)l].r) > height(nd[(size_t)l].l)) nd[(size_t)x].l = rot_left(l);
+        return rot_right(x);
+    };
+    int32_t root = -1;
+    std::vector<int32_t> path;
+    std::vector<uint8_t> went_left;
+    for (size_t i = 0; i < n; i++) {
+        if (root < 0) { root = (int32_t)i; continue; }
+        path.clear();
+        went_left.clear();
+        int32_t cur = root;
+        for (;;) {
+            path.push_back(cur);
+            const bool left = starts[i] <= starts[(size_t)cur];
+            went_left.push_back(left ? 1 : 0);
+            int32_t& child = left ? nd[(size_t)cur].l : nd[(size_t)cur].r;
+            if (child < 0) { child = (int32_t)i; break; }
+            cur = child;
+        }
+        // repair bottom-up; a rotation changes the subtree root, which the parent must point to
+        for (size_t d = path.size(); d-- > 0;) {
+            const int32_t x = path[d];
+            const int32_t nr = repair(x);
+            if (d == 0) root = nr;
+            else if (went_left[d - 1]) nd[(size_t)path[d - 1]].l = nr;
+            else nd[(size_t)path[d - 1]].r = nr;
+        }
+    }
+    std::vector<uint32_t> rank(n, 0);
+    std::vector<int32_t> stack;
+    if (root >= 0) stack.push_back(root);
+    uint32_t k = 0;
+    while (!stack.empty()) {
+        const int32_t x = stack.back();
+        stack.pop_back();
+        rank[(size_t)x] = k++;
+        if (nd[(size_t)x].l >= 0) stack.push_back(nd[(size_t)x].l);
+        if (nd[(size_t)x].r >= 0) stack.push_back(nd[(size_t)x].r);
+    }
+    return rank;
+}
+
+inline SortedIntervals sort_intervals(const mbfbam_intervals* iv, int c, bool with_rank = false) {
     uint64_t a = iv->iv_offsets[c], b = iv->iv_offsets[c + 1];
     std::vector<uint32_t> order((size_t)(b - a));
     for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
@@ -340,6 +416,8 @@ inline SortedIntervals sort_intervals(const mbfbam_intervals* iv, int c) {
         return x < y;
     });
     SortedIntervals s;
+    std::vector<uint32_t> ranks;
+    if (with_rank) ranks = bio_tree_ranks(iv->iv_start + a, order.size());
     uint32_t m = 0;
     for (uint32_t o : order) {
         uint32_t st = iv->iv_start[a + o], en = iv->iv_end[a + o];
@@ -348,29 +426,29 @@ inline SortedIntervals sort_intervals(const mbfbam_intervals* iv, int c) {
         s.end.push_back(en);
         s.gene.push_back(iv->iv_gene[a + o]);
         s.strand.push_back(iv->iv_strand[a + o]);
+        if (with_rank) s.rank.push_back(ranks[o]);
         m = std::max(m, en);
         s.pmax.push_back(m);
     }
     return s;
 }
 
-// chunked_genome.rs:93-109: push the chunk's right edge past any gene interval covering it.  When
-// several cover it the reference takes whatever bio's tree yields first; every choice reaches the
-// same fixed point except in 1-bp-abutting corner layouts.  We take the largest end.
+// chunked_genome.rs:93-109: push the chunk's right edge past a gene interval covering it.  When several
+// cover it the reference takes the FIRST entry bio's find(stop..stop+1) yields, i.e. the covering interval of
+// least rank in the tree's iteration order (bio_tree_ranks above).
 inline uint32_t extend_stop(const SortedIntervals& g, uint32_t stop) {
     for (;;) {
-        size_t hi = (size_t)(std::upper_bound(g.start.begin(), g.start.end(), stop) - g.start.begin());
-        uint32_t best = 0;
-        bool found = false;
+        size_t hi = (size_t)(std::upper_bound(g.start.begin(), g.start.end(), stop) - g.start.begin());  // start <= stop
+        uint32_t best_rank = 0xffffffffu, best_end = 0;
         for (size_t i = hi; i-- > 0;) {
             if (g.pmax[i] <= stop) break;
-            if (g.end[i] > stop) {
-                best = found ? std::max(best, g.end[i]) : g.end[i];
-                found = true;
+            if (g.end[i] > stop && g.rank[i] < best_rank) {
+                best_rank = g.rank[i];
+                best_end = g.end[i];
             }
         }
-        if (!found) return stop;
-        stop = best + 1;
+        if (best_rank == 0xffffffffu) return stop;
+        stop = best_end + 1;
     }
 }
 
@@ -385,7 +463,7 @@ inline std::vector<Chunk> make_chunks(const Reader& r, const mbfbam_intervals* g
             auto it = r.name2tid.find(genes->contig_names[c]);
             if (it == r.name2tid.end()) continue;  // chunked_genome.rs:21-25
             tid = it->second;
-            g = sort_intervals(genes, c);
+            g = sort_intervals(genes, c, true);
         }
         uint32_t len = r.lens[(size_t)tid], start = 0;
         do {

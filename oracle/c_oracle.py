@@ -80,7 +80,8 @@ def flatten(intervals: dict):
     return iv, a, names, gene_ids
 
 
-def raw_counts(path, index_path, intervals, gene_intervals, mode, nthreads=1, sample_chunks=0, chunk_lo=-1, chunk_hi=-1):
+def raw_counts(path, index_path, intervals, gene_intervals, mode, nthreads=1, sample_chunks=0, chunk_lo=-1, chunk_hi=-1,
+               each_read_counts_once=False):
     iv, keep1, names, gene_ids = flatten(intervals)
     gv, keep2, _, _ = flatten(gene_intervals)
     tot = int(keep1["n_genes"].sum())
@@ -95,7 +96,7 @@ def raw_counts(path, index_path, intervals, gene_intervals, mode, nthreads=1, sa
     err = C.create_string_buffer(512)
     rc = lib().oracle_count_reads(
         path.encode(), index_path.encode() if index_path else None, C.byref(iv), C.byref(gv),
-        C.c_int(mode), C.c_int(nthreads), C.c_int64(sample_chunks), C.c_int64(chunk_lo), C.c_int64(chunk_hi),
+        C.c_int(mode), C.c_int(1 if each_read_counts_once else 0), C.c_int(nthreads), C.c_int64(sample_chunks), C.c_int64(chunk_lo), C.c_int64(chunk_hi),
         fwd.ctypes.data_as(C.c_void_p), rev.ctypes.data_as(C.c_void_p),
         wf.ctypes.data_as(C.c_void_p), wr.ctypes.data_as(C.c_void_p),
         scanned.ctypes.data_as(C.c_void_p), C.byref(outside), C.byref(nrec), C.byref(nck), err,
@@ -160,28 +161,25 @@ def _assemble_dual(r, key_f, key_r, conv):
 
 def count_reads_unstranded(path, index_path, intervals, gene_intervals, each_read_counts_once=None,
                            nthreads=1):
-    if each_read_counts_once:
-        raise NotImplementedError
-    return _assemble_unstranded(raw_counts(path, index_path, intervals, gene_intervals, 0, nthreads))
+    return _assemble_unstranded(raw_counts(path, index_path, intervals, gene_intervals, 0, nthreads,
+                                           each_read_counts_once=bool(each_read_counts_once)))
 
 
 def count_reads_stranded(path, index_path, intervals, gene_intervals, each_read_counts_once=None,
                          nthreads=1):
-    if each_read_counts_once:
-        raise NotImplementedError
-    return _assemble_dual(raw_counts(path, index_path, intervals, gene_intervals, 1, nthreads),
-                          "fwd", "rev", int)
+    return _assemble_dual(raw_counts(path, index_path, intervals, gene_intervals, 1, nthreads,
+                                     each_read_counts_once=bool(each_read_counts_once)), "fwd", "rev", int)
 
 
 def count_reads_weighted(path, index_path, intervals, gene_intervals, each_read_counts_once=None,
                          nthreads=1):
     if each_read_counts_once:
-        raise NotImplementedError
+        raise ValueError("each_read_counts_once=True is not defined for count_reads_weighted")
     return _assemble_dual(raw_counts(path, index_path, intervals, gene_intervals, 2, nthreads),
                           "wfwd", "wrev", float)
 
 
-def count_introns(path, index_path=None, nthreads=1, return_stats=False):
+def count_introns(path, index_path=None, nthreads=1, return_stats=False, sample_chunks=0):
     n = C.c_uint64(0)
     tid = C.POINTER(C.c_int32)()
     st = C.POINTER(C.c_uint32)()
@@ -189,15 +187,16 @@ def count_introns(path, index_path=None, nthreads=1, return_stats=False):
     cnt = C.POINTER(C.c_uint64)()
     seen = np.zeros(1 << 16, dtype=np.uint8)
     nrec = C.c_uint64(0)
+    nck = C.c_int64(0)
     err = C.create_string_buffer(512)
     L = lib()
     rc = L.oracle_count_introns(path.encode(), index_path.encode() if index_path else None,
-                                C.c_int(nthreads), C.byref(n), C.byref(tid), C.byref(st), C.byref(en),
+                                C.c_int(nthreads), C.c_int64(sample_chunks), C.byref(nck), C.byref(n), C.byref(tid), C.byref(st), C.byref(en),
                                 C.byref(cnt), seen.ctypes.data_as(C.c_void_p), C.c_int32(len(seen)),
                                 C.byref(nrec), err, C.c_size_t(512))
     if rc:
         raise ValueError(err.value.decode())
-    from mbf_bam_b200.synth.bamio import iter_bgzf_blocks  # noqa: F401  (header names via reader below)
+    from synth.bamio import iter_bgzf_blocks  # noqa: F401  (header names via reader below)
     names = header_names(path)
     out = {names[t]: {} for t in range(len(names)) if seen[t]}
     for i in range(n.value):
@@ -205,7 +204,7 @@ def count_introns(path, index_path=None, nthreads=1, return_stats=False):
     for p in (tid, st, en, cnt):
         L.oracle_free(p)
     if return_stats:
-        return out, dict(n_records=nrec.value)
+        return out, dict(n_records=nrec.value, n_chunks=nck.value)
     return out
 
 

@@ -246,81 +246,130 @@ static char* default_bai(const char* bam, const char* bai) {
     return NULL;
 }
 
-/* ------------------------------------------------------------------ interval sets */
+/* ------------------------------------------------------------------ interval trees */
+/* bio 0.25.0 data_structures::interval_tree::IntervalTree<u32,(u32,i8)> (reference Cargo.lock:100-101,
+ * src/count_reads/mod.rs:19; the crate's source is not under /root/reference: restated from its published
+ * algorithm, SURVEY.md App. B.2 -- PARITY UNPINNED).  AVL tree keyed on interval.start; insert descends
+ * LEFT when new.start <= node.start, else right, and repairs every node on the way back up; find() pops a
+ * node from an explicit stack, pushes its left child when query.start < node.max and, when
+ * query.end > node.start, its right child, and yields the node if it overlaps -- so hits come in the order
+ * node, right subtree, left subtree.  The counters depend on that order only with each_read_counts_once
+ * (counters.rs:83-92,173-182) and at chunk edges covered by several genes (chunked_genome.rs:98). */
+typedef struct {
+    uint32_t start, end, max, gene;
+    int32_t l, r;
+    int32_t h;
+    int8_t strand;
+} tnode_t;
 typedef struct {
     uint32_t n;
-    uint32_t *start, *end, *gene, *pmax; /* sorted by start; pmax = prefix max of end */
-    int8_t* strand;
+    int32_t root;
+    tnode_t* nd;
 } ivset_t;
 
-typedef struct { uint32_t s, e, g; int8_t st; } ivrow_t;
-static int cmp_row(const void* a, const void* b) {
-    const ivrow_t *x = a, *y = b;
-    if (x->s != y->s) return x->s < y->s ? -1 : 1;
-    if (x->e != y->e) return x->e < y->e ? -1 : 1;
-    return x->g < y->g ? -1 : (x->g > y->g);
+static inline int t_h(const ivset_t* t, int32_t x) { return x < 0 ? 0 : t->nd[x].h; }
+static void t_update(ivset_t* t, int32_t x) {
+    tnode_t* n = &t->nd[x];
+    int lh = t_h(t, n->l), rh = t_h(t, n->r);
+    n->h = 1 + (lh > rh ? lh : rh);
+    uint32_t m = n->end;
+    if (n->l >= 0 && t->nd[n->l].max > m) m = t->nd[n->l].max;
+    if (n->r >= 0 && t->nd[n->r].max > m) m = t->nd[n->r].max;
+    n->max = m;
 }
+static int32_t t_rot_right(ivset_t* t, int32_t x) {
+    int32_t y = t->nd[x].l;
+    t->nd[x].l = t->nd[y].r;
+    t->nd[y].r = x;
+    t_update(t, x);
+    t_update(t, y);
+    return y;
+}
+static int32_t t_rot_left(ivset_t* t, int32_t x) {
+    int32_t y = t->nd[x].r;
+    t->nd[x].r = t->nd[y].l;
+    t->nd[y].l = x;
+    t_update(t, x);
+    t_update(t, y);
+    return y;
+}
+static int32_t t_repair(ivset_t* t, int32_t x) {
+    int lh = t_h(t, t->nd[x].l), rh = t_h(t, t->nd[x].r);
+    if (lh - rh <= 1 && rh - lh <= 1) { t_update(t, x); return x; }
+    if (rh > lh) {
+        int32_t r = t->nd[x].r;
+        if (t_h(t, t->nd[r].l) > t_h(t, t->nd[r].r)) t->nd[x].r = t_rot_right(t, r);
+        return t_rot_left(t, x);
+    }
+    int32_t l = t->nd[x].l;
+    if (t_h(t, t->nd[l].r) > t_h(t, t->nd[l].l)) t->nd[x].l = t_rot_left(t, l);
+    return t_rot_right(t, x);
+}
+static int32_t t_insert(ivset_t* t, int32_t x, int32_t nw) {
+    if (x < 0) return nw;
+    if (t->nd[nw].start <= t->nd[x].start) t->nd[x].l = t_insert(t, t->nd[x].l, nw);
+    else t->nd[x].r = t_insert(t, t->nd[x].r, nw);
+    return t_repair(t, x);
+}
+/* src/count_reads/mod.rs:27-45 build_tree: intervals are inserted in list order */
 static void build_ivset(const mbfbam_intervals* iv, int c, ivset_t* s) {
     uint64_t a = iv->iv_offsets[c], b = iv->iv_offsets[c + 1];
     s->n = (uint32_t)(b - a);
-    ivrow_t* rows = malloc((s->n + 1) * sizeof *rows);
+    s->root = -1;
+    s->nd = malloc(((size_t)s->n + 1) * sizeof *s->nd);
     for (uint32_t i = 0; i < s->n; i++) {
-        rows[i].s = iv->iv_start[a + i];
-        rows[i].e = iv->iv_end[a + i];
-        rows[i].g = iv->iv_gene[a + i];
-        rows[i].st = iv->iv_strand[a + i];
+        tnode_t* n = &s->nd[i];
+        n->start = iv->iv_start[a + i];
+        n->end = iv->iv_end[a + i];
+        n->max = n->end;
+        n->gene = iv->iv_gene[a + i];
+        n->strand = iv->iv_strand[a + i];
+        n->l = n->r = -1;
+        n->h = 1;
+        s->root = t_insert(s, s->root, (int32_t)i);
     }
-    qsort(rows, s->n, sizeof *rows, cmp_row);
-    s->start = malloc((s->n + 1) * 4);
-    s->end = malloc((s->n + 1) * 4);
-    s->gene = malloc((s->n + 1) * 4);
-    s->pmax = malloc((s->n + 1) * 4);
-    s->strand = malloc(s->n + 1);
-    uint32_t m = 0;
-    for (uint32_t i = 0; i < s->n; i++) {
-        s->start[i] = rows[i].s;
-        s->end[i] = rows[i].e;
-        s->gene[i] = rows[i].g;
-        s->strand[i] = rows[i].st;
-        if (rows[i].e > m) m = rows[i].e;
-        s->pmax[i] = m;
-    }
-    free(rows);
 }
-static void free_ivset(ivset_t* s) {
-    free(s->start); free(s->end); free(s->gene); free(s->pmax); free(s->strand);
+static void free_ivset(ivset_t* s) { free(s->nd); }
+
+/* find(q0..q1) as an explicit-stack iterator (bio's IntervalTreeIterator::next) */
+typedef struct {
+    int32_t stack[160]; /* <= 2 * height entries; an AVL tree of 2^32 nodes is < 47 high */
+    int sp;
+    uint32_t q0, q1;
+} tfind_t;
+static void t_find_begin(const ivset_t* t, tfind_t* f, uint32_t q0, uint32_t q1) {
+    f->sp = 0;
+    f->q0 = q0;
+    f->q1 = q1;
+    if (t->root >= 0) f->stack[f->sp++] = t->root;
 }
-/* first index with start >= x */
-static uint32_t lower_start(const ivset_t* s, uint32_t x) {
-    uint32_t lo = 0, hi = s->n;
-    while (lo < hi) {
-        uint32_t mid = lo + (hi - lo) / 2;
-        if (s->start[mid] < x) lo = mid + 1; else hi = mid;
+static int32_t t_find_next(const ivset_t* t, tfind_t* f) {
+    while (f->sp) {
+        int32_t x = f->stack[--f->sp];
+        const tnode_t* n = &t->nd[x];
+        if (f->q0 < n->max) {
+            if (n->l >= 0) f->stack[f->sp++] = n->l;
+            if (f->q1 > n->start) {
+                if (n->r >= 0) f->stack[f->sp++] = n->r;
+                if (f->q0 < n->end && n->start < f->q1) return x;
+            }
+        }
     }
-    return lo;
+    return -1;
 }
 
 /* ------------------------------------------------------------------ chunk table */
 typedef struct { int32_t contig; int32_t tid; uint32_t start, stop; } chunk_t;
 
-/* src/count_reads/chunked_genome.rs:72-119.  When several gene intervals cover the provisional
- * stop the reference takes whichever bio's tree yields first; the fixed point is the same for all
- * choices except in 1-bp-abutting corner layouts, which the generators reject.
- * We take the covering interval with the largest end. */
+/* src/count_reads/chunked_genome.rs:93-109: while tree.find(stop..stop+1) yields anything, the edge moves
+ * past the FIRST interval it yields. */
 static uint32_t extend_stop(const ivset_t* g, uint32_t stop) {
     for (;;) {
-        uint32_t hi = lower_start(g, stop + 1); /* start <= stop */
-        uint32_t best = 0;
-        int found = 0;
-        for (uint32_t i = hi; i-- > 0;) {
-            if (g->pmax[i] <= stop) break;
-            if (g->end[i] > stop) { /* start <= stop < end */
-                if (!found || g->end[i] > best) best = g->end[i];
-                found = 1;
-            }
-        }
-        if (!found) return stop;
-        stop = best + 1;
+        tfind_t f;
+        t_find_begin(g, &f, stop, stop + 1);
+        int32_t x = t_find_next(g, &f);
+        if (x < 0) return stop;
+        stop = g->nd[x].end + 1;
     }
 }
 static chunk_t* make_chunks(const bamidx_t* h, const mbfbam_intervals* genes, const ivset_t* gsets,
@@ -497,6 +546,7 @@ typedef struct {
     size_t n_chunks;
     size_t next_chunk;  /* atomic */
     int mode;
+    int once;  /* each_read_counts_once */
     int introns;
     int nthreads;
     int failed;
@@ -636,10 +686,9 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
                 uint32_t b0 = p, b1 = p + len;
                 p += len;
                 if (j->mode == MBFBAM_MODE_UNSTRANDED && b0 >= ck->stop) continue; /* counters.rs:52 */
-                uint32_t hi = lower_start(set, b1);
-                for (uint32_t k = hi; k-- > 0;) {
-                    if (set->pmax[k] <= b0) break;
-                    if (!(set->start[k] < b1 && b0 < set->end[k])) continue;
+                tfind_t f;
+                t_find_begin(set, &f, b0, b1);
+                for (int32_t k; (k = t_find_next(set, &f)) >= 0;) { /* counters.rs:61 / :144 tree.find(iv.0..iv.1) */
                     hit = 1;
                     if (!have_nh) {
                         int rc = aux_nh(aux, end, &nh); /* counters.rs:65-66 */
@@ -649,13 +698,15 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
                     }
                     int bucket = 0;
                     if (j->mode != MBFBAM_MODE_UNSTRANDED) { /* counters.rs:151 */
-                        int rv = (flag & 0x10) != 0, st = set->strand[k];
+                        int rv = (flag & 0x10) != 0, st = set->nd[k].strand;
                         bucket = ((st == 1 && !rv) || (st != 1 && rv)) ? 0 : 1;
                     }
-                    uint32_t g = set->gene[k];
+                    uint32_t g = set->nd[k].gene;
                     if (j->mode == MBFBAM_MODE_WEIGHTED || nh == 1) vec_add_unique(&seen[bucket], g);
                     else mm_insert(&mm, (uint8_t)bucket, g, qn, l_qn ? l_qn - 1 : 0);
+                    if (j->once) break; /* counters.rs:83-85 / :173-175 */
                 }
+                if (j->once && hit) break; /* counters.rs:87-92 / :177-182 */
             } else if (op == 2 || op == 3) {
                 p += len;
             }
@@ -726,7 +777,7 @@ static int open_idx(const char* bam, const char* bai, bamidx_t* idx, char* err, 
  * (bench.py's bounded CPU sample); n_records_out reports the records they owned.
  * chunk_lo >= 0: only chunks [chunk_lo, chunk_hi) of the chunk table (what one shard owns). */
 int oracle_count_reads(const char* bam, const char* bai, const mbfbam_intervals* iv,
-                       const mbfbam_intervals* genes, int mode, int nthreads, int64_t sample_chunks,
+                       const mbfbam_intervals* genes, int mode, int each_read_counts_once, int nthreads, int64_t sample_chunks,
                        int64_t chunk_lo, int64_t chunk_hi,
                        uint64_t* fwd, uint64_t* rev, double* wfwd, double* wrev, uint8_t* scanned,
                        uint64_t* outside, uint64_t* n_records_out, int64_t* n_chunks_out, char* err,
@@ -737,7 +788,7 @@ int oracle_count_reads(const char* bam, const char* bai, const mbfbam_intervals*
     job_t j;
     memset(&j, 0, sizeof j);
     pthread_mutex_init(&j.mu, NULL);
-    j.bam_path = bam; j.idx = &idx; j.iv = iv; j.mode = mode; j.nthreads = nthreads < 1 ? 1 : nthreads;
+    j.bam_path = bam; j.idx = &idx; j.iv = iv; j.mode = mode; j.once = each_read_counts_once != 0; j.nthreads = nthreads < 1 ? 1 : nthreads;
     j.sets = calloc((size_t)iv->n_contigs + 1, sizeof(ivset_t));
     j.gene_base = calloc((size_t)iv->n_contigs + 1, 8);
     for (int c = 0; c < iv->n_contigs; c++) {
@@ -799,7 +850,8 @@ int oracle_count_reads(const char* bam, const char* bai, const mbfbam_intervals*
 }
 
 /* introns.rs:56-88.  Result arrays are malloc'ed; free with oracle_free. */
-int oracle_count_introns(const char* bam, const char* bai, int nthreads, uint64_t* n_out, int32_t** tid_out,
+int oracle_count_introns(const char* bam, const char* bai, int nthreads, int64_t sample_chunks, int64_t* n_chunks_out,
+                         uint64_t* n_out, int32_t** tid_out,
                          uint32_t** start_out, uint32_t** stop_out, uint64_t** count_out,
                          uint8_t* contig_seen, int32_t n_targets_cap, uint64_t* n_records_out, char* err,
                          size_t errlen) {
@@ -812,6 +864,12 @@ int oracle_count_introns(const char* bam, const char* bai, int nthreads, uint64_
     j.bam_path = bam; j.idx = &idx; j.introns = 1; j.nthreads = nthreads < 1 ? 1 : nthreads;
     size_t nck;
     chunk_t* cks = make_chunks(&idx, NULL, NULL, &nck);
+    if (sample_chunks > 0 && (size_t)sample_chunks < nck) { /* bounded sample for the timed CPU baseline */
+        size_t step = nck / (size_t)sample_chunks, m = 0;
+        for (size_t i = 0; i < nck; i += step) cks[m++] = cks[i];
+        nck = m;
+    }
+    if (n_chunks_out) *n_chunks_out = (int64_t)nck;
     j.chunks = cks; j.n_chunks = nck;
     j.imaps = calloc((size_t)j.nthreads, sizeof(imap));
     for (int t = 0; t < j.nthreads; t++) imap_init(&j.imaps[t], 1 << 12);

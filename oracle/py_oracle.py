@@ -27,7 +27,7 @@ import sys
 from collections import defaultdict
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from mbf_bam_b200.synth.bamio import aux_get_int, read_bam  # noqa: E402
+from synth.bamio import aux_get_int, read_bam  # noqa: E402
 
 CHUNK_SIZE = 1_000_000  # reference src/count_reads/chunked_genome.rs:75
 U32 = 0xFFFFFFFF
@@ -77,38 +77,147 @@ def find(ivs, b0, b1):
     return [iv for iv in ivs if iv[0] < b1 and b0 < iv[1]]
 
 
-def chunk_fixed_points(gene_ivs, stop):
-    """All fixed points reachable by `while some iv covers stop: stop = iv.end + 1`
-    (reference chunked_genome.rs:93-109).  More than one => result depends on bio's
-    tree order; callers reject such gene sets."""
-    seen = set()
-    finals = set()
-    stack = [stop]
-    while stack:
-        s = stack.pop()
-        if s in seen:
-            continue
-        seen.add(s)
-        cov = [iv for iv in gene_ivs if iv[0] <= s < iv[1]]
-        if not cov:
-            finals.add(s)
-        for iv in cov:
-            stack.append(iv[1] + 1)
-    return finals
+class BioTree:
+    """bio 0.25.0 data_structures::interval_tree::IntervalTree (Cargo.lock:100-101; the crate's source is not
+    under /root/reference -- restated from its published algorithm; PARITY UNPINNED).
+
+    An AVL tree keyed on interval.start.  insert(): descend LEFT when new.start <= node.start, else right;
+    every node on the way back up is repaired (height/max update, or the usual single/double rotation).
+    find(): explicit stack seeded with the root; pop a node, if query.start < node.max push its left child
+    and, if query.end > node.start, push its right child and yield the node when it overlaps.  The stack is
+    LIFO, so hits come in the order: node, right subtree, left subtree.
+
+    Only two things in the counters depend on that order: each_read_counts_once=True (first hit wins,
+    reference counters.rs:83-92,173-182) and which covering gene moves a chunk edge when several do
+    (chunked_genome.rs:98)."""
+
+    class Node:
+        __slots__ = ("start", "end", "value", "max", "height", "left", "right")
+
+        def __init__(self, start, end, value):
+            self.start, self.end, self.value = start, end, value
+            self.max = end
+            self.height = 1
+            self.left = self.right = None
+
+    def __init__(self):
+        self.root = None
+
+    @staticmethod
+    def _h(n):
+        return n.height if n is not None else 0
+
+    @classmethod
+    def _update(cls, n):
+        n.height = 1 + max(cls._h(n.left), cls._h(n.right))
+        m = n.end
+        if n.left is not None and n.left.max > m:
+            m = n.left.max
+        if n.right is not None and n.right.max > m:
+            m = n.right.max
+        n.max = m
+
+    @classmethod
+    def _rot_right(cls, n):
+        l = n.left
+        n.left = l.right
+        l.right = n
+        cls._update(n)
+        cls._update(l)
+        return l
+
+    @classmethod
+    def _rot_left(cls, n):
+        r = n.right
+        n.right = r.left
+        r.left = n
+        cls._update(n)
+        cls._update(r)
+        return r
+
+    @classmethod
+    def _repair(cls, n):
+        lh, rh = cls._h(n.left), cls._h(n.right)
+        if abs(lh - rh) <= 1:
+            cls._update(n)
+            return n
+        if rh > lh:
+            if cls._h(n.right.left) > cls._h(n.right.right):
+                n.right = cls._rot_right(n.right)
+            return cls._rot_left(n)
+        if cls._h(n.left.right) > cls._h(n.left.left):
+            n.left = cls._rot_left(n.left)
+        return cls._rot_right(n)
+
+    def insert(self, start, end, value):
+        if start > end:
+            raise ValueError("interval start > end")  # bio panics
+        new = BioTree.Node(start, end, value)
+        if self.root is None:
+            self.root = new
+            return
+        path = []
+        n = self.root
+        while True:
+            left = start <= n.start
+            path.append((n, left))
+            nxt = n.left if left else n.right
+            if nxt is None:
+                if left:
+                    n.left = new
+                else:
+                    n.right = new
+                break
+            n = nxt
+        for i in range(len(path) - 1, -1, -1):  # the recursion's `self.repair()` on the way back up
+            node, _ = path[i]
+            rep = BioTree._repair(node)
+            if i == 0:
+                self.root = rep
+            else:
+                parent, went_left = path[i - 1]
+                if went_left:
+                    parent.left = rep
+                else:
+                    parent.right = rep
+
+    def find(self, q0, q1):
+        """yields (start, end, value) of overlapping intervals in bio's iteration order"""
+        stack = [self.root] if self.root is not None else []
+        while stack:
+            n = stack.pop()
+            if q0 < n.max:
+                if n.left is not None:
+                    stack.append(n.left)
+                if q1 > n.start:
+                    if n.right is not None:
+                        stack.append(n.right)
+                    if q0 < n.end and n.start < q1:
+                        yield (n.start, n.end, n.value)
+
+
+def build_tree(ivs):
+    """reference src/count_reads/mod.rs:27-45: intervals are inserted in list order."""
+    t = BioTree()
+    for s, e, gene_no, strand in ivs:
+        t.insert(s, e, (gene_no, strand))
+    return t
 
 
 def make_chunks(contigs, gene_sets):
-    """reference chunked_genome.rs:72-119. contigs: [(name, tid, length)]; gene_sets: name->ivs or None."""
+    """reference chunked_genome.rs:72-119. contigs: [(name, tid, length)]; gene_sets: name->ivs or None.
+    The edge moves past the FIRST interval bio's find(stop..stop+1) yields (chunked_genome.rs:98)."""
     chunks = []
     for name, tid, length in contigs:
+        tree = build_tree(gene_sets[name]) if gene_sets is not None else None
         start = 0
         while True:
             stop = start + CHUNK_SIZE
-            if gene_sets is not None:
-                fin = chunk_fixed_points(gene_sets[name], stop)
-                if len(fin) != 1:
-                    raise ValueError("chunk edge depends on interval-tree order")
-                stop = fin.pop()
+            while tree is not None:
+                first = next(tree.find(stop, stop + 1), None)
+                if first is None:
+                    break
+                stop = first[1] + 1
             chunks.append((name, tid, start, stop))
             start = stop
             if start >= length:
@@ -126,8 +235,6 @@ def _nh(rec):
 
 
 def _count(path, intervals, gene_intervals, mode, each_read_counts_once=False):
-    if each_read_counts_once:
-        raise NotImplementedError("each_read_counts_once=True depends on bio's AVL order")
     hdr, recs = read_bam(path)
     name2tid = {n: i for i, (n, _) in enumerate(hdr.refs)}
     trees = {c: build_intervals(l) for c, l in intervals.items()}
@@ -144,8 +251,11 @@ def _count(path, intervals, gene_intervals, mode, each_read_counts_once=False):
     rev = defaultdict(int)
     weighted = mode == "weighted"
     outside_total = 0
+    once_trees = {}
     for chr_, tid, start, stop in chunks:
         ivs, gene_ids = trees[chr_]
+        if each_read_counts_once and chr_ not in once_trees:
+            once_trees[chr_] = build_tree(ivs)
         n = len(gene_ids)
         res = [[0] * n, [0] * n]
         mm = [defaultdict(set), defaultdict(set)]
@@ -159,7 +269,11 @@ def _count(path, intervals, gene_intervals, mode, each_read_counts_once=False):
             for b0, b1 in cigar_blocks(r.pos, r.cigar):
                 if mode == "unstranded" and b0 >= stop:  # counters.rs:52 (live clause)
                     continue
-                for (s, e, gene_no, strand) in find(ivs, b0, b1):
+                if each_read_counts_once:   # hits in bio's order; the loop below breaks after the first
+                    hits = [(s, e, v[0], v[1]) for s, e, v in once_trees[chr_].find(b0, b1)]
+                else:
+                    hits = find(ivs, b0, b1)
+                for (s, e, gene_no, strand) in hits:
                     hit = True
                     nh = _nh(r)
                     if mode == "unstranded":
@@ -171,6 +285,10 @@ def _count(path, intervals, gene_intervals, mode, each_read_counts_once=False):
                         seen[bucket].add(gene_no)
                     else:
                         mm[bucket][gene_no].add(r.qname)
+                    if each_read_counts_once:
+                        break                      # counters.rs:83-85 / :173-175
+                if each_read_counts_once and hit:
+                    break                          # counters.rs:87-92 / :177-182
             if not hit:
                 outside += 1
             if weighted:

@@ -7,7 +7,7 @@ import random
 import subprocess
 from typing import Dict, List, Tuple
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # GRCh38 primary assembly lengths
 HUMAN_CONTIGS = [

@@ -32,20 +32,11 @@ def has_gpu(built):
 
 
 def make_case(tmpdir, seed, n_reads=3000, **kw):
-    """(path, contigs, records, intervals, gene_intervals); regenerates until the chunk table is
-    independent of bio's tree order."""
-    from mbf_bam_b200.synth import bamio, small
-    from oracle import py_oracle
+    """(path, contigs, records, intervals, gene_intervals)"""
+    from synth import bamio, small
 
     write_kw = {k: kw.pop(k) for k in list(kw) if k in ("level", "split_records", "payload_limit", "strategy", "sync_every")}
-    for bump in range(20):
-        contigs, recs, iv, giv = small.simple_case(seed + 1000 * bump, n_reads=n_reads, **kw)
-        try:
-            for name, length in contigs:
-                py_oracle.make_chunks([(name, 0, length)], {name: py_oracle.build_intervals(giv[name])[0]})
-        except ValueError:
-            continue
-        path = os.path.join(str(tmpdir), "case_%d.bam" % seed)
-        bamio.write_bam(path, contigs, recs, **write_kw)
-        return path, contigs, recs, iv, giv
-    raise RuntimeError("no order-independent gene layout found")
+    contigs, recs, iv, giv = small.simple_case(seed, n_reads=n_reads, **kw)
+    path = os.path.join(str(tmpdir), "case_%d.bam" % seed)
+    bamio.write_bam(path, contigs, recs, **write_kw)
+    return path, contigs, recs, iv, giv

@@ -31,7 +31,7 @@ def test_shard_plan_partitions_the_chunk_table(built, tmp_path):
         assert all(covered[k][1] == covered[k + 1][0] for k in range(n - 1))
     # every record of an owned chunk lies inside the shard's byte ranges (checked through virtual offsets
     # recomputed from the file)
-    from mbf_bam_b200.synth import bamio
+    from synth import bamio
 
     data = open(path, "rb").read()
     starts = []
@@ -76,7 +76,6 @@ def _free_port():
 
 
 def _rank_main(rank, world, port, path, iv, giv, out_q):
-    import torch
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -85,33 +84,59 @@ def _rank_main(rank, world, port, path, iv, giv, out_q):
     import sys
 
     sys.path.insert(0, ROOT)
-    import mbf_bam_b200 as mb
+    from mbf_bam_b200 import dist as mbd
     from oracle import c_oracle as orc
 
-    rd = mb.Reader(path)
-    lo, hi, _ = rd.plan(giv, rank, world)
-    chunks = rd.chunks(giv)
-    # the per-shard dense result: the oracle restricted to this rank's chunks stands in for the GPU here
-    raw = orc.raw_counts(path, None, iv, giv, 1, nthreads=1)
-    # emulate ownership: recompute counts over owned chunks only by masking records via a per-chunk oracle run
-    part = orc.raw_counts_chunks(path, iv, giv, 1, lo, hi)
-    fwd = torch.from_numpy(part["fwd"].astype(np.int64))
-    rev = torch.from_numpy(part["rev"].astype(np.int64))
-    extra = torch.tensor([part["outside"]], dtype=torch.int64)
-    sc = torch.from_numpy(part["scanned"].astype(np.int32))
-    for t in (fwd, rev, extra, sc):
-        dist.all_reduce(t)
-    if rank == 0:
-        res = rd.assemble(1, iv, fwd.numpy().astype(np.uint64).tobytes(), rev.numpy().astype(np.uint64).tobytes(),
-                          np.zeros(len(fwd)).tobytes(), np.zeros(len(fwd)).tobytes(),
-                          (sc.numpy() > 0).astype(np.uint8).tobytes(), int(extra.item()))
-        out_q.put((res, raw["n_records"], len(chunks)))
+    # No GPU here: the oracle restricted to this rank's chunk range stands in for the device part
+    # (Reader.count_reads_raw / Reader.count_introns); planning, merge and assembly are the product's.
+    def raw_for(mode, once=False):
+        def f(rd):
+            lo, hi, _ = rd.plan(giv, rank, world)
+            part = orc.raw_counts(path, None, iv, giv, mode, nthreads=1, chunk_lo=lo, chunk_hi=hi, each_read_counts_once=once)
+            return (part["fwd"].tobytes(), part["rev"].tobytes(), part["wfwd"].tobytes(), part["wrev"].tobytes(),
+                    part["scanned"].tobytes(), int(part["outside"]))
+        return f
+
+    def introns_part(rd):
+        lo, hi, _ = rd.plan(None, rank, world)
+        chunks = rd.chunks(None)[lo:hi]
+        names = [n for n, _ in rd.targets()]
+        whole = orc.count_introns(path)
+        # 1 Mb chunks: keep the gaps of reads whose pos falls into an owned chunk -- recomputed from the records
+        from synth import bamio
+        from oracle import py_oracle
+
+        _, recs = bamio.read_bam(path)
+        out = {}
+        for tid, s, e in chunks:
+            d = out.setdefault(names[tid], {})
+            for r in recs:
+                if r.tid != tid or not (s <= (r.pos & 0xFFFFFFFF) < e):
+                    continue
+                k = 0
+                for gap in py_oracle.cigar_introns(r.pos, r.cigar):
+                    d[gap] = d.get(gap, 0) + 1
+                    k += 1
+                key = (0xFFFFFFFF, 0xFFFFFFFF - k)
+                d[key] = d.get(key, 0) + 1
+        return out, whole
+
+    res = {
+        "stranded": mbd.count_reads_stranded(path, None, iv, giv, _raw=raw_for(1)),
+        "unstranded": mbd.count_reads_unstranded(path, None, iv, giv, _raw=raw_for(0)),
+        "weighted": mbd.count_reads_weighted(path, None, iv, giv, _raw=raw_for(2)),
+        "once": mbd.count_reads_stranded(path, None, iv, giv, True, _raw=raw_for(1, True)),
+    }
+    whole_box = []
+    res["introns"] = mbd.count_introns(path, _part=lambda rd: (lambda pw: (whole_box.append(pw[1]), pw[0])[1])(introns_part(rd)))
+    res["introns_whole"] = whole_box[0]
+    out_q.put((rank, res))
     dist.destroy_process_group()
 
 
 def test_two_rank_merge_over_gloo(built, tmp_path):
-    """world_size 2: each rank counts its chunk range, results are all-reduced, rank 0 assembles the dicts
-    with the product's host extension; must equal the single-process oracle."""
+    """world_size 2 through mbf_bam_b200.dist: each rank counts its chunk range, dense results are all-reduced,
+    intron maps gathered and merged, EVERY rank gets the whole-job dicts; must equal the single-process oracle."""
     import torch.multiprocessing as mp
 
     path, contigs, recs, iv, giv = make_case(tmp_path, 42, n_reads=8_000, n_contigs=3)
@@ -121,9 +146,16 @@ def test_two_rank_merge_over_gloo(built, tmp_path):
     procs = [ctx.Process(target=_rank_main, args=(r, 2, port, path, iv, giv, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res, nrec, nchunks = q.get(timeout=120)
+    got = dict(q.get(timeout=180) for _ in range(2))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    want = c_oracle.count_reads_stranded(path, None, iv, giv)
-    assert res[0] == want[0] and res[1] == want[1]
+    for rank in (0, 1):
+        res = got[rank]
+        assert res["stranded"] == c_oracle.count_reads_stranded(path, None, iv, giv)
+        assert res["unstranded"] == c_oracle.count_reads_unstranded(path, None, iv, giv)
+        assert res["once"] == c_oracle.count_reads_stranded(path, None, iv, giv, True)
+        want_w = c_oracle.count_reads_weighted(path, None, iv, giv)
+        for a, b in zip(res["weighted"], want_w):
+            assert set(a) == set(b) and all(abs(a[k] - b[k]) <= 1e-9 * max(1.0, abs(b[k])) for k in a)
+        assert res["introns"] == res["introns_whole"] == c_oracle.count_introns(path)

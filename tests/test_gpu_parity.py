@@ -8,8 +8,8 @@ import zlib
 import pytest
 
 from conftest import ROOT, make_case
-from mbf_bam_b200.synth import bamio
-from oracle import c_oracle
+from synth import bamio
+from oracle import c_oracle, py_oracle
 
 pytestmark = pytest.mark.gpu
 GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "cigar_golden.json")))
@@ -291,7 +291,7 @@ def test_preloaded_file_gives_same_result(mb, tmp_path):
 def test_baseline_config_shapes(mb, tmp_path, cfg, reads):
     """The BASELINE.json config shapes (tools/bamgen, reduced read counts except config 1 which runs at
     its full 1M reads): every entry point against the multi-threaded C oracle."""
-    from mbf_bam_b200.synth import model
+    from synth import model
 
     path = str(tmp_path / (cfg + ".bam"))
     iv, giv, info = model.build_config(cfg, path, reads=reads, threads=os.cpu_count() or 4)
@@ -327,3 +327,186 @@ def test_pinned_file_mapping_gives_same_result(mb, tmp_path):
     rd.unpin_file()
     c = rd.count_reads(1, iv, giv)
     assert a == b == c == c_oracle.count_reads_stranded(path, None, iv, giv)
+
+
+# ------------------------------------------------------------------------------------------------ round 2
+@pytest.mark.parametrize("seed,kw", [(31, {}), (32, dict(exon_mode=False, genes_per_contig=120)),
+                                     (33, dict(paired=True, genes_per_contig=200)), (34, dict(n_reads=40_000, genes_per_contig=400))])
+def test_each_read_counts_once(mb, tmp_path, seed, kw):
+    """each_read_counts_once=True (reference counters.rs:83-92,173-182): first hit in bio's tree order."""
+    path, contigs, recs, iv, giv = make_case(tmp_path, seed, **kw)
+    nt = 4
+    assert mb.count_reads_unstranded(path, None, iv, giv, True) == c_oracle.count_reads_unstranded(path, None, iv, giv, True, nthreads=nt)
+    assert mb.count_reads_stranded(path, None, iv, giv, True) == c_oracle.count_reads_stranded(path, None, iv, giv, True, nthreads=nt)
+    assert mb.count_reads_stranded(path, None, iv, giv, each_read_counts_once=False) == c_oracle.count_reads_stranded(path, None, iv, giv, nthreads=nt)
+    if seed != 34:
+        assert mb.count_reads_unstranded(path, None, iv, giv, True) == py_oracle.count_reads_unstranded(path, None, iv, giv, True)
+    with pytest.raises(ValueError, match="each_read_counts_once"):
+        mb.count_reads_weighted(path, None, iv, giv, True)
+
+
+def test_chunk_edges_with_stacked_genes(mb, tmp_path):
+    """Counts on a layout where the chunk table depends on bio's iteration order (chunked_genome.rs:98)."""
+    from test_oracle import _stacked_genes
+    import random
+
+    contigs, giv = _stacked_genes()
+    rng = random.Random(3)
+    recs = []
+    for i in range(30_000):
+        tid = rng.randrange(len(contigs))
+        b = rng.choice([1_000_000, 2_000_000, 3_000_000])
+        pos = b + rng.randrange(-5000, 5000) if i % 2 else rng.randrange(0, 4_000_000)
+        nh = bamio.aux_int(b"NH", rng.choice([1, 1, 2, 3]))
+        recs.append(bamio.Rec(tid, pos, b"q%d" % (i // 2), rng.choice([0, 16]), 255, [(0, 30), (3, rng.randrange(1, 3000)), (0, 20)], 50, nh))
+    recs.sort(key=lambda r: (r.tid, r.pos))
+    path = str(tmp_path / "stacked.bam")
+    bamio.write_bam(path, contigs, recs)
+    check_all(mb, path, giv, giv)
+    assert mb.count_reads_unstranded(path, None, giv, giv) == py_oracle.count_reads_unstranded(path, None, giv, giv)
+
+
+def test_property_gpu_vs_python_oracle(mb, tmp_path):
+    """Random gene sets and reads (SURVEY App. A.6 edge cases come from synth.small) against the brute-force
+    pure-Python oracle -- the independent statement of the semantics, not the C restatement."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from synth import small
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(0, 10 ** 6), st.integers(1, 3), st.integers(1, 60), st.booleans(), st.booleans(), st.sampled_from([0, 1, 6]))
+    def prop(seed, n_contigs, genes, exon_mode, paired, level):
+        contigs, recs, iv, giv = small.simple_case(seed, n_reads=600, n_contigs=n_contigs, contig_len=1_300_000,
+                                                   genes_per_contig=genes, exon_mode=exon_mode, paired=paired)
+        path = str(tmp_path / ("p%d.bam" % seed))
+        bamio.write_bam(path, contigs, recs, level=level)
+        assert mb.count_reads_unstranded(path, None, iv, giv) == py_oracle.count_reads_unstranded(path, None, iv, giv)
+        assert mb.count_reads_stranded(path, None, iv, giv) == py_oracle.count_reads_stranded(path, None, iv, giv)
+        assert mb.count_reads_stranded(path, None, iv, giv, True) == py_oracle.count_reads_stranded(path, None, iv, giv, True)
+        assert_weighted_close(mb.count_reads_weighted(path, None, iv, giv), py_oracle.count_reads_weighted(path, None, iv, giv))
+        assert mb.count_introns(path) == py_oracle.count_introns(path)
+        os.unlink(path)
+        os.unlink(path + ".bai")
+
+    prop()
+
+
+def test_inflated_buffers_grow_in_the_middle_of_a_job(mb, tmp_path, monkeypatch):
+    """A window that inflates to more than the buffers hold makes U (and what is sized from it) grow while the
+    previous window's second half (intron pass 2, emit-only re-run) is still outstanding; only the growing
+    window's own buffers may be replaced.  Fresh pipeline, 1-2 MiB windows, inflate ratio ~10."""
+    monkeypatch.setenv("MBF_BAM_WINDOW_MB", "2")
+    monkeypatch.setenv("MBF_BAM_MM_CAP", "64")
+    path, contigs, recs, iv, giv = make_case(tmp_path, 51, n_reads=400_000)
+    assert os.path.getsize(path) > 4 * (1 << 20)
+    for fn in ("introns", "stranded"):
+        mb.release_device(0)
+        if fn == "introns":
+            assert mb.count_introns(path) == c_oracle.count_introns(path, nthreads=4)
+        else:
+            assert mb.count_reads_stranded(path, None, iv, giv) == c_oracle.count_reads_stranded(path, None, iv, giv, nthreads=4)
+        st = mb.last_stats()
+        assert st["n_windows"] >= 3 and st["uncompressed_bytes"] > 8 * st["compressed_bytes"]
+    mb.release_device(0)
+
+
+def test_job_restarts_with_smaller_windows_after_a_ratio_jump(mb, tmp_path, monkeypatch):
+    """Windows are planned from the largest inflate ratio seen so far; a much more compressible stretch can
+    push one past the 32-bit offset range.  The job then starts again with smaller windows (lowered limits
+    here: 48 MiB hard, 40 MiB planning target)."""
+    rng = random.Random(8)
+    payload = rng.randbytes(int(38.35 * (1 << 20))) + bytes(40 << 20)
+    p = tmp_path / "jump.bgzf"
+    with open(p, "wb") as fh:
+        w = bamio.BgzfWriter(fh, level=1)
+        w.write(payload, atomic=False)
+        w.close()
+    data = p.read_bytes()
+    monkeypatch.setenv("MBF_BAM_WINDOW_MB", "16")
+    monkeypatch.setenv("MBF_BAM_U_LIMIT_MB", "40")
+    monkeypatch.setenv("MBF_BAM_U_HARD_LIMIT_MB", "48")
+    got = mb.inflate_buffer(data)
+    assert got == payload
+    assert mb.last_stats()["n_retries"] >= 1
+
+
+def test_fan_out_over_devices(mb, tmp_path):
+    """One call, several devices (the rayon pool of counters.rs:217-259 at GPU granularity): every visible GPU
+    gets a chunk range; results must not depend on the device list."""
+    path, contigs, recs, iv, giv = make_case(tmp_path, 52, n_reads=60_000, n_contigs=4)
+    n = mb.device_count()
+    want = c_oracle.count_reads_stranded(path, None, iv, giv, nthreads=4)
+    want_i = c_oracle.count_introns(path, nthreads=4)
+    lists = [[0], list(range(n)), list(range(n))[::-1]]
+    for devs in lists:
+        rd = mb.Reader(path)
+        rd.set_devices(devs)
+        assert tuple(rd.count_reads(1, iv, giv)) == want
+        assert rd.stats()["n_devices"] == len(devs)
+        assert rd.count_introns() == want_i
+        assert rd.count_reads(0, iv, giv, True) == c_oracle.count_reads_unstranded(path, None, iv, giv, True)
+    # device fan-out composes with explicit shards (what one rank of a multi-node job would do)
+    import numpy as np
+
+    rd = mb.Reader(path)
+    rd.set_devices(list(range(n)))
+    whole = rd.count_reads_raw(1, iv, giv)
+    acc = None
+    for i in range(3):
+        rd.set_shard(i, 3)
+        part = rd.count_reads_raw(1, iv, giv)
+        arrs = [np.frombuffer(part[0], dtype=np.uint64), np.frombuffer(part[1], dtype=np.uint64), np.uint64(part[5])]
+        acc = arrs if acc is None else [a + b for a, b in zip(acc, arrs)]
+    assert acc[0].tobytes() == whole[0] and acc[1].tobytes() == whole[1] and int(acc[2]) == whole[5]
+    with pytest.raises(ValueError):
+        rd.set_devices([0, 0]) or rd.count_reads(1, iv, giv)
+
+
+def test_concurrent_calls_from_threads(mb, tmp_path):
+    """No process-wide lock: calls from several threads are serialised per device and all give the right answer."""
+    import threading
+
+    path, contigs, recs, iv, giv = make_case(tmp_path, 53, n_reads=20_000)
+    want = c_oracle.count_reads_stranded(path, None, iv, giv)
+    out = [None] * 4
+
+    def work(k):
+        out[k] = mb.count_reads_stranded(path, None, iv, giv)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert all(o == want for o in out)
+
+
+def test_page_locked_file_cache(mb, tmp_path, monkeypatch):
+    """hostmap.hpp: after MBF_BAM_PIN_AFTER jobs on a file its mapping is page-locked and later jobs DMA straight
+    from the page cache; results are the same on the staged path, the pread path and the page-locked path."""
+    path, contigs, recs, iv, giv = make_case(tmp_path, 54, n_reads=50_000, random_seq=True)
+    want = c_oracle.count_reads_stranded(path, None, iv, giv)
+    mb.host_cache_clear()
+    monkeypatch.setenv("MBF_BAM_PIN_AFTER", "2")
+    stats = []
+    for _ in range(4):
+        assert mb.count_reads_stranded(path, None, iv, giv) == want
+        stats.append(mb.last_stats())
+    assert stats[0]["h2d_pinned_bytes"] == 0 and stats[1]["h2d_pinned_bytes"] == 0
+    if stats[2]["h2d_pinned_bytes"] == 0:
+        pytest.skip("platform refuses to page-lock a file mapping")
+    assert stats[2]["ms_pin"] > 0 and stats[3]["ms_pin"] == 0
+    assert stats[3]["h2d_pinned_bytes"] == stats[3]["h2d_bytes"] > 0
+    mb.host_cache_clear()
+    monkeypatch.setenv("MBF_BAM_PIN_AFTER", "never")
+    monkeypatch.setenv("MBF_BAM_STAGE", "pread")
+    assert mb.count_reads_stranded(path, None, iv, giv) == want
+    assert mb.last_stats()["h2d_pinned_bytes"] == 0
+    # a rewritten file (other size/mtime) is never served from a stale mapping
+    monkeypatch.delenv("MBF_BAM_STAGE")
+    monkeypatch.setenv("MBF_BAM_PIN_AFTER", "0")
+    assert mb.count_reads_stranded(path, None, iv, giv) == want
+    path2, contigs2, recs2, iv2, giv2 = make_case(tmp_path, 55, n_reads=30_000, random_seq=True)
+    os.replace(path2, path)
+    os.replace(path2 + ".bai", path + ".bai")
+    assert mb.count_reads_stranded(path, None, iv2, giv2) == c_oracle.count_reads_stranded(path, None, iv2, giv2)
+    mb.host_cache_clear()

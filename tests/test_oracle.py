@@ -8,7 +8,7 @@ import zlib
 import pytest
 
 from conftest import ROOT, make_case
-from mbf_bam_b200.synth import bamio
+from synth import bamio
 from oracle import c_oracle, py_oracle
 
 GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "cigar_golden.json")))
@@ -106,3 +106,143 @@ def test_deflate_core_logic_on_host(tmp_path, kw):
     path, *_ = make_case(tmp_path, 12, n_reads=6000, **kw)
     out = subprocess.run([exe, path], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
+# ------------------------------------------------------------------------------------------------ bio's tree
+def _check_avl(n):
+    """-> (height, max_end, min_start, max_start); asserts the AVL + search-tree + max-augmentation invariants"""
+    if n is None:
+        return 0, -1, None, None
+    lh, lm, lmin, lmax = _check_avl(n.left)
+    rh, rm, rmin, rmax = _check_avl(n.right)
+    assert abs(lh - rh) <= 1 and n.height == 1 + max(lh, rh)
+    assert n.max == max(n.end, lm, rm)
+    if lmax is not None:
+        assert lmax <= n.start            # left: start <= node.start
+    if rmin is not None:
+        assert rmin >= n.start            # right: start > node.start when inserted; rotations can move an equal start here
+    lo = lmin if lmin is not None else n.start
+    hi = rmax if rmax is not None else n.start
+    return n.height, n.max, lo, hi
+
+
+def test_bio_tree_restatement_properties():
+    """The restated bio IntervalTree: AVL invariants hold after every insert, find() yields
+    exactly the overlapping intervals (compared with the brute-force scan) and yields them in the order
+    node / right subtree / left subtree."""
+    from hypothesis import given, settings, strategies as st
+
+    ivs_st = st.lists(st.tuples(st.integers(0, 300), st.integers(0, 60)), min_size=0, max_size=60)
+
+    @settings(max_examples=150, deadline=None)
+    @given(ivs_st, st.lists(st.tuples(st.integers(0, 320), st.integers(0, 50)), min_size=1, max_size=10))
+    def prop(raw, queries):
+        ivs = [(s, s + l, i, 1) for i, (s, l) in enumerate(raw)]
+        t = py_oracle.BioTree()
+        for s, e, g, sd in ivs:
+            t.insert(s, e, (g, sd))
+            _check_avl(t.root)
+        order = []
+
+        def walk(n):
+            if n is None:
+                return
+            order.append(n.value[0])
+            walk(n.right)
+            walk(n.left)
+
+        walk(t.root)
+        rank = {g: k for k, g in enumerate(order)}
+        assert sorted(order) == list(range(len(ivs)))
+        for q0, ql in queries:
+            q1 = q0 + ql
+            got = [v[0] for _, _, v in t.find(q0, q1)]
+            want = [iv[2] for iv in py_oracle.find(ivs, q0, q1)]
+            assert sorted(got) == sorted(want)
+            assert got == sorted(got, key=lambda g: rank[g])  # pruning never reorders
+
+    prop()
+
+
+def test_bio_tree_known_shapes():
+    """Hand-checked AVL shapes: ascending inserts rotate left, equal starts go left."""
+    t = py_oracle.BioTree()
+    for i, s in enumerate([10, 20, 30]):
+        t.insert(s, s + 5, (i, 1))
+    assert t.root.value[0] == 1 and t.root.left.value[0] == 0 and t.root.right.value[0] == 2
+    assert [v[0] for _, _, v in t.find(0, 100)] == [1, 2, 0]     # node, right, left
+    t = py_oracle.BioTree()
+    for i in range(3):
+        t.insert(10, 15 + i, (i, 1))                              # equal starts descend left: 0 <- 1 <- 2, then rotate right
+    assert t.root.value[0] == 1 and t.root.left.value[0] == 2 and t.root.right.value[0] == 0
+    assert [v[0] for _, _, v in t.find(12, 13)] == [1, 0, 2]
+
+
+def _stacked_genes(n_contigs=2):
+    """Gene layouts where SEVERAL genes cover a 1 Mb boundary, with ends 1 bp apart: the chunk table depends on
+    which one bio's tree yields first."""
+    import random
+
+    rng = random.Random(77)
+    giv = {}
+    contigs = []
+    for c in range(n_contigs):
+        name = "chr%s" % "ABCD"[c]
+        contigs.append((name, 4_200_000 + c))
+        lst = []
+        for k in range(40):
+            b = rng.choice([1_000_000, 2_000_000, 3_000_000])
+            s = b - rng.randrange(1, 4000)
+            e = b + rng.choice([1, 2, 3, 5, 100, 101, 102, 2000, 2001])
+            lst.append(("g%d_%d" % (c, k), rng.choice([1, -1]), [s], [e]))
+        for k in range(20):
+            s = rng.randrange(0, 4_000_000)
+            lst.append(("h%d_%d" % (c, k), 1, [s], [s + rng.randrange(10, 30000)]))
+        rng.shuffle(lst)
+        giv[name] = lst
+    return contigs, giv
+
+
+def test_chunk_edges_follow_tree_order(built, tmp_path):
+    """chunked_genome.rs:98: the edge moves past the FIRST covering interval in bio's order.  Product host code,
+    C oracle and the pure-Python tree must agree on layouts where that choice matters."""
+    contigs, giv = _stacked_genes()
+    path = str(tmp_path / "edges.bam")
+    bamio.write_bam(path, contigs, [bamio.Rec(0, 10, b"r", 0, 255, [(0, 10)], 10)])
+    want = py_oracle.make_chunks([(n, i, l) for i, (n, l) in enumerate(contigs)],
+                                 {n: py_oracle.build_intervals(giv[n])[0] for n, _ in contigs})
+    want = [(t, s, e) for _, t, s, e in want]
+    assert c_oracle.chunks(path, None, giv) == want
+    assert [tuple(x) for x in built.Reader(path).chunks(giv)] == want
+    # the choice does matter here: "largest end" gives another table
+    greedy = []
+    for n, tid, length in [(n, i, l) for i, (n, l) in enumerate(contigs)]:
+        ivs = py_oracle.build_intervals(giv[n])[0]
+        start = 0
+        while True:
+            stop = start + py_oracle.CHUNK_SIZE
+            while True:
+                cov = [iv for iv in ivs if iv[0] <= stop < iv[1]]
+                if not cov:
+                    break
+                stop = max(iv[1] for iv in cov) + 1
+            greedy.append((tid, start, stop))
+            start = stop
+            if start >= length:
+                break
+    assert greedy != want
+
+
+@pytest.mark.parametrize("seed,kw", [(31, {}), (32, dict(exon_mode=False, genes_per_contig=120)), (33, dict(paired=True, genes_per_contig=200))])
+def test_each_read_counts_once_oracles_agree(tmp_path, seed, kw):
+    """each_read_counts_once=True (counters.rs:83-92,173-182): the C oracle (array AVL) against the pure-Python
+    tree; overlapping genes make the first hit differ from 'any hit'."""
+    path, contigs, recs, iv, giv = make_case(tmp_path, seed, n_reads=4000, **kw)
+    a = c_oracle.count_reads_unstranded(path, None, iv, giv, True, nthreads=2)
+    assert a == py_oracle.count_reads_unstranded(path, None, iv, giv, True)
+    f = c_oracle.count_reads_stranded(path, None, iv, giv, True, nthreads=2)
+    assert f == py_oracle.count_reads_stranded(path, None, iv, giv, True)
+    b = c_oracle.count_reads_unstranded(path, None, iv, giv, False)
+    assert a["_outside"] == b["_outside"] and a["_total"] <= b["_total"]
+    if kw:
+        assert a != b  # with dense overlapping genes the flag changes results
