@@ -1,16 +1,9 @@
-// K1, production form: one BGZF block per warp, "decode on lane 0, materialise on 32 lanes".
+// Table entry formats and the warp-cooperative table build shared by the K1 kernels (inflate_par.cuh,
+// inflate_twopass.cuh).  (The one-pass "decode on lane 0, materialise on 32 lanes" kernel this header was written
+// for is gone: superseded by the two-pass form, see DESIGN.md for its measurements.)
 //
-// Why this shape (measured on the synthetic BAMs, profiles/): 40 % of the DEFLATE symbols are
-// matches, they produce 86 % of the output bytes, and half of them reach back more than 2 KB.  A
-// decoder that copies bytes on the decoding lane spends most of its issue slots on copies.  Here
-//   * lane 0 only decodes: up to 32 symbols per batch go to a queue in shared memory.  The LUTs
-//     carry (code length, extra-bit count, base value, kind) in one 32-bit entry, so a symbol costs
-//     one shared load, one bit-field extract and one 64-bit shift;
-//   * the warp materialises the batch: inclusive scan of the symbol lengths -> output offsets, all
-//     literals stored at once, each match copied by up to 32 lanes (periodic index when
-//     distance < length).  Sources at most BATCH_NEAR bytes back come from the output ring in
-//     shared memory, older ones from L2/HBM, which is why the ring is flushed before every batch;
-//   * Huffman tables are built by all 32 lanes (warp counting sort by code length, parallel LUT fill).
+// Measured on the synthetic BAMs (profiles/r01_symbol_stats.txt): 40 % of the DEFLATE symbols are matches, they
+// produce 86 % of the output bytes, and half of them reach back more than 2 KB.
 //
 // Replaces zlib's inflate under htslib's bgzf_read_block (reference src/count_reads/counters.rs:41).
 #pragma once
@@ -30,21 +23,6 @@ constexpr uint32_t E_INVALID = K_SPECIAL | 0xffu, E_SLOW = K_SPECIAL;
 
 constexpr int LL_ROOTB = 9;  // 32-bit entries; literal codes of the BAM streams are <= 7 or >= 10 bits long
 constexpr int D_ROOTB = 8;
-struct BatchShared {
-    uint32_t ll_lut[1 << LL_ROOTB];
-    uint32_t d_lut[1 << D_ROOTB];
-    __align__(16) uint8_t ring[RINGB];
-    uint32_t q[2 * 32];  // (len << 16 | dist - 1, output offset) per queued match
-    uint16_t ll_sym[288];
-    uint16_t d_sym[32];
-    HuffDec ll_hd, d_hd;
-    uint32_t run[16];
-    uint8_t lens[320];
-    uint32_t qn, qacc;
-    int status;  // 0 more symbols follow, 1 member finished, 2 table build requested, <0 -InflateError
-    uint32_t hlit, hdist;
-};
-
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));

@@ -44,6 +44,7 @@ struct TokenArgs {
     uint32_t* err_info;
     TokScratch* scratch;     // gridDim.x * 32
     unsigned long long* n_tokens;  // statistics (may be null)
+    const uint32_t* list;    // null: members 0..n_blocks-1; else the members to decode are list[0..*n_blocks)
 };
 
 // first error wins; the failed member gets an empty token list, so pass 2 never walks stale tokens for it
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(32, 16) k_tokens_bf(TokenArgs a) {
             if (b >= n_blocks) {
                 st = B_DONE;
             } else {
+                if (a.list) b = a.list[b];
                 clen_b = a.clen[b];
                 isize_b = a.isize[b];
                 mis = br.init(a.cbuf + a.cpos[b], clen_b);

@@ -1,7 +1,7 @@
 // sm_100a kernels of the read-counting path.  One "window" = a slice of the BGZF file resident
 // in HBM; per window the launch sequence is
 //   k_win_begin -> k_scan<count> -> k_excl_scan -> k_scan<emit> -> k_blocks_finalize -> k_excl_scan
-//   -> k_tokens_bf -> k_lz_resolve   (inflate_twopass.cuh; or the one-pass k_inflate_batched / k_inflate)
+//   -> k_tokens_par (+ k_tokens_bf for the members it hands over) -> k_lz_resolve   (inflate_par.cuh, inflate_twopass.cuh)
 //   -> k_frame_walk<count> -> k_frame_fix -> k_excl_scan -> k_frame_walk<emit> -> k_carry_copy
 //   -> k_count_reads<MODE> | k_count_introns -> k_mm_insert
 // Everything reads its sizes from a device-resident WinMeta, so the host never has to wait for a
@@ -9,7 +9,7 @@
 //
 // Reference behaviour replaced (paths relative to the reference tree):
 //   k_scan_*/k_blocks_finalize  htslib bgzf block iteration under bam.fetch/read (counters.rs:40-41)
-//   k_tokens_bf + k_lz_resolve  zlib inflate in htslib bgzf_read_block (also k_inflate_batched, k_inflate)
+//   k_tokens_par/_bf + k_lz_resolve  zlib inflate in htslib bgzf_read_block
 //   k_frame_walk                htslib bam_read1 record framing
 //   k_count_reads               count_reads_in_region_{unstranded,stranded} (counters.rs:26-202),
 //                               BamRecordExtensions::blocks (bam_ext.rs:29-34), Record::aux(b"NH"),
@@ -25,8 +25,6 @@
 
 namespace mbf {
 
-constexpr int RING = 2048;  // bytes of recent output kept in shared memory per decoder
-constexpr uint32_t RING_MASK = RING - 1;
 constexpr uint32_t U_PREFIX = 4u << 20;  // room in front of a window's data for a carried record
 constexpr int NH_DENSE = 64;             // weighted mode: exact integer counters for NH 1..64
 constexpr int HIST_DENSE = 64;           // introns-per-read histogram kept dense below this
@@ -58,7 +56,9 @@ struct WinMeta {
     uint32_t mm_count;      // multi-mapper keys appended this window (may exceed capacity)
     uint32_t owned_records;
     uint32_t cigar_ops;     // sum of n_cigar_op of owned records (bound for intron inserts)
-    uint32_t inflate_next;  // work queue head of the multi-decoder inflate kernel
+    uint32_t inflate_next;  // work queue head of the token kernel (pass 1 of K1)
+    uint32_t fb_count;      // members pass 1 handed to the fallback token kernel ...
+    uint32_t fb_next;       // ... and that kernel's work queue head
     uint32_t range_start;   // first window of a byte range: no carry, first record at first_rec_uoff
     uint32_t first_rec_uoff;
     unsigned long long outside;
@@ -276,11 +276,8 @@ __global__ void __launch_bounds__(256) k_blocks_finalize(ScanArgs a, BlockArrays
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1: DEFLATE inflate, one BGZF block per CTA (one warp).  Lane 0 runs the serial Huffman decode
-// against LUTs in shared memory; the warp cooperates on flushing the shared-memory output ring to
-// HBM with 16-byte stores.  Back-references within RING bytes are served from shared memory, older
-// ones from L2/HBM (already flushed by this warp).
-// explicit 32-bit shared-memory addressing for the hot loop (generic-pointer accesses make ptxas
+// K1 (inflate_par.cuh, inflate_twopass.cuh): helpers shared by the inflate kernels.
+// explicit 32-bit shared-memory addressing for the hot loops (generic-pointer accesses make ptxas
 // re-derive the shared window base, SR_CgaCtaId, on the decode chain)
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     uint16_t v;
@@ -303,485 +300,9 @@ __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 
-struct RingOut {
-    uint32_t s_ring;  // shared address of the ring
-    const uint8_t* U;
-    uint32_t opos, ostart, soft_lim;
-    __device__ __forceinline__ bool want_flush() const { return opos > soft_lim; }
-    __device__ __forceinline__ void put(uint32_t b) {
-        sts_u8(s_ring + (opos & RING_MASK), b);
-        opos++;
-    }
-    __device__ __forceinline__ bool copy(uint32_t dist, uint32_t len) {
-        if (dist > opos - ostart) return false;
-        const uint32_t o = opos;
-        if (dist <= (uint32_t)RING) {
-            const uint32_t src = o - dist;
-            uint32_t i = 0;
-            if (dist == 1) {  // run of one byte
-                const uint32_t b = lds_u8(s_ring + (src & RING_MASK));
-                for (; i < len; i++) sts_u8(s_ring + ((o + i) & RING_MASK), b);
-            } else if (dist >= 4) {  // source and destination do not overlap within 4 bytes
-                for (; i + 4 <= len; i += 4) {
-                    const uint32_t b0 = lds_u8(s_ring + ((src + i) & RING_MASK));
-                    const uint32_t b1 = lds_u8(s_ring + ((src + i + 1) & RING_MASK));
-                    const uint32_t b2 = lds_u8(s_ring + ((src + i + 2) & RING_MASK));
-                    const uint32_t b3 = lds_u8(s_ring + ((src + i + 3) & RING_MASK));
-                    sts_u8(s_ring + ((o + i) & RING_MASK), b0);
-                    sts_u8(s_ring + ((o + i + 1) & RING_MASK), b1);
-                    sts_u8(s_ring + ((o + i + 2) & RING_MASK), b2);
-                    sts_u8(s_ring + ((o + i + 3) & RING_MASK), b3);
-                }
-            }
-            for (; i < len; i++) sts_u8(s_ring + ((o + i) & RING_MASK), lds_u8(s_ring + ((src + i) & RING_MASK)));
-        } else {
-            const uint8_t* sp = U + (o - dist);  // flushed long ago by this warp; read through L2
-            uint32_t i = 0;
-            for (; i + 4 <= len; i += 4) {
-                const uint32_t b0 = __ldcg(sp + i), b1 = __ldcg(sp + i + 1), b2 = __ldcg(sp + i + 2), b3 = __ldcg(sp + i + 3);
-                sts_u8(s_ring + ((o + i) & RING_MASK), b0);
-                sts_u8(s_ring + ((o + i + 1) & RING_MASK), b1);
-                sts_u8(s_ring + ((o + i + 2) & RING_MASK), b2);
-                sts_u8(s_ring + ((o + i + 3) & RING_MASK), b3);
-            }
-            for (; i < len; i++) sts_u8(s_ring + ((o + i) & RING_MASK), __ldcg(sp + i));
-        }
-        opos = o + len;
-        return true;
-    }
-};
-
-// Hot loop of the inflate kernel: same contract as mbf::decode_symbols (inflate_core.cuh), with the
-// two LUTs and the ring addressed through 32-bit shared addresses.
-__device__ __forceinline__ int decode_symbols_fast(const DecoderTables* T, uint32_t s_ll, uint32_t s_d, BitReader& br, RingOut& out) {
-    for (;;) {
-        if (out.want_flush()) return DEC_NEED_FLUSH;
-        br.refill();
-        uint32_t e = lds_u16(s_ll + (br.peek(LL_ROOT) << 1));
-        if (e < 0x1000u) {  // literal
-            br.consume(e & 15);
-            out.put(e >> 4);
-            // >= 17 bits left: enough for one more literal/length code without a refill
-            e = lds_u16(s_ll + (br.peek(LL_ROOT) << 1));
-            if (e < 0x1000u) {
-                br.consume(e & 15);
-                out.put(e >> 4);
-                continue;
-            }
-            br.refill();
-        }
-        if (e >= LUT_SLOW) {
-            if (e != LUT_SLOW) return -INF_BAD_SYMBOL;
-            e = slow_decode(&T->ll_hd, T->ll_sym, br.peek(15), LL_ROOT);
-            if (!e) return -INF_BAD_SYMBOL;
-            if (e < 0x1000u) {
-                br.consume(e & 15);
-                out.put(e >> 4);
-                continue;
-            }
-        }
-        br.consume(e & 15);
-        uint32_t sym = e >> 4;
-        if (sym == 256) return DEC_END_BLOCK;
-        sym -= 257;
-        if (sym >= 29) return -INF_BAD_SYMBOL;
-        const uint32_t len = MBF_TBL(LEN_BASE, sym) + br.take(MBF_TBL(LEN_EXTRA, sym));
-        br.refill();
-        e = lds_u16(s_d + (br.peek(D_ROOT) << 1));
-        if (e >= LUT_SLOW) {
-            if (e != LUT_SLOW) return -INF_BAD_DISTANCE;
-            e = slow_decode(&T->d_hd, T->d_sym, br.peek(15), D_ROOT);
-            if (!e) return -INF_BAD_DISTANCE;
-        }
-        br.consume(e & 15);
-        const uint32_t ds = e >> 4;
-        if (ds >= 30) return -INF_BAD_DISTANCE;
-        const uint32_t dist = MBF_TBL(DIST_BASE, ds) + br.take(MBF_TBL(DIST_EXTRA, ds));
-        if (!out.copy(dist, len)) return -INF_BAD_DISTANCE;
-    }
-}
-
-template <uint32_t MASK>
-__device__ __forceinline__ void ring_flush_n(const uint8_t* ring, uint8_t* U, uint32_t from, uint32_t to, int lane) {
-    if (from >= to) return;
-    uint32_t head_end = min(to, (from + 15u) & ~15u);
-    for (uint32_t i = from + lane; i < head_end; i += 32) U[i] = ring[i & MASK];
-    uint32_t body_end = to & ~15u;
-    if (body_end > head_end) {
-        for (uint32_t i = head_end + 16u * lane; i < body_end; i += 512u)
-            *(uint4*)(U + i) = *(const uint4*)(ring + (i & MASK));
-    } else {
-        body_end = head_end;
-    }
-    for (uint32_t i = body_end + lane; i < to; i += 32) U[i] = ring[i & MASK];
-}
-__device__ __forceinline__ void ring_flush(const uint8_t* ring, uint8_t* U, uint32_t from, uint32_t to, int lane) {
-    ring_flush_n<RING_MASK>(ring, U, from, to, lane);
-}
-
-struct InflateArgs {
-    const uint8_t* cbuf;
-    BlockArrays blk;
-    uint8_t* U;
-    WinMeta* meta;
-};
-
-__global__ void __launch_bounds__(32) k_inflate(InflateArgs a) {
-    __shared__ DecoderTables T;
-    __shared__ __align__(16) uint8_t ring[RING];
-    const uint32_t b = blockIdx.x;
-    if (b >= a.meta->n_blocks) return;
-    const int lane = threadIdx.x;
-    const uint32_t ostart = a.blk.uoff[b], isize = a.blk.isize[b], oend = ostart + isize;
-    // lane-0 decoder state
-    BitReader br;
-    RingOut out;
-    uint32_t mis = 0, bfinal = 0, stored_left = 0;
-    int st = 0;  // 0 header, 1 huffman, 2 stored, 3 done
-    int err = 0;
-    uint32_t flushed = ostart;
-    const uint32_t s_ll = smem_addr(T.ll_lut);
-    const uint32_t s_d = smem_addr(T.d_lut);
-    if (lane == 0) {
-        const uint8_t* p = a.cbuf + a.blk.cpos[b];
-        mis = (uint32_t)((uintptr_t)p & 3);
-        br.init(p, a.blk.clen[b]);
-        out.s_ring = smem_addr(ring);
-        out.U = a.U;
-        out.opos = out.ostart = ostart;
-        out.soft_lim = min(flushed + (uint32_t)RING - 258u, oend);
-    }
-    for (;;) {
-        int action = 0;  // 0 flush and continue, 1 finished
-        if (lane == 0) {
-            for (;;) {
-                if (st == 0) {
-                    if (bfinal) { st = 3; action = 1; break; }
-                    br.refill();
-                    bfinal = br.take(1);
-                    uint32_t btype = br.take(2);
-                    if (btype == 0) {
-                        br.consume(br.cnt & 7);
-                        br.refill();
-                        uint32_t len = br.take(16);
-                        br.refill();
-                        uint32_t nlen = br.take(16);
-                        if ((len ^ 0xffffu) != nlen) { err = INF_BAD_STORED; action = 1; break; }
-                        stored_left = len;
-                        st = 2;
-                    } else if (btype == 1) {
-                        err = build_fixed(&T);
-                        if (err) { action = 1; break; }
-                        st = 1;
-                    } else if (btype == 2) {
-                        err = build_dynamic(&T, br);
-                        if (err) { action = 1; break; }
-                        st = 1;
-                    } else {
-                        err = INF_BAD_BTYPE; action = 1; break;
-                    }
-                } else if (st == 1) {
-                    int rc = decode_symbols_fast(&T, s_ll, s_d, br, out);
-                    if (rc == DEC_END_BLOCK) { st = 0; continue; }
-                    if (rc == DEC_NEED_FLUSH) {
-                        if (out.opos > oend) { err = INF_OUTPUT_OVERRUN; action = 1; }
-                        break;
-                    }
-                    err = -rc; action = 1; break;
-                } else {  // stored
-                    bool need = false;
-                    while (stored_left) {
-                        if (out.want_flush()) { need = true; break; }
-                        br.refill();
-                        out.put((uint8_t)br.take(8));
-                        stored_left--;
-                    }
-                    if (need) {
-                        if (out.opos > oend) { err = INF_OUTPUT_OVERRUN; action = 1; }
-                        break;
-                    }
-                    st = 0;
-                }
-            }
-            if (action == 1 && !err) {
-                if (out.opos != oend) err = INF_SIZE_MISMATCH;
-                else if (br.bytes_consumed(mis) > a.blk.clen[b]) err = INF_INPUT_OVERRUN;
-            }
-        }
-        action = __shfl_sync(0xffffffffu, action, 0);
-        uint32_t opos = __shfl_sync(0xffffffffu, out.opos, 0);
-        uint32_t upto = action ? min(opos, oend) : min(opos & ~15u, oend);
-        __syncwarp();
-        ring_flush(ring, a.U, flushed, upto, lane);
-        if (upto > flushed) flushed = upto;
-        __syncwarp();
-        if (action) break;
-        if (lane == 0) out.soft_lim = min(flushed + (uint32_t)RING - 258u, oend);
-    }
-    if (lane == 0 && err) set_err(a.meta, WERR_INFLATE + (uint32_t)err, b);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1 (batched form; see inflate_batched.cuh for the design)
-__global__ void __launch_bounds__(32, 32) k_inflate_batched(InflateArgs a) {
-    __shared__ BatchShared S;
-    const uint32_t b = blockIdx.x;
-    if (b >= a.meta->n_blocks) return;
-    const int lane = threadIdx.x;
-    const uint32_t ostart = a.blk.uoff[b], isize = a.blk.isize[b], oend = ostart + isize;
-    uint8_t* const U = a.U;
-    const uint32_t s_ll = smem_addr(S.ll_lut);
-    const uint32_t s_d = smem_addr(S.d_lut);
-    const uint32_t s_ring = smem_addr(S.ring);
-    const uint32_t s_q = smem_addr(S.q);
-    // lane-0 decoder state
-    BitReader br;
-    br.words = nullptr; br.wpos = br.wlimit = 0; br.buf = 0; br.cnt = 0; br.nextw = 0;
-    uint32_t mis = 0, bfinal = 0, stored_left = 0, held = 0;
-    int st = 0;  // 0 header, 1 huffman, 2 stored
-    if (lane == 0) {
-        const uint8_t* p = a.cbuf + a.blk.cpos[b];
-        mis = (uint32_t)((uintptr_t)p & 3);
-        br.init(p, a.blk.clen[b]);
-    }
-    uint32_t opos = ostart, flushed = ostart;  // warp-uniform
-    int err = 0;
-    for (;;) {
-        if (lane == 0) {
-            // ================================================== decode: literals -> ring, matches -> queue
-            uint32_t nm = 0, acc = 0;
-            int status = 0;
-            if (st == 1) {
-                if (held) {
-                    sts_u32(s_q, held);
-                    sts_u32(s_q + 4, 0u);
-                    nm = 1;
-                    acc = held >> 16;
-                    held = 0;
-                }
-                while (nm < BQ_MATCHES && acc < BATCH_MAX_OUT) {
-                    br.refill();
-                    uint32_t e = lds_u32(s_ll + (((uint32_t)br.buf & ((1u << LL_ROOTB) - 1)) << 2));
-                    if (e < K_LEN) {  // literal
-                        br.consume(e & 15);
-                        sts_u8(s_ring + ((opos + acc) & RINGB_MASK), (e >> 8) & 0xffu);
-                        acc++;
-                        continue;
-                    }
-                    if (e >= K_SPECIAL) {
-                        if (e == E_SLOW) e = slow_entry<false>(&S.ll_hd, S.ll_sym, br.peek(15), LL_ROOTB);
-                        if (e >= K_SPECIAL) { status = -INF_BAD_SYMBOL; break; }
-                        if (e < K_LEN) {
-                            br.consume(e & 15);
-                            sts_u8(s_ring + ((opos + acc) & RINGB_MASK), (e >> 8) & 0xffu);
-                            acc++;
-                            continue;
-                        }
-                    }
-                    if (e >= K_EOB) {  // end of this deflate block
-                        br.consume(e & 15);
-                        st = 0;
-                        break;
-                    }
-                    const uint32_t cl = e & 15, xb = (e >> 4) & 15;
-                    const uint32_t len = ((e >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, cl, xb);
-                    br.consume(cl + xb);
-                    br.refill();
-                    uint32_t d = lds_u32(s_d + (((uint32_t)br.buf & ((1u << D_ROOTB) - 1)) << 2));
-                    if (d >= K_SPECIAL) {
-                        if (d == E_SLOW) d = slow_entry<true>(&S.d_hd, S.d_sym, br.peek(15), D_ROOTB);
-                        if (d >= K_SPECIAL) { status = -INF_BAD_DISTANCE; break; }
-                    }
-                    const uint32_t dcl = d & 15, dxb = (d >> 4) & 15;
-                    const uint32_t dist = ((d >> 8) & 0xffffu) + bfe_u32((uint32_t)br.buf, dcl, dxb);
-                    br.consume(dcl + dxb);
-                    if (dist > opos + acc - ostart) { status = -INF_BAD_DISTANCE; break; }
-                    const uint32_t packed = (len << 16) | (dist - 1);
-                    if (acc + len > BATCH_MAX_OUT) {  // does not fit: first entry of the next batch
-                        held = packed;
-                        break;
-                    }
-                    sts_u32(s_q + 8 * nm, packed);
-                    sts_u32(s_q + 8 * nm + 4, acc);
-                    nm++;
-                    acc += len;
-                }
-            } else if (st == 2) {
-                while (stored_left && acc < BATCH_MAX_OUT) {
-                    br.refill();
-                    sts_u8(s_ring + ((opos + acc) & RINGB_MASK), br.take(8));
-                    acc++;
-                    stored_left--;
-                }
-                if (!stored_left) st = 0;
-            } else if (bfinal) {
-                status = 1;
-            } else {
-                // ---- block header
-                br.refill();
-                bfinal = br.take(1);
-                const uint32_t btype = br.take(2);
-                if (btype == 0) {
-                    br.consume(br.cnt & 7);
-                    br.refill();
-                    const uint32_t len = br.take(16);
-                    br.refill();
-                    const uint32_t nlen = br.take(16);
-                    if ((len ^ 0xffffu) != nlen) status = -INF_BAD_STORED;
-                    stored_left = len;
-                    st = len ? 2 : 0;
-                } else if (btype == 1) {
-                    for (int i = 0; i < 144; i++) S.lens[i] = 8;
-                    for (int i = 144; i < 256; i++) S.lens[i] = 9;
-                    for (int i = 256; i < 280; i++) S.lens[i] = 7;
-                    for (int i = 280; i < 288; i++) S.lens[i] = 8;
-                    for (int i = 0; i < 32; i++) S.lens[288 + i] = 5;
-                    S.hlit = 288;
-                    S.hdist = 32;
-                    status = 2;
-                    st = 1;
-                } else if (btype == 2) {
-                    // code-length code -> lens[]; its small LUT lives in d_lut until the real one is built
-                    br.refill();
-                    const uint32_t hlit = br.take(5) + 257, hdist = br.take(5) + 1, hclen = br.take(4) + 4;
-                    uint8_t cl[19];
-                    for (int i = 0; i < 19; i++) cl[i] = 0;
-                    for (uint32_t i = 0; i < hclen; i++) {
-                        br.refill();
-                        cl[MBF_TBL(CL_ORDER, i)] = (uint8_t)br.take(3);
-                    }
-                    uint16_t* cl_lut = (uint16_t*)S.d_lut;
-                    int rc = (hlit > 286 || hdist > 30) ? (int)INF_BAD_HEADER
-                                                        : build_table(cl, 19, CL_ROOT, cl_lut, S.d_sym, &S.d_hd, true);
-                    uint32_t nn = hlit + hdist, i = 0;
-                    while (!rc && i < nn) {
-                        br.refill();
-                        const uint32_t e = cl_lut[br.peek(CL_ROOT)];
-                        if (e >= LUT_SLOW) { rc = INF_BAD_HEADER; break; }
-                        br.consume(e & 15);
-                        const uint32_t s2 = e >> 4;
-                        if (s2 < 16) { S.lens[i++] = (uint8_t)s2; continue; }
-                        uint32_t rep, val = 0;
-                        if (s2 == 16) {
-                            if (i == 0) { rc = INF_BAD_HEADER; break; }
-                            val = S.lens[i - 1];
-                            rep = 3 + br.take(2);
-                        } else if (s2 == 17) {
-                            rep = 3 + br.take(3);
-                        } else {
-                            rep = 11 + br.take(7);
-                        }
-                        if (i + rep > nn) { rc = INF_BAD_HEADER; break; }
-                        for (uint32_t k = 0; k < rep; k++) S.lens[i++] = (uint8_t)val;
-                    }
-                    if (!rc && S.lens[256] == 0) rc = INF_BAD_HEADER;
-                    S.hlit = hlit;
-                    S.hdist = hdist;
-                    status = rc ? -rc : 2;
-                    st = 1;
-                } else {
-                    status = -INF_BAD_BTYPE;
-                }
-            }
-            S.qn = nm;
-            S.qacc = acc;
-            S.status = status;
-        }
-        __syncwarp();
-        const uint32_t nm = S.qn, acc = S.qacc;
-        const int status = S.status;
-        if (opos + acc > oend) { err = INF_OUTPUT_OVERRUN; break; }
-        if (acc) {
-            // ================================================== materialise the batch
-            // older output goes to HBM first (far matches read it back through L2)
-            const uint32_t upto = min(opos & ~15u, oend);
-            ring_flush_n<RINGB_MASK>(S.ring, U, flushed, upto, lane);
-            if (upto > flushed) flushed = upto;
-            __syncwarp();
-            // pass 1: one whole match per lane, provided it reads nothing of this batch
-            uint32_t len = 0, dist = 1, off = 0;
-            bool dep = false;
-            if ((uint32_t)lane < nm) {
-                const uint32_t m = lds_u32(s_q + 8 * lane);
-                off = lds_u32(s_q + 8 * lane + 4);
-                len = m >> 16;
-                dist = (m & 0x7fffu) + 1u;
-                dep = dist < off + len;
-            }
-            const uint32_t dst = opos + off, src = dst - dist;
-            const uint32_t len1 = dep ? 0u : len;
-            const bool near = dist <= BATCH_NEAR;
-            for (uint32_t base = 0; __any_sync(0xffffffffu, base < len1); base += 16) {
-                if (base < len1) {
-                    const uint32_t rem = min(16u, len1 - base);
-                    uint32_t w[4];
-                    if (near) {
-                        // 16 source bytes from the ring with aligned 32-bit loads + funnel shifts
-                        const uint32_t s0 = src + base;
-                        const uint32_t sh = (s0 & 3u) * 8u;
-                        uint32_t x[5];
-#pragma unroll
-                        for (int q = 0; q < 5; q++) x[q] = lds_u32(s_ring + (((s0 & ~3u) + 4u * q) & RINGB_MASK));
-#pragma unroll
-                        for (int q = 0; q < 4; q++) w[q] = __funnelshift_r(x[q], x[q + 1], sh);
-                    } else {
-                        const uint8_t* sp = U + src + base;  // flushed before this batch; through L2
-#pragma unroll
-                        for (int q = 0; q < 4; q++) w[q] = (uint32_t)(4 * q) < rem ? ldu32_cg(sp + 4 * q) : 0u;
-                    }
-                    const uint32_t d0 = (dst + base) & RINGB_MASK;
-                    if (d0 + 16 <= (uint32_t)RINGB) {
-#pragma unroll
-                        for (int k = 0; k < 16; k++)
-                            if ((uint32_t)k < rem) sts_u8(s_ring + d0 + k, (w[k >> 2] >> (8 * (k & 3))) & 0xffu);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 16; k++)
-                            if ((uint32_t)k < rem) sts_u8(s_ring + ((d0 + k) & RINGB_MASK), (w[k >> 2] >> (8 * (k & 3))) & 0xffu);
-                    }
-                }
-            }
-            __syncwarp();
-            // pass 2: matches that read this batch's own output (or overlap themselves), in order, 32 lanes each
-            unsigned mm = __ballot_sync(0xffffffffu, dep);
-            while (mm) {
-                const int j = __ffs(mm) - 1;
-                mm &= mm - 1;
-                const uint32_t lj = __shfl_sync(0xffffffffu, len, j);
-                const uint32_t dj = __shfl_sync(0xffffffffu, dist, j);
-                const uint32_t dstj = opos + __shfl_sync(0xffffffffu, off, j);
-                const uint32_t sj = dstj - dj;
-                if (dj >= lj) {
-                    for (uint32_t i = lane; i < lj; i += 32)
-                        sts_u8(s_ring + ((dstj + i) & RINGB_MASK), lds_u8(s_ring + ((sj + i) & RINGB_MASK)));
-                } else {  // the source repeats with period dist (all of it precedes dst)
-                    for (uint32_t i = lane; i < lj; i += 32)
-                        sts_u8(s_ring + ((dstj + i) & RINGB_MASK), lds_u8(s_ring + ((sj + i % dj) & RINGB_MASK)));
-                }
-                __syncwarp();
-            }
-            opos += acc;
-        }
-        if (status < 0) { err = -status; break; }
-        if (status == 1) break;
-        if (status == 2) {
-            const uint32_t hlit = S.hlit, hdist = S.hdist;
-            err = build_lut_warp<false>(S.lens, (int)hlit, LL_ROOTB, S.ll_lut, S.ll_sym, &S.ll_hd, S.run, lane);
-            if (!err) err = build_lut_warp<true>(S.lens + hlit, (int)hdist, D_ROOTB, S.d_lut, S.d_sym, &S.d_hd, S.run, lane);
-            if (err) break;
-        }
-    }
-    __syncwarp();
-    if (!err) {
-        ring_flush_n<RINGB_MASK>(S.ring, U, flushed, min(opos, oend), lane);
-        if (opos != oend) err = INF_SIZE_MISMATCH;
-        else if (lane == 0 && br.bytes_consumed(mis) > a.blk.clen[b]) err = INF_INPUT_OVERRUN;
-    }
-    if (err && lane == 0) set_err(a.meta, WERR_INFLATE + (uint32_t)err, b);
-}
-
 }  // namespace mbf
 #include "inflate_twopass.cuh"
+#include "inflate_par.cuh"
 namespace mbf {
 
 // ---------------------------------------------------------------------------------------------

@@ -184,7 +184,7 @@ struct Pipeline {
     WinBufs wb[2];
     DevBuf U[2];
     size_t U_cap[2] = {0, 0};  // data bytes (without prefix/slack); the two buffers grow independently
-    DevBuf d_meta, d_chain, d_carry, d_tscratch, d_tok[2], d_ntok[2];
+    DevBuf d_meta, d_chain, d_carry, d_tscratch, d_tok[2], d_ntok[2], d_fb[2];
     PinnedBuf h_meta_front, h_meta_main;
     int sm_count = 148;
     bool sync_debug = false;
@@ -593,70 +593,72 @@ struct Pipeline {
         w.timed = true;
     }
 
-    // K1 selection (MBF_BAM_INFLATE_D): 308 = two-pass, 8 decoders per warp (production; 302/304/316 =
-    // 2/4/16 decoders), 1 = one-pass warp-per-block kernel, 0 = single-lane reference kernel
+    // K1.  Pass 1 (Huffman decode -> tokens): MBF_BAM_INFLATE_D = 400 (default) k_tokens_par<128,41>, 401
+    // <256,21>, 402 <128,33>, 403 <64,41> (one CTA per member, lanes share the tables; members it cannot
+    // handle go to k_tokens_bf<8>); 302/304/308/316 = k_tokens_bf for every member with 2/4/8/16 decoders per
+    // warp (the round-1 production kernel).  Pass 2 (LZ77): k_lz_resolve.
     void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks, cudaStream_t si) {
-        const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 308);
-        w.two_pass = false;
+        const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 400);
+        DevBuf& tokb = d_tok[bi];
+        DevBuf& ntokb = d_ntok[bi];
+        tokb.ensure((U_cap[bi] + 65536) * 4);
+        ntokb.ensure((size_t)(cand_cap + 8) * 4);
+        d_fb[bi].ensure((size_t)(cand_cap + 8) * 4);
+        d_tscratch.ensure((size_t)2 * sm_count * 32 * 32 * sizeof(TokScratch));
+        TokenArgs ta{w.c_ptr, b.cpos, b.clen, b.isize, b.uoff, tokb.as<uint32_t>(), ntokb.as<uint32_t>(), U_PREFIX,
+                     &dmeta(bi)->n_blocks, &dmeta(bi)->inflate_next, &dmeta(bi)->err, &dmeta(bi)->err_info,
+                     d_tscratch.as<TokScratch>() + (size_t)bi * sm_count * 32 * 32,
+                     &dmeta(bi)->n_tokens, nullptr};
+        auto launch_bf = [&](auto kernel, int smem, int dl, uint32_t n_members) {
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
+            // The persistent decoders take about 4/5 of what shared memory allows (9 of 11 CTAs per SM
+            // with 8 decoders per warp): the rest is room for the other window's resolve pass, scan and
+            // count kernels to run beside them (the decoders are latency bound and leave issue slots
+            // free).  Measured on the 50M-read bench: 11 -> 112 ms, 10 -> 110 ms, 9 -> 108 ms per job.
+            const uint32_t cap = env_u32("MBF_BAM_TOKENS_PER_SM", (uint32_t)std::max(1, per_sm * 9 / 11));
+            if (cap) per_sm = std::min<int>(per_sm, (int)cap);
+            uint32_t grid = std::min<uint32_t>((n_members + dl - 1) / dl, (uint32_t)(sm_count * per_sm));
+            kernel<<<std::max(1u, grid), 32, smem, si>>>(ta);
+        };
+        auto launch_par = [&](auto kernel, int nt, size_t smem) {
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int per_sm = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem));
+            const uint32_t cap = env_u32("MBF_BAM_PAR_PER_SM", 0);
+            if (cap) per_sm = std::min<int>(per_sm, (int)cap);
+            const uint32_t grid = std::min<uint32_t>(n_blocks, (uint32_t)(sm_count * std::max(1, per_sm)));
+            ParArgs pa{ta, d_fb[bi].as<uint32_t>(), &dmeta(bi)->fb_count};
+            kernel<<<std::max(1u, grid), nt, smem, si>>>(pa);
+            launched("k_tokens_par", si);
+            // the members it handed over (stored blocks, exotic tables, corrupt streams): usually none
+            ta.list = d_fb[bi].as<uint32_t>();
+            ta.n_blocks = &dmeta(bi)->fb_count;
+            ta.queue_head = &dmeta(bi)->fb_next;
+            launch_bf(k_tokens_bf<8, true>, (int)sizeof(TokensShared32<8>), 8, (uint32_t)sm_count * 8u);
+            launched("k_tokens_bf(fallback)", si);
+        };
         switch (mode_d) {
-            case 0: {
-                InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
-                k_inflate<<<n_blocks, 32, 0, si>>>(ia);
-                launched("k_inflate", si);
-                break;
-            }
-            case 1: {
-                InflateArgs ia{w.c_ptr, b, U[bi].as<uint8_t>(), dmeta(bi)};
-                k_inflate_batched<<<n_blocks, 32, 0, si>>>(ia);
-                launched("k_inflate_batched", si);
-                break;
-            }
-            case 302: case 304: case 308: case 316: {
-                // two-pass: SIMT token decode (DL = mode - 300 decoders per warp), then one warp per block
-                // resolves LZ77
-                const int dl = (int)mode_d - 300;
-                DevBuf& tokb = d_tok[bi];
-                DevBuf& ntokb = d_ntok[bi];
-                tokb.ensure((U_cap[bi] + 65536) * 4);
-                ntokb.ensure((size_t)(cand_cap + 8) * 4);
-                d_tscratch.ensure((size_t)2 * sm_count * 32 * 32 * sizeof(TokScratch));
-                TokenArgs ta{w.c_ptr, b.cpos, b.clen, b.isize, b.uoff, tokb.as<uint32_t>(), ntokb.as<uint32_t>(), U_PREFIX,
-                             &dmeta(bi)->n_blocks, &dmeta(bi)->inflate_next, &dmeta(bi)->err, &dmeta(bi)->err_info,
-                             d_tscratch.as<TokScratch>() + (size_t)bi * sm_count * 32 * 32,
-                             &dmeta(bi)->n_tokens};
-                auto launch_tokens = [&](auto kernel, int smem) {
-                    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                    int per_sm = std::max(1, std::min(32, (227 * 1024) / (smem + 1024)));
-                    // The persistent decoders take about 4/5 of what shared memory allows (9 of 11 CTAs per SM
-                    // with 8 decoders per warp): the rest is room for the other window's resolve pass, scan and
-                    // count kernels to run beside them (the decoders are latency bound and leave issue slots
-                    // free).  Measured on the 50M-read bench: 11 -> 112 ms, 10 -> 110 ms, 9 -> 108 ms per job.
-                    const uint32_t cap = env_u32("MBF_BAM_TOKENS_PER_SM", (uint32_t)std::max(1, per_sm * 9 / 11));
-                    if (cap) per_sm = std::min<int>(per_sm, (int)cap);
-                    uint32_t grid = std::min<uint32_t>((n_blocks + dl - 1) / dl, (uint32_t)(sm_count * per_sm));
-                    kernel<<<grid, 32, smem, si>>>(ta);
-                };
-                const bool pipe = env_u32("MBF_BAM_TOKENS_PIPE", 1) != 0;  // 0: token emitted in its own trip
-                if (dl == 16) launch_tokens(k_tokens_bf<16, true>, (int)sizeof(TokensShared32<16>));
-                else if (dl == 8 && pipe) launch_tokens(k_tokens_bf<8, true>, (int)sizeof(TokensShared32<8>));
-                else if (dl == 8) launch_tokens(k_tokens_bf<8, false>, (int)sizeof(TokensShared32<8>));
-                else if (dl == 4) launch_tokens(k_tokens_bf<4, true>, (int)sizeof(TokensShared32<4>));
-                else launch_tokens(k_tokens_bf<2, true>, (int)sizeof(TokensShared32<2>));
-                launched("k_tokens_bf", si);
-                CK(cudaEventRecord(w.t[7], si));
-                CK(cudaEventRecord(w.ev_cfree, si));  // pass 2 reads tokens only: the next H2D into this buffer may start
-                w.two_pass = true;
-                ResolveArgs ra{tokb.as<uint32_t>(), ntokb.as<uint32_t>(), b.isize, b.uoff, U_PREFIX, U[bi].as<uint8_t>(),
-                               &dmeta(bi)->n_blocks, &dmeta(bi)->err, &dmeta(bi)->err_info};
-                const uint32_t rgrid = (n_blocks + RESOLVE_WARPS - 1) / RESOLVE_WARPS;
-                if (env_u32("MBF_BAM_RESOLVE_RING", 2048) == 1024) k_lz_resolve<1024><<<rgrid, 32 * RESOLVE_WARPS, 0, si>>>(ra);
-                else k_lz_resolve<2048><<<rgrid, 32 * RESOLVE_WARPS, 0, si>>>(ra);
-                launched("k_lz_resolve", si);
-                break;
-            }
+            case 400: launch_par(k_tokens_par<128, 41>, 128, sizeof(ParShared<128, 41>)); break;
+            case 401: launch_par(k_tokens_par<256, 21>, 256, sizeof(ParShared<256, 21>)); break;
+            case 402: launch_par(k_tokens_par<128, 33>, 128, sizeof(ParShared<128, 33>)); break;
+            case 403: launch_par(k_tokens_par<64, 41>, 64, sizeof(ParShared<64, 41>)); break;
+            case 302: launch_bf(k_tokens_bf<2, true>, (int)sizeof(TokensShared32<2>), 2, n_blocks); launched("k_tokens_bf", si); break;
+            case 304: launch_bf(k_tokens_bf<4, true>, (int)sizeof(TokensShared32<4>), 4, n_blocks); launched("k_tokens_bf", si); break;
+            case 308: launch_bf(k_tokens_bf<8, true>, (int)sizeof(TokensShared32<8>), 8, n_blocks); launched("k_tokens_bf", si); break;
+            case 316: launch_bf(k_tokens_bf<16, true>, (int)sizeof(TokensShared32<16>), 16, n_blocks); launched("k_tokens_bf", si); break;
             default:
-                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 0, 1, 302, 304, 308 or 316");
+                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 400-403 or 302, 304, 308, 316");
         }
+        CK(cudaEventRecord(w.t[7], si));
+        CK(cudaEventRecord(w.ev_cfree, si));  // pass 2 reads tokens only: the next H2D into this buffer may start
+        w.two_pass = true;
+        ResolveArgs ra{tokb.as<uint32_t>(), ntokb.as<uint32_t>(), b.isize, b.uoff, U_PREFIX, U[bi].as<uint8_t>(),
+                       &dmeta(bi)->n_blocks, &dmeta(bi)->err, &dmeta(bi)->err_info};
+        const uint32_t rgrid = (n_blocks + RESOLVE_WARPS - 1) / RESOLVE_WARPS;
+        if (env_u32("MBF_BAM_RESOLVE_RING", 2048) == 1024) k_lz_resolve<1024><<<rgrid, 32 * RESOLVE_WARPS, 0, si>>>(ra);
+        else k_lz_resolve<2048><<<rgrid, 32 * RESOLVE_WARPS, 0, si>>>(ra);
+        launched("k_lz_resolve", si);
     }
 
     int count_grid() const { return sm_count * 8; }

@@ -84,7 +84,7 @@ def test_inflate_long_matches_near_far_and_overlapping(mb, tmp_path, monkeypatch
         w.write(payload, atomic=False)
         w.close()
     data = p.read_bytes()
-    for d in ("308", "304", "1", "0"):
+    for d in ("400", "401", "402", "403", "308", "304"):
         monkeypatch.setenv("MBF_BAM_INFLATE_D", d)
         assert mb.inflate_buffer(data) == payload, d
 
@@ -307,12 +307,12 @@ def test_baseline_config_shapes(mb, tmp_path, cfg, reads):
 
 
 def test_alternate_inflate_kernels_agree(mb, tmp_path, monkeypatch):
-    """The single-lane and the two-pass inflate kernels (MBF_BAM_INFLATE_D) must give the same bytes as the
-    production kernel and zlib."""
+    """Every pass-1 variant (MBF_BAM_INFLATE_D: the CTA-per-member kernel in four shapes, the lane-per-member
+    kernel with 2..16 decoders per warp) must give the same bytes as zlib."""
     path, *_ = make_case(tmp_path, 17, n_reads=30_000, random_seq=True)
     data = open(path, "rb").read()
     want = b"".join(p for _, _, p in bamio.iter_bgzf_blocks(data))
-    for d in ("0", "1", "302", "304", "308", "316"):
+    for d in ("400", "401", "402", "403", "302", "304", "308", "316"):
         monkeypatch.setenv("MBF_BAM_INFLATE_D", d)
         assert mb.inflate_buffer(data) == want, d
 

@@ -8,8 +8,10 @@ import bench  # noqa: E402
 import mbf_bam_b200 as mb  # noqa: E402
 
 reads = int(os.environ.get("MBF_BENCH_READS", "4000000"))
-path, iv, giv, info, _ = bench.ensure_bam(os.environ.get("MBF_BENCH_DIR", "/tmp/mbf_bench"), reads, 0, 1, lambda: None)
+cfg = int(os.environ.get("MBF_BENCH_CONFIG", "1"))
+path, iv, giv, info, _ = bench.ensure_bam(bench.BENCH_CONFIGS[cfg], os.environ.get("MBF_BENCH_DIR"), reads, 0, lambda: None)
 rd = mb.Reader(path)
+rd.set_device(0)
 if os.environ.get("MBF_PROFILE_RESIDENT", "1") != "0":
     rd.preload()
 else:
