@@ -183,6 +183,37 @@ int mbfbam_count_introns_multi(mbfbam_reader* r, const int32_t* devices, int32_t
                                mbfbam_stats* stats, char* err, size_t errlen);
 void mbfbam_free_introns(mbfbam_introns* x);
 
+/* Replaces py_quantify_gene_reads (src/count_reads/quantify.rs:20-75, :98-146; wrapper src/lib.rs:247-264): per gene the
+ * number of reads starting at each position, split into reads congruent (bucket 0) and incongruent (bucket 1)
+ * with the gene's strand; a read counts once per gene, no NH logic.  job->mode and each_read_counts_once are
+ * ignored.  Library-allocated result: n entries (global gene slot as in mbfbam_counts, bucket, pos, count) in no
+ * particular order; scanned[c] has the meaning it has in the mbfbam_counts struct: every gene of a scanned contig gets
+ * a -- possibly empty -- list in the Python result, quantify.rs:148-153. */
+typedef struct mbfbam_gene_pos_counts {
+    uint64_t n;
+    uint32_t* gene;
+    uint32_t* pos;
+    uint32_t* count;
+    uint8_t* bucket;
+    uint8_t* scanned;
+} mbfbam_gene_pos_counts;
+int mbfbam_quantify_gene_reads(mbfbam_reader* r, const mbfbam_count_job* job, mbfbam_gene_pos_counts* out,
+                               mbfbam_stats* stats, char* err, size_t errlen);
+void mbfbam_free_gene_pos_counts(mbfbam_gene_pos_counts* x);
+
+/* Replaces py_calculate_duplicate_distribution (src/duplicate_distribution.rs:44-86; wrapper src/lib.rs:108-116):
+ * {k: how many distinct (reference, position, strand, sequence) occur exactly k times}.  Reads are keyed by a
+ * 96-bit fingerprint of (tid, pos, is_reverse, SEQ) instead of the byte string (deviations). */
+typedef struct mbfbam_dup_hist {
+    uint64_t n;
+    uint32_t* k;
+    uint64_t* count;
+} mbfbam_dup_hist;
+int mbfbam_duplicate_distribution(mbfbam_reader* r, const int32_t* devices, int32_t n_devices, int32_t shard_index,
+                                  int32_t shard_count, mbfbam_dup_hist* out, mbfbam_stats* stats, char* err,
+                                  size_t errlen);
+void mbfbam_free_dup_hist(mbfbam_dup_hist* x);
+
 /* ChunkedGenome (src/count_reads/chunked_genome.rs:17-43,72-119): writes up to `cap`
  * chunks (tid,start,stop) and returns the total count.  gene_intervals == NULL gives
  * new_without_tree().  Exposed for tests and for sharding decisions made by the host. */

@@ -7,6 +7,9 @@ star-imports the native module; reference src/lib.rs:286-299 lists its functions
     count_reads_stranded(...)      -> (forward_dict, reverse_dict)
     count_reads_weighted(...)      -> (forward_dict, reverse_dict) of 1/NH weighted floats (new)
     count_introns(filename, index_filename=None)
+    quantify_gene_reads(filename, index_filename, intervals, gene_intervals)
+                                   -> (congruent, incongruent) {gene_id: [(pos, n_reads)]}
+    calculate_duplicate_distribution(filename, index_filename=None) -> {k: occurrences}
 
 The native module is built in-tree by `__graft_entry__.build()` (or `make -C mbf_bam_b200/csrc`).
 There is no CPU implementation behind these names: importing works anywhere, calling needs a GPU.
@@ -15,6 +18,7 @@ try:
     from .mbf_bam import (  # noqa: F401
         Reader,
         __version__,
+        calculate_duplicate_distribution,
         cigar_expand,
         count_introns,
         count_reads_stranded,
@@ -25,6 +29,7 @@ try:
         release_device,
         inflate_buffer,
         last_stats,
+        quantify_gene_reads,
     )
 except ImportError as e:  # pragma: no cover
     raise ImportError(

@@ -34,7 +34,9 @@ constexpr int PT_ROOT_LL = 9;       // root bits of the literal/length table
 constexpr int PT_ROOT_D = 8;        // ... of the distance table
 constexpr int PT_SUB_CAP = 768;     // shared pool of second-level entries (zlib's bound for 9 root bits is 340)
 constexpr uint32_t E2_LINK = 1u << 29;          // with K_SPECIAL: [8:5] second-level bits, [19:10] pool offset
-constexpr uint32_t E2_LINKTMP = 0xD0000000u;    // during the build: | second-level bits so far (atomicMax)
+constexpr uint32_t E3_BAD = K_SPECIAL | E2_LINK;  // "no such code": a link to pool slot 0, which holds E3_TERM
+constexpr uint32_t E3_TERM = K_SPECIAL;           // terminal: kind 3, consumes nothing
+constexpr uint32_t E2_LINKTMP = 0xF0000000u;    // during the build: | second-level bits so far (atomicMax; > E3_BAD)
 constexpr uint32_t PF_EOB = 1u << 31, PF_INV = 1u << 30, PF_DEAD = 1u << 29;  // flags beside a bit position
 constexpr uint32_t PF_ANY = PF_EOB | PF_INV | PF_DEAD;
 constexpr int PT_SW_MIN = 5;        // shortest sub-sequence in words
@@ -72,7 +74,7 @@ __device__ __forceinline__ int build_two_level(const uint8_t* lens, int n, int r
                                                uint32_t* sub_alloc, uint32_t* run, uint32_t* first, uint16_t* rev, int lane) {
     const uint32_t rmask = (1u << root) - 1u;
     if (lane < 16) run[lane] = 0;
-    for (int i = lane; i < (1 << root); i += 32) lut[i] = E2_INVALID;
+    for (int i = lane; i < (1 << root); i += 32) lut[i] = E3_BAD;
     __syncwarp();
     for (int s = lane; s < n; s += 32) {
         const uint32_t l = lens[s];
@@ -112,7 +114,8 @@ __device__ __forceinline__ int build_two_level(const uint8_t* lens, int n, int r
             const uint32_t r = __brev(code) >> (32 - l);
             rev[s] = (uint16_t)r;
             if (l <= (uint32_t)root) {
-                const uint32_t e = make_entry<IS_DIST, 2>((uint32_t)s, l);
+                uint32_t e = make_entry<IS_DIST, 2>((uint32_t)s, l);
+                if (e >= K_SPECIAL) e = E3_BAD;  // a symbol that may not occur (286, 287; distance 30, 31)
                 for (uint32_t k = r; k <= rmask; k += (1u << l)) lut[k] = e;
             } else {
                 atomicMax(&lut[r & rmask], E2_LINKTMP | (l - (uint32_t)root));  // longest code below this prefix
@@ -138,7 +141,8 @@ __device__ __forceinline__ int build_two_level(const uint8_t* lens, int n, int r
             const uint32_t r = rev[s];
             const uint32_t e = lut[r & rmask];
             const uint32_t sl = (e >> 5) & 15u, off = (e >> 10) & 0x3ffu;
-            const uint32_t ent = make_entry<IS_DIST, 2>((uint32_t)s, l);
+            uint32_t ent = make_entry<IS_DIST, 2>((uint32_t)s, l);
+            if (ent >= K_SPECIAL) ent = E3_TERM;
             for (uint32_t k = r >> root; k < (1u << sl); k += (1u << (l - (uint32_t)root))) sub[off + k] = ent;
         }
     }
@@ -152,9 +156,19 @@ struct SmemBits {
     uint32_t s_cb;    // shared address of the staged words
     uint32_t rel;     // bit position relative to the first staged word
     uint32_t limit;   // bits that may be consumed
-    __device__ __forceinline__ uint32_t peek() const {
-        const uint32_t a = s_cb + ((rel >> 5) << 2);
-        return __funnelshift_r(lds_u32(a), lds_u32(a + 4), rel & 31u);
+    uint32_t lo, hi, cur;  // the two words at word index `cur`
+    __device__ __forceinline__ void init(uint32_t s_cb_, uint32_t rel_, uint32_t limit_) {
+        s_cb = s_cb_; rel = rel_; limit = limit_; cur = 0xffffffffu; lo = hi = 0;
+    }
+    __device__ __forceinline__ uint32_t peek() {
+        const uint32_t wi = rel >> 5;
+        if (wi != cur) {
+            const uint32_t a = s_cb + (wi << 2);
+            lo = lds_u32(a);
+            hi = lds_u32(a + 4);
+            cur = wi;
+        }
+        return __funnelshift_r(lo, hi, rel & 31u);
     }
     __device__ __forceinline__ uint32_t take(uint32_t n) {
         const uint32_t v = peek() & ((1u << n) - 1u);
@@ -170,11 +184,9 @@ template <int NT, int SW_MAX>
 __device__ void par_parse_header(ParShared<NT, SW_MAX>& S, uint32_t s_cb, uint32_t bp, uint32_t cw0, uint32_t staged_words,
                                  uint32_t member_bits) {
     SmemBits br;
-    br.s_cb = s_cb;
-    br.rel = bp - cw0 * 32u;
-    br.limit = min((staged_words - 2u) * 32u, member_bits - cw0 * 32u);
+    br.init(s_cb, bp - cw0 * 32u, min((staged_words - 2u) * 32u, member_bits - cw0 * 32u));
     S.hdr_err = 0;
-    S.sub_alloc = 0;
+    S.sub_alloc = 1;  // pool slot 0 is the terminal entry every "no such code" links to
     S.bad = 0;
     S.zero = 0;
     S.hdr_bfinal = br.take(1);
@@ -200,10 +212,11 @@ __device__ void par_parse_header(ParShared<NT, SW_MAX>& S, uint32_t s_cb, uint32
         HuffDec* cl_hd = reinterpret_cast<HuffDec*>(cl_sym + 32);
         if (build_table(cl, 19, CL_ROOT, cl_lut, cl_sym, cl_hd, true)) { S.hdr_err = 1; return; }
         const uint32_t nn = hlit + hdist;
+        const uint32_t s_cl = smem_addr(cl_lut);
         uint32_t i = 0, prev = 0;
         while (i < nn) {
             const uint32_t w = br.peek();
-            const uint32_t e = cl_lut[w & ((1u << CL_ROOT) - 1u)];
+            const uint32_t e = lds_u16(s_cl + ((w & ((1u << CL_ROOT) - 1u)) << 1));
             if (e >= LUT_SLOW) { S.hdr_err = 1; return; }
             const uint32_t cl_bits = e & 15u, s2 = e >> 4;
             if (s2 < 16u) {
@@ -245,52 +258,63 @@ __device__ void par_parse_header(ParShared<NT, SW_MAX>& S, uint32_t s_cb, uint32
 // Decode tokens from bit `start_bp` until the position reaches `end_bp` (a token that starts before end_bp is
 // decoded whole), the end-of-block code, or an invalid code.  Returns where it stopped | PF_EOB | PF_INV.
 // All positions are member-relative; cw0_bits = first staged word * 32.
+// second-level lookup without divergence: e = special ? shared[addr] : e
+__device__ __forceinline__ uint32_t lds_if_special(uint32_t e, uint32_t addr) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.u32 p, %0, 0xC0000000;\n\t@p ld.shared.u32 %0, [%1];\n\t}" : "+r"(e) : "r"(addr));
+    return e;
+}
+
 template <bool EMIT>
 __device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t cw0_bits, uint32_t s_ll, uint32_t s_d, uint32_t s_sub,
                                             uint32_t s_zero, uint32_t start_bp, uint32_t end_bp, uint32_t& n_out, uint32_t* tk) {
-    const uint32_t rel = start_bp - cw0_bits;
-    uint32_t a = s_cb + ((rel >> 5) << 2);
-    uint32_t bo = rel & 31u;
+    uint32_t pos = start_bp - cw0_bits;  // bits from the first staged word
+    uint32_t lim = end_bp - cw0_bits;    // set to 0 to leave the loop
+    uint32_t a = s_cb + ((pos >> 5) << 2);
     uint32_t lo = lds_u32(a), hi = lds_u32(a + 4), nx = lds_u32(a + 8);
     a += 12;
-    const uint32_t a_base = s_cb + 12u;
-    const uint32_t end_rel = end_bp - cw0_bits;
     uint32_t n = 0, flags = 0;
-    while ((((a - a_base) << 3) + bo) < end_rel) {
+    // One trip = one token, one straight-line instruction sequence whatever the token is: literal/length
+    // lookup, second-level lookup (predicated load), distance lookup (a literal reads a zero word), second-level
+    // lookup, predicated token store, window advance.  End of block and invalid codes are table entries of their
+    // own (kind bit 31 set): they end the loop through `lim`, not through a branch.
+    while (pos < lim) {
+        const uint32_t bo = pos & 31u;
         const uint32_t w = __funnelshift_r(lo, hi, bo);
         uint32_t e = lds_u32(s_ll + ((w & ((1u << PT_ROOT_LL) - 1u)) << 2));
-        if (e >= K_SPECIAL) {  // second-level table (5.8 % of the literals of the bench files) or no such code
-            if (!(e & E2_LINK)) { flags = PF_INV; break; }
-            e = lds_u32(s_sub + ((((e >> 10) & 0x3ffu) + ((w >> PT_ROOT_LL) & ((1u << ((e >> 5) & 15u)) - 1u))) << 2));
-            if (e >= K_SPECIAL) { flags = PF_INV; break; }
-        }
-        const uint32_t bo1 = bo + (e & 31u);  // <= 31 + 20
-        const uint32_t kind = e >> 30;
-        if (kind == 2u) { bo = bo1; flags = PF_EOB; break; }
-        const bool m = kind == 1u;
+        e = lds_if_special(e, s_sub + ((((e >> 10) & 0x3ffu) + ((w >> PT_ROOT_LL) & ~(0xffffffffu << ((e >> 5) & 15u)))) << 2));
+        const uint32_t c1 = e & 31u;
+        const bool m = (e >> 30) == 1u;
+        const uint32_t bo1 = bo + c1;  // <= 31 + 20
         const bool up = bo1 >= 32u;
         const uint32_t w2 = __funnelshift_r(up ? hi : lo, up ? nx : hi, bo1);  // shift amount is taken mod 32
-        // distance lookup in every trip: a literal reads a zero word (consumes nothing) -- no divergence
         uint32_t d = lds_u32(m ? s_d + ((w2 & ((1u << PT_ROOT_D) - 1u)) << 2) : s_zero);
-        if (d >= K_SPECIAL) {
-            if (!(d & E2_LINK)) { flags = PF_INV; break; }
-            d = lds_u32(s_sub + ((((d >> 10) & 0x3ffu) + ((w2 >> PT_ROOT_D) & ((1u << ((d >> 5) & 15u)) - 1u))) << 2));
-            if (d >= K_SPECIAL) { flags = PF_INV; break; }
-        }
+        d = lds_if_special(d, s_sub + ((((d >> 10) & 0x3ffu) + ((w2 >> PT_ROOT_D) & ~(0xffffffffu << ((d >> 5) & 15u)))) << 2));
+        const uint32_t c2 = d & 31u;
+        const bool stop = (int32_t)(e | d) < 0;  // end of block (kind 2), no such code (kind 3: consumes nothing)
         if (EMIT) {
-            const uint32_t val = ((e >> 10) & 0xffffu) + ((w & ~(0xffffffffu << (e & 31u))) >> ((e >> 5) & 15u));
-            const uint32_t dist = ((d >> 10) & 0xffffu) + ((w2 & ~(0xffffffffu << (d & 31u))) >> ((d >> 5) & 15u));
-            __stcg(tk + n, m ? (0x80000000u | (val << 16) | ((dist - 1u) & 0x7fffu)) : val);
+            const uint32_t val = ((e >> 10) & 0xffffu) + ((w & ~(0xffffffffu << c1)) >> ((e >> 5) & 15u));
+            const uint32_t dist = ((d >> 10) & 0xffffu) + ((w2 & ~(0xffffffffu << c2)) >> ((d >> 5) & 15u));
+            if (!stop) __stcg(tk, m ? (0x80000000u | (val << 16) | ((dist - 1u) & 0x7fffu)) : val);
+            tk += stop ? 0 : 1;
         }
-        n++;
-        bo = bo1 + (d & 31u);  // <= 79
-        if (bo >= 32u) {
-            lo = hi; hi = nx; nx = lds_u32(a); a += 4; bo -= 32u;
-            if (bo >= 32u) { lo = hi; hi = nx; nx = lds_u32(a); a += 4; bo -= 32u; }
-        }
+        n += stop ? 0u : 1u;
+        flags = stop ? (((e | d) & (1u << 30)) ? PF_INV : PF_EOB) : flags;
+        lim = stop ? 0u : lim;
+        const uint32_t adv = bo1 + c2;  // <= 79
+        pos += c1 + c2;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ge.u32 p, %4, 32;\n\t"
+            "@p mov.b32 %0, %1;\n\t"
+            "@p mov.b32 %1, %2;\n\t"
+            "@p ld.shared.u32 %2, [%3];\n\t"
+            "@p add.u32 %3, %3, 4;\n\t}"
+            : "+r"(lo), "+r"(hi), "+r"(nx), "+r"(a)
+            : "r"(adv));
+        if (adv >= 64u) { lo = hi; hi = nx; nx = lds_u32(a); a += 4; }  // a token of more than 32 bits: rare
     }
     n_out = n;
-    return (cw0_bits + ((a - a_base) << 3) + bo) | flags;
+    return (cw0_bits + pos) | flags;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -334,6 +358,7 @@ __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
             __syncthreads();
             if (S.hdr_err) { fallback = true; break; }
             const uint32_t bfinal = S.hdr_bfinal, hlit = S.hdr_hlit, hdist = S.hdr_hdist;
+            if (t == 64 % NT) S.sub[0] = E3_TERM;  // (the header's scratch lived in the pool)
             if (wid == 0) {
                 const int rc = build_two_level<false>(S.lens, (int)hlit, PT_ROOT_LL, S.ll, S.sub, &S.sub_alloc, S.run[0], S.first[0], S.rev, lane);
                 if (rc && lane == 0) atomicOr(&S.bad, 1);

@@ -55,7 +55,8 @@ struct WinMeta {
     uint32_t err_info;
     uint32_t mm_count;      // multi-mapper keys appended this window (may exceed capacity)
     uint32_t owned_records;
-    uint32_t cigar_ops;     // sum of n_cigar_op of owned records (bound for intron inserts)
+    uint32_t cigar_ops;     // bound for the map inserts of a window's second pass: sum of n_cigar_op of owned records
+                            // (introns), (read, gene) hits (quantify)
     uint32_t inflate_next;  // work queue head of the token kernel (pass 1 of K1)
     uint32_t fb_count;      // members pass 1 handed to the fallback token kernel ...
     uint32_t fb_next;       // ... and that kernel's work queue head
@@ -544,6 +545,10 @@ struct CountCtx {
     uint32_t mm_cap;
     int emit_only;                   // re-run after an mm overflow: append keys, touch no counter
     double* wspill;                  // weighted, NH > NH_DENSE: [2][n_genes] f64 (1/NH added atomically)
+    // MODE 3 (quantify_gene_reads): (gene, pos) -> count per bucket in the job's 16-byte-slot map
+    ulonglong2* qmap;
+    uint32_t qmask;
+    int q_count_only;                // pass 1: only count the (read, gene) hits of owned reads (sizes the map)
 };
 
 
@@ -552,12 +557,8 @@ __device__ __forceinline__ void map_add(ulonglong2* map, uint32_t mask, unsigned
     unsigned long long h = fmix64(key ^ ((unsigned long long)tag * 0x9E3779B97F4A7C15ull));
     uint32_t i = (uint32_t)h & mask;
     for (;;) {
-        ulonglong2 cur;
-        {
-            const volatile unsigned long long* vp = (const volatile unsigned long long*)(map + i);
-            cur.x = vp[0];
-            cur.y = vp[1];
-        }
+        ulonglong2 cur;  // one 128-bit load: a slot is published by a 128-bit CAS, two 64-bit loads could tear
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(cur.x), "=l"(cur.y) : "l"(map + i));
         if (cur.x == ~0ull && cur.y == ~0ull) {
             ulonglong2 mine = make_ulonglong2(key, (unsigned long long)tag | ((unsigned long long)n << 32));
             ulonglong2 old = cas128(map + i, make_ulonglong2(~0ull, ~0ull), mine);
@@ -707,7 +708,7 @@ __global__ void __launch_bounds__(256) k_count_reads(CountCtx c) {
     const uint32_t n = c.meta->n_records;
     const int lane = threadIdx.x & 31;
     const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t my_outside = 0, my_owned = 0;
+    uint32_t my_outside = 0, my_owned = 0, my_hits = 0;
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += stride) {
         const uint32_t i = base + lane;
         uint32_t keys[SEEN_K];
@@ -731,6 +732,10 @@ __global__ void __launch_bounds__(256) k_count_reads(CountCtx c) {
                     long long nh = 1;
                     uint32_t h_index = 0;
                     enumerate_hits(c, v, iv_lo, iv_hi, MODE == 0, cstop, [&](uint32_t gw) {
+                        if (MODE == 3) {  // quantify: no NH logic at all (quantify.rs:117-140)
+                            have_nh = true;
+                            counted_direct = true;
+                        }
                         if (!have_nh) {
                             have_nh = true;
                             int rc = aux_find_nh(v.aux, v.end, &nh);
@@ -771,7 +776,11 @@ __global__ void __launch_bounds__(256) k_count_reads(CountCtx c) {
                             return true;
                         });
                         if (seen) return true;
-                        if (counted_direct) {
+                        if (MODE == 3) {
+                            my_hits++;
+                            if (!c.q_count_only)
+                                map_add(c.qmap, c.qmask, (unsigned long long)v.upos | ((unsigned long long)gene << 32), bucket, 1);
+                        } else if (counted_direct) {
                             if (!c.emit_only) {
                                 if (MODE == 2 && wclass == 0xffffffffu)
                                     atomicAdd(c.wspill + (size_t)bucket * c.n_genes + gene, 1.0 / (double)nh);
@@ -788,6 +797,14 @@ __global__ void __launch_bounds__(256) k_count_reads(CountCtx c) {
                         return true;
                     });
                     if (!hit) my_outside++;
+                    if (MODE == 3) {
+                        my_hits += (uint32_t)nk;
+                        if (!c.q_count_only)
+                            for (int k = 0; k < nk; k++)
+                                map_add(c.qmap, c.qmask, (unsigned long long)v.upos | ((unsigned long long)(keys[k] & 0x7fffffffu) << 32),
+                                        keys[k] >> 31, 1);
+                        nk = 0;
+                    }
                     if (nk && !counted_direct) {
                         // multi-mapper: one key per distinct (gene,bucket) of this read
                         for (int k = 0; k < nk; k++) {
@@ -823,7 +840,16 @@ __global__ void __launch_bounds__(256) k_count_reads(CountCtx c) {
             }
         }
     }
-    if (!c.emit_only) {
+    if (MODE == 3) {
+        if (c.q_count_only) {  // pass 1 publishes the bound for the map, pass 2 nothing
+            my_hits = __reduce_add_sync(0xffffffffu, my_hits);
+            my_owned = __reduce_add_sync(0xffffffffu, my_owned);
+            if (lane == 0) {
+                if (my_hits) atomicAdd(&c.meta->cigar_ops, my_hits);
+                if (my_owned) atomicAdd(&c.meta->owned_records, my_owned);
+            }
+        }
+    } else if (!c.emit_only) {
         my_outside = __reduce_add_sync(0xffffffffu, my_outside);
         my_owned = __reduce_add_sync(0xffffffffu, my_owned);
         if (lane == 0) {
@@ -956,6 +982,90 @@ __global__ void __launch_bounds__(256) k_count_introns(IntronCtx c) {
     if (lane == 0 && c.count_only) {
         if (my_owned) atomicAdd(&c.meta->owned_records, my_owned);
         if (my_ops) atomicAdd(&c.meta->cigar_ops, my_ops);
+    }
+}
+
+// calculate_duplicate_distribution (reference src/duplicate_distribution.rs:44-86): how often exactly k reads
+// share (reference, position, strand, sequence).  Every owned record adds 1 to the map entry of a 96-bit
+// fingerprint of (tid, pos, is_reverse, l_seq, packed SEQ bytes); k_dup_hist then turns the entry counts into
+// the histogram {k: number of distinct (position, strand, sequence) seen exactly k times}.  The reference walks
+// each contig with fetch(tid, 0, len) and groups equal `pos`: records of one group are adjacent and never
+// straddle a chunk (ownership is by pos), so chunk-range shards see whole groups.
+struct DupCtx {
+    const uint8_t* U;
+    const uint32_t* rec_off;
+    WinMeta* meta;
+    int32_t n_ref;
+    const uint32_t* ref_chunk_off;  // n_ref + 1: global chunk id base per tid (1 Mb chunks, like the intron job)
+    const uint32_t* ref_len;        // n_ref: fetch(tid, 0, len) sees pos < len only
+    uint32_t chunk_lo, chunk_hi;
+    ulonglong2* map;
+    uint32_t map_mask;
+    unsigned long long* owned_total;  // job-wide count of owned records
+};
+
+__global__ void __launch_bounds__(256) k_dup_insert(DupCtx c) {
+    const uint32_t n = c.meta->n_records;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t my_owned = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        RecView v;
+        if (!rec_view(c.U, c.rec_off[i], v)) { set_err(c.meta, WERR_RECORD, i); continue; }
+        if (v.tid < 0 || v.tid >= c.n_ref) continue;
+        if ((int32_t)v.upos < 0 || v.upos >= c.ref_len[v.tid]) continue;  // not returned by fetch(tid, 0, len)
+        const uint32_t nchunks = c.ref_chunk_off[v.tid + 1] - c.ref_chunk_off[v.tid];
+        const uint32_t ci = v.upos / 1000000u;
+        if (ci >= nchunks) continue;
+        const uint32_t g = c.ref_chunk_off[v.tid] + ci;
+        if (g < c.chunk_lo || g >= c.chunk_hi) continue;
+        my_owned++;
+        const uint8_t* seq = v.cigar + 4ull * v.n_cig;
+        const uint32_t nb = (v.l_seq + 1u) >> 1;
+        // an odd l_seq leaves the low nibble of the last byte unspecified: mask it out of the key
+        const ulonglong2 fp = qname_fingerprint(seq, nb - ((v.l_seq & 1u) ? 1u : 0u), (uint32_t)v.tid, v.upos);
+        unsigned long long h1 = fp.x, h2 = fp.y;
+        if (v.l_seq & 1u) h1 = fmix64(h1 ^ (unsigned long long)(seq[nb - 1] & 0xf0u) * 0x9E3779B97F4A7C15ull);
+        h2 = fmix64(h2 + ((v.flag & 0x10u) ? 0x51ull : 0x17ull) + ((unsigned long long)v.l_seq << 8));
+        uint32_t tag = (uint32_t)h2;
+        if (h1 == ~0ull && tag == 0xffffffffu) tag = 0;  // the empty-slot pattern
+        map_add(c.map, c.map_mask, h1, tag, 1);
+    }
+    my_owned = __reduce_add_sync(0xffffffffu, my_owned);
+    if (lane == 0 && my_owned) atomicAdd(c.owned_total, (unsigned long long)my_owned);
+}
+
+// live slots of a map, densely packed (order arbitrary): what the host downloads instead of the whole table
+__global__ void __launch_bounds__(256) k_map_compact(const ulonglong2* map, uint32_t cap, ulonglong2* out, unsigned long long out_cap,
+                                                      unsigned long long* n_out) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < cap; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        ulonglong2 e = make_ulonglong2(~0ull, ~0ull);
+        if (i < cap) e = map[i];
+        const bool live = !(e.x == ~0ull && e.y == ~0ull);
+        const unsigned b = __ballot_sync(0xffffffffu, live);
+        if (!b) continue;
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(n_out, (unsigned long long)__popc(b));
+        at = __shfl_sync(0xffffffffu, at, 0) + __popc(b & ((1u << lane) - 1u));
+        if (live && at < out_cap) out[at] = e;
+    }
+}
+
+constexpr uint32_t DUP_DENSE = 1u << 16;  // multiplicities below this are counted in a dense array
+__global__ void __launch_bounds__(256) k_dup_hist(const ulonglong2* map, uint32_t cap, unsigned long long* dense,
+                                                   unsigned long long* big, uint32_t big_cap, uint32_t* n_big) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const ulonglong2 e = map[i];
+        if (e.x == ~0ull && e.y == ~0ull) continue;
+        const uint32_t k = (uint32_t)(e.y >> 32);
+        if (k < DUP_DENSE) {
+            atomicAdd(dense + k, 1ull);
+        } else {
+            const uint32_t j = atomicAdd(n_big, 1u);
+            if (j < big_cap) big[j] = k;
+        }
     }
 }
 

@@ -147,7 +147,7 @@ struct MemSource : Source {
     void read(uint64_t off, size_t len, uint8_t* dst) const override { memcpy(dst, p + off, len); }
 };
 
-enum JobKind { JOB_COUNT, JOB_INTRONS, JOB_INFLATE };
+enum JobKind { JOB_COUNT, JOB_INTRONS, JOB_INFLATE, JOB_QUANTIFY, JOB_DUPS };
 
 struct WinBufs {
     PinnedBuf h_c;
@@ -204,6 +204,9 @@ struct Pipeline {
     DevBuf d_ref_chunk_off, d_map, d_hist, d_scalar;
     unsigned long long* hist_ptr = nullptr;
     uint64_t map_cap = 0, map_ub = 0;
+    // ---- duplicate-distribution job (shares d_map / map_cap with the intron job)
+    DupCtx dc{};
+    DevBuf d_ref_len, d_dup_dense, d_dup_big, d_dup_nbig;
     // ---- inflate-only job
     uint8_t* out_host = nullptr;
     uint64_t out_cap = 0, out_len = 0;
@@ -584,7 +587,9 @@ struct Pipeline {
             launched("k_carry_copy", s_main);
             CK(cudaEventRecord(w.t[4], s_main));
             if (kind == JOB_COUNT) launch_count(bi, 0);
-            else launch_introns(bi, 1);
+            else if (kind == JOB_QUANTIFY) launch_quantify(bi, 1);
+            else if (kind == JOB_INTRONS) launch_introns(bi, 1);
+            // JOB_DUPS: one insert per record, bounded by n_records: everything happens in the second half
             CK(cudaEventRecord(w.t[5], s_main));
         }
         CK(cudaMemcpyAsync(h_meta_main.as<WinMeta>() + bi, dmeta(bi), sizeof(WinMeta), cudaMemcpyDeviceToHost, s_main));
@@ -684,6 +689,33 @@ struct Pipeline {
         launched("k_count_reads", s_main);
     }
 
+    // quantify_gene_reads: pass 1 counts the (read, gene) hits of the window, pass 2 adds them to the map
+    void launch_quantify(int bi, int count_only) {
+        WinBufs& w = wb[bi];
+        CountCtx c = cc;
+        c.U = U[bi].as<uint8_t>();
+        c.rec_off = w.rec_off.as<uint32_t>();
+        c.meta = dmeta(bi);
+        c.qmap = d_map.as<ulonglong2>();
+        c.qmask = (uint32_t)(map_cap - 1);
+        c.q_count_only = count_only;
+        k_count_reads<3><<<count_grid(), 256, 0, s_main>>>(c);
+        launched("k_count_reads<quantify>", s_main);
+    }
+
+    void launch_dups(int bi) {
+        WinBufs& w = wb[bi];
+        DupCtx c = dc;
+        c.U = U[bi].as<uint8_t>();
+        c.rec_off = w.rec_off.as<uint32_t>();
+        c.meta = dmeta(bi);
+        c.map = d_map.as<ulonglong2>();
+        c.map_mask = (uint32_t)(map_cap - 1);
+        c.owned_total = d_scalar.as<unsigned long long>() + 1;
+        k_dup_insert<<<count_grid(), 256, 0, s_main>>>(c);
+        launched("k_dup_insert", s_main);
+    }
+
     void launch_introns(int bi, int count_only) {
         WinBufs& w = wb[bi];
         IntronCtx c = ic;
@@ -750,6 +782,30 @@ struct Pipeline {
         map_cap = ncap;
     }
 
+    // the live entries of the 16-byte-slot map, compacted on the device before they cross PCIe
+    std::vector<ulonglong2> download_map() {
+        std::vector<ulonglong2> out;
+        if (!map_cap) return out;
+        CK(cudaMemsetAsync(d_scalar.p, 0, 8, s_main));
+        k_map_count<<<sm_count * 8, 256, 0, s_main>>>(d_map.as<ulonglong2>(), (uint32_t)map_cap, d_scalar.as<unsigned long long>());
+        launched("k_map_count", s_main);
+        unsigned long long live = 0;
+        CK(cudaMemcpyAsync(&live, d_scalar.p, 8, cudaMemcpyDeviceToHost, s_main));
+        CK(cudaStreamSynchronize(s_main));
+        if (!live) return out;
+        DevBuf packed;
+        packed.ensure((size_t)live * 16);
+        CK(cudaMemsetAsync(d_scalar.p, 0, 8, s_main));
+        k_map_compact<<<sm_count * 8, 256, 0, s_main>>>(d_map.as<ulonglong2>(), (uint32_t)map_cap, packed.as<ulonglong2>(), live,
+                                                        d_scalar.as<unsigned long long>());
+        launched("k_map_compact", s_main);
+        out.resize((size_t)live);
+        CK(cudaMemcpyAsync(out.data(), packed.p, (size_t)live * 16, cudaMemcpyDeviceToHost, s_main));
+        CK(cudaStreamSynchronize(s_main));
+        st.d2h_bytes += (size_t)live * 16;
+        return out;
+    }
+
     // second half of a window's main stage: needs numbers from the first half
     void finish_main(int bi) {
         WinBufs& w = wb[bi];
@@ -795,6 +851,17 @@ struct Pipeline {
             if (m.owned_records) {
                 ensure_map((uint64_t)m.cigar_ops + 64);
                 launch_introns(bi, 0);
+            }
+        } else if (kind == JOB_QUANTIFY) {
+            st.n_records_owned += m.owned_records;
+            if (m.cigar_ops) {
+                ensure_map((uint64_t)m.cigar_ops + 64);
+                launch_quantify(bi, 0);
+            }
+        } else if (kind == JOB_DUPS) {
+            if (m.n_records) {
+                ensure_map((uint64_t)m.n_records + 64);
+                launch_dups(bi);
             }
         }
         if (w.timed) {
@@ -1186,6 +1253,23 @@ void build_count_tables(const Reader& r, const mbfbam_count_job* job, CountTable
     T.slot_iv_off[T.slot_iv.size()] = (uint32_t)T.ivs.size();
 }
 
+void upload_count_tables(Pipeline& p, const CountTables& T, const ShardPlan& plan, bool with_rank) {
+    CountCtx& c = p.cc;
+    c.tid2slot = upload(p.d_tid2slot, T.tid2slot, p.s_main);
+    c.n_ref = (int32_t)T.tid2slot.size();
+    c.slot_iv_off = upload(p.d_slot_iv_off, T.slot_iv_off, p.s_main);
+    c.iv_start = upload(p.d_iv_start, T.ivs, p.s_main);
+    c.iv_end = upload(p.d_iv_end, T.ive, p.s_main);
+    c.iv_pmax = upload(p.d_iv_pmax, T.ivp, p.s_main);
+    c.iv_gene = upload(p.d_iv_gene, T.ivg, p.s_main);
+    c.iv_rank = with_rank ? upload(p.d_iv_rank, T.ivr, p.s_main) : nullptr;
+    c.slot_chunk_off = upload(p.d_slot_chunk_off, T.slot_chunk_off, p.s_main);
+    c.chunk_stop = upload(p.d_chunk_stop, T.chunk_stop, p.s_main);
+    c.chunk_lo = (uint32_t)plan.lo;
+    c.chunk_hi = (uint32_t)plan.hi;
+    c.n_genes = (uint32_t)T.G;
+}
+
 struct CountPart {
     std::vector<unsigned long long> h;
     std::vector<double> spill;
@@ -1218,22 +1302,10 @@ void count_on_device(mbfbam_reader* rd, const CountTables& T, const mbfbam_count
         CK(cudaMemsetAsync(p.d_wspill.p, 0, std::max<size_t>(G, 1) * 16, p.s_main));
         p.d_set_size.ensure(8);
         CK(cudaMemsetAsync(p.d_set_size.p, 0, 8, p.s_main));
+        upload_count_tables(p, T, plan, job->each_read_counts_once != 0);
         CountCtx& c = p.cc;
-        c.tid2slot = upload(p.d_tid2slot, T.tid2slot, p.s_main);
-        c.n_ref = (int32_t)T.tid2slot.size();
-        c.slot_iv_off = upload(p.d_slot_iv_off, T.slot_iv_off, p.s_main);
-        c.iv_start = upload(p.d_iv_start, T.ivs, p.s_main);
-        c.iv_end = upload(p.d_iv_end, T.ive, p.s_main);
-        c.iv_pmax = upload(p.d_iv_pmax, T.ivp, p.s_main);
-        c.iv_gene = upload(p.d_iv_gene, T.ivg, p.s_main);
-        c.iv_rank = job->each_read_counts_once ? upload(p.d_iv_rank, T.ivr, p.s_main) : nullptr;
-        c.slot_chunk_off = upload(p.d_slot_chunk_off, T.slot_chunk_off, p.s_main);
-        c.chunk_stop = upload(p.d_chunk_stop, T.chunk_stop, p.s_main);
-        c.chunk_lo = (uint32_t)plan.lo;
-        c.chunk_hi = (uint32_t)plan.hi;
         c.counts = p.d_counts.as<unsigned long long>();
         c.wspill = p.d_wspill.as<double>();
-        c.n_genes = (uint32_t)G;
         CK(cudaStreamSynchronize(p.s_main));  // the tables are read by kernels on other streams too
         p.st.n_chunks = plan.hi - plan.lo;
     });
@@ -1290,14 +1362,12 @@ void introns_on_device(mbfbam_reader* rd, const std::vector<Chunk>& chunks, cons
         p.ensure_map(1024);
         p.st.n_chunks = plan.hi - plan.lo;
     });
-    // pull the map and the dense histogram
-    std::vector<ulonglong2> slots((size_t)p.map_cap);
-    CK(cudaMemcpy(slots.data(), p.d_map.p, (size_t)p.map_cap * 16, cudaMemcpyDeviceToHost));
+    // pull the live map entries and the dense histogram
+    std::vector<ulonglong2> slots = p.download_map();
     std::vector<unsigned long long> hist(std::max<size_t>(1, n_ref) * HIST_DENSE);
     CK(cudaMemcpy(hist.data(), p.d_hist.p, hist.size() * 8, cudaMemcpyDeviceToHost));
-    p.st.d2h_bytes += (size_t)p.map_cap * 16 + hist.size() * 8;
+    p.st.d2h_bytes += hist.size() * 8;
     for (const auto& s : slots) {
-        if (s.x == ~0ull && s.y == ~0ull) continue;
         out.entries.push_back({(int32_t)(uint32_t)s.y, (uint32_t)s.x, (uint32_t)(s.x >> 32), s.y >> 32});
     }
     for (size_t t = 0; t < n_ref; t++)
@@ -1306,6 +1376,105 @@ void introns_on_device(mbfbam_reader* rd, const std::vector<Chunk>& chunks, cons
     // introns.rs:75-79: every chunk that was scanned inserts its contig key (possibly empty dict)
     out.seen.assign(n_ref + 1, 0);
     for (size_t i = plan.lo; i < plan.hi; i++) out.seen[(size_t)plan.chunks[i].tid] = 1;
+    p.st.ms_pin = ms_pin;
+    p.st.n_devices = 1;
+    out.st = p.st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// quantify_gene_reads (reference src/count_reads/quantify.rs:98-146): (gene, bucket, pos) -> reads
+struct QuantEntry {
+    uint32_t gene, pos, count;
+    uint8_t bucket;
+};
+struct QuantPart {
+    std::vector<QuantEntry> entries;
+    mbfbam_stats st{};
+};
+
+void quantify_on_device(mbfbam_reader* rd, const CountTables& T, int device, int shard, int nshards, int read_threads,
+                        uint64_t prior_jobs, QuantPart& out) {
+    const Reader& r = rd->r;
+    ShardPlan plan;
+    plan.chunks = T.chunks;
+    plan_shard(r, plan, shard, nshards);
+    const double ms_pin = maybe_pin(rd, plan.ranges, prior_jobs);
+    FileSource src(&r, rd->fmap);
+    DevSlot& slot = dev_slot(device);
+    std::lock_guard<std::mutex> lk(slot.mu);
+    Pipeline& p = slot_pipeline(slot, device);
+    p.read_threads = read_threads;
+    run_with_retry(p, plan.ranges, [&](Pipeline& p) {
+        p.begin_job(&src, JOB_QUANTIFY, range_bytes(plan.ranges));
+        p.mode = 3;
+        p.d_scalar.ensure(16);
+        upload_count_tables(p, T, plan, false);
+        CK(cudaStreamSynchronize(p.s_main));
+        p.ensure_map(1024);
+        p.st.n_chunks = plan.hi - plan.lo;
+    });
+    for (const ulonglong2& s : p.download_map())
+        out.entries.push_back({(uint32_t)(s.x >> 32), (uint32_t)s.x, (uint32_t)(s.y >> 32), (uint8_t)((uint32_t)s.y & 1u)});
+    p.st.ms_pin = ms_pin;
+    p.st.n_devices = 1;
+    out.st = p.st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// calculate_duplicate_distribution (reference src/duplicate_distribution.rs:44-86)
+struct DupPart {
+    std::vector<unsigned long long> dense;  // DUP_DENSE counters
+    std::vector<unsigned long long> big;    // multiplicities >= DUP_DENSE, one entry each
+    mbfbam_stats st{};
+};
+
+void dups_on_device(mbfbam_reader* rd, const std::vector<Chunk>& chunks, const std::vector<uint32_t>& ref_chunk_off, int device,
+                    int shard, int nshards, int read_threads, uint64_t prior_jobs, DupPart& out) {
+    const Reader& r = rd->r;
+    ShardPlan plan;
+    plan.chunks = chunks;
+    plan_shard(r, plan, shard, nshards);
+    const double ms_pin = maybe_pin(rd, plan.ranges, prior_jobs);
+    const size_t n_ref = r.names.size();
+    FileSource src(&r, rd->fmap);
+    DevSlot& slot = dev_slot(device);
+    std::lock_guard<std::mutex> lk(slot.mu);
+    Pipeline& p = slot_pipeline(slot, device);
+    p.read_threads = read_threads;
+    const uint32_t BIG_CAP = 1u << 20;
+    run_with_retry(p, plan.ranges, [&](Pipeline& p) {
+        p.begin_job(&src, JOB_DUPS, range_bytes(plan.ranges));
+        p.d_scalar.ensure(16);
+        CK(cudaMemsetAsync(p.d_scalar.p, 0, 16, p.s_main));
+        p.dc.n_ref = (int32_t)n_ref;
+        p.dc.ref_chunk_off = upload(p.d_ref_chunk_off, ref_chunk_off, p.s_main);
+        p.dc.ref_len = upload(p.d_ref_len, r.lens, p.s_main);
+        p.dc.chunk_lo = (uint32_t)plan.lo;
+        p.dc.chunk_hi = (uint32_t)plan.hi;
+        CK(cudaStreamSynchronize(p.s_main));
+        p.ensure_map(1024);
+        p.st.n_chunks = plan.hi - plan.lo;
+    });
+    p.d_dup_dense.ensure((size_t)DUP_DENSE * 8);
+    p.d_dup_big.ensure((size_t)BIG_CAP * 8);
+    p.d_dup_nbig.ensure(16);
+    CK(cudaMemsetAsync(p.d_dup_dense.p, 0, (size_t)DUP_DENSE * 8, p.s_main));
+    CK(cudaMemsetAsync(p.d_dup_nbig.p, 0, 16, p.s_main));
+    k_dup_hist<<<p.sm_count * 8, 256, 0, p.s_main>>>(p.d_map.as<ulonglong2>(), (uint32_t)p.map_cap, p.d_dup_dense.as<unsigned long long>(),
+                                                     p.d_dup_big.as<unsigned long long>(), BIG_CAP, p.d_dup_nbig.as<uint32_t>());
+    p.launched("k_dup_hist", p.s_main);
+    out.dense.resize(DUP_DENSE);
+    uint32_t n_big = 0;
+    unsigned long long owned[2] = {0, 0};
+    CK(cudaMemcpyAsync(out.dense.data(), p.d_dup_dense.p, (size_t)DUP_DENSE * 8, cudaMemcpyDeviceToHost, p.s_main));
+    CK(cudaMemcpyAsync(&n_big, p.d_dup_nbig.p, 4, cudaMemcpyDeviceToHost, p.s_main));
+    CK(cudaMemcpyAsync(owned, p.d_scalar.p, 16, cudaMemcpyDeviceToHost, p.s_main));
+    CK(cudaStreamSynchronize(p.s_main));
+    if (n_big > BIG_CAP) throw Error(MBFBAM_ERR_UNSUPPORTED, "more than 2^20 distinct reads with 65536 or more copies");
+    out.big.resize(n_big);
+    if (n_big) CK(cudaMemcpy(out.big.data(), p.d_dup_big.p, (size_t)n_big * 8, cudaMemcpyDeviceToHost));
+    p.st.d2h_bytes += (size_t)DUP_DENSE * 8 + (size_t)n_big * 8 + 20;
+    p.st.n_records_owned = owned[1];
     p.st.ms_pin = ms_pin;
     p.st.n_devices = 1;
     out.st = p.st;
@@ -1584,6 +1753,104 @@ int mbfbam_count_introns_multi(mbfbam_reader* rd, const int32_t* devices, int32_
 int mbfbam_count_introns(mbfbam_reader* rd, int32_t device, int32_t shard_index, int32_t shard_count, mbfbam_introns* out,
                          mbfbam_stats* stats, char* err, size_t errlen) {
     return mbfbam_count_introns_multi(rd, &device, 1, shard_index, shard_count, out, stats, err, errlen);
+}
+
+int mbfbam_quantify_gene_reads(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_gene_pos_counts* out, mbfbam_stats* stats,
+                               char* err, size_t errlen) {
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (out) memset(out, 0, sizeof *out);
+    return guarded(err, errlen, [&] {
+        const double t0 = now_ms();
+        const Reader& r = rd->r;
+        if (!job || !job->intervals || !job->gene_intervals || !out) throw Error(MBFBAM_ERR_ARG, "null argument");
+        int ndev_have = 0;
+        if (cudaGetDeviceCount(&ndev_have) != cudaSuccess || ndev_have == 0)
+            throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
+        const std::vector<int> devs = job_devices(job->devices, job->n_devices, job->device);
+        mbfbam_count_job j2 = *job;
+        j2.each_read_counts_once = 0;
+        CountTables T;
+        build_count_tables(r, &j2, T);
+        const int nsh = std::max(1, job->shard_count), sh = job->shard_index;
+        if (sh < 0 || sh >= nsh) throw Error(MBFBAM_ERR_ARG, "bad shard index/count");
+        const uint64_t prior = rd->fmap ? rd->fmap->jobs.fetch_add(1) : 0;
+        std::vector<QuantPart> parts(devs.size());
+        const int rt = default_read_threads(devs.size());
+        fan_out(devs.size(), [&](size_t k) {
+            quantify_on_device(rd, T, devs[k], sh * (int)devs.size() + (int)k, nsh * (int)devs.size(), rt, prior, parts[k]);
+        });
+        size_t n = 0;
+        mbfbam_stats st{};
+        for (const QuantPart& pt : parts) { n += pt.entries.size(); merge_stats(st, pt.st); }
+        out->gene = (uint32_t*)malloc((n + 1) * 4);
+        out->pos = (uint32_t*)malloc((n + 1) * 4);
+        out->count = (uint32_t*)malloc((n + 1) * 4);
+        out->bucket = (uint8_t*)malloc(n + 1);
+        out->scanned = (uint8_t*)calloc((size_t)job->intervals->n_contigs + 1, 1);
+        for (int c : T.slot_iv) out->scanned[c] = 1;
+        size_t k = 0;
+        for (const QuantPart& pt : parts)
+            for (const QuantEntry& e : pt.entries) {  // chunk-range shards never share a (gene, pos): plain concatenation
+                out->gene[k] = e.gene; out->pos[k] = e.pos; out->count[k] = e.count; out->bucket[k] = e.bucket;
+                k++;
+            }
+        out->n = k;
+        st.ms_total = now_ms() - t0;
+        if (stats) *stats = st;
+    });
+}
+
+void mbfbam_free_gene_pos_counts(mbfbam_gene_pos_counts* x) {
+    if (!x) return;
+    free(x->gene); free(x->pos); free(x->count); free(x->bucket); free(x->scanned);
+    memset(x, 0, sizeof *x);
+}
+
+int mbfbam_duplicate_distribution(mbfbam_reader* rd, const int32_t* devices, int32_t n_devices, int32_t shard_index,
+                                  int32_t shard_count, mbfbam_dup_hist* out, mbfbam_stats* stats, char* err, size_t errlen) {
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (out) memset(out, 0, sizeof *out);
+    return guarded(err, errlen, [&] {
+        const double t0 = now_ms();
+        const Reader& r = rd->r;
+        if (!out) throw Error(MBFBAM_ERR_ARG, "null argument");
+        int ndev_have = 0;
+        if (cudaGetDeviceCount(&ndev_have) != cudaSuccess || ndev_have == 0)
+            throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
+        const std::vector<int> devs = job_devices(devices, n_devices, 0);
+        std::vector<Chunk> chunks = make_chunks(r, nullptr);
+        std::vector<uint32_t> ref_chunk_off(r.names.size() + 1, 0);
+        for (const Chunk& c : chunks) ref_chunk_off[(size_t)c.tid + 1]++;
+        for (size_t i = 0; i < r.names.size(); i++) ref_chunk_off[i + 1] += ref_chunk_off[i];
+        const int nsh = std::max(1, shard_count), sh = shard_index;
+        if (sh < 0 || sh >= nsh) throw Error(MBFBAM_ERR_ARG, "bad shard index/count");
+        const uint64_t prior = rd->fmap ? rd->fmap->jobs.fetch_add(1) : 0;
+        std::vector<DupPart> parts(devs.size());
+        const int rt = default_read_threads(devs.size());
+        fan_out(devs.size(), [&](size_t k) {
+            dups_on_device(rd, chunks, ref_chunk_off, devs[k], sh * (int)devs.size() + (int)k, nsh * (int)devs.size(), rt, prior, parts[k]);
+        });
+        std::map<uint32_t, uint64_t> hist;  // duplicate_distribution.rs:8-14 add_hashmaps
+        mbfbam_stats st{};
+        for (const DupPart& pt : parts) {
+            for (uint32_t k = 0; k < DUP_DENSE; k++) if (pt.dense[k]) hist[k] += pt.dense[k];
+            for (unsigned long long k : pt.big) hist[(uint32_t)k] += 1;
+            merge_stats(st, pt.st);
+        }
+        out->n = hist.size();
+        out->k = (uint32_t*)malloc((hist.size() + 1) * 4);
+        out->count = (uint64_t*)malloc((hist.size() + 1) * 8);
+        size_t i = 0;
+        for (const auto& kv : hist) { out->k[i] = kv.first; out->count[i] = kv.second; i++; }
+        st.ms_total = now_ms() - t0;
+        if (stats) *stats = st;
+    });
+}
+
+void mbfbam_free_dup_hist(mbfbam_dup_hist* x) {
+    if (!x) return;
+    free(x->k); free(x->count);
+    memset(x, 0, sizeof *x);
 }
 
 void mbfbam_free_introns(mbfbam_introns* x) {

@@ -8,9 +8,12 @@
 //   count_reads_stranded     src/lib.rs:161-181 + counters.rs:262-273,309-314
 //   count_introns            src/lib.rs:216-225
 //   count_reads_weighted     not in the reference
+//   quantify_gene_reads      src/lib.rs:247-264 + quantify.rs:20-75
+//   calculate_duplicate_distribution   src/lib.rs:108-116
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -490,6 +493,123 @@ struct PyReader {
         return out;
     }
 
+    // quantify.rs:20-75: (congruent, incongruent) {gene_id: [(pos, count)]}.  Every gene of a scanned contig gets a
+    // list (to_hashmap, quantify.rs:148-157: within one contig the LAST gene_no of a duplicated id wins); equal ids
+    // on different contigs are merged and a (gene_id, pos) seen twice is the reference's "still not disjoint" panic
+    // (quantify.rs:189-203) -> ValueError.  Lists are sorted by position (HashMap order in the reference).
+    py::tuple quantify_gene_reads(const py::dict& intervals, const py::dict& gene_intervals) {
+        Flat iv, gv;
+        flatten(intervals, iv);
+        flatten(gene_intervals, gv);
+        mbfbam_count_job job{};
+        job.intervals = &iv.c;
+        job.gene_intervals = &gv.c;
+        job.mode = MBFBAM_MODE_STRANDED;
+        job.device = devices[0];
+        job.n_devices = (int32_t)devices.size();
+        job.devices = devices.data();
+        job.shard_index = shard_index;
+        job.shard_count = shard_count;
+        mbfbam_gene_pos_counts res{};
+        char err[512] = {0};
+        int rc;
+        {
+            py::gil_scoped_release rel;
+            rc = mbfbam_quantify_gene_reads(r, &job, &res, &last, err, sizeof err);
+        }
+        if (rc) {
+            mbfbam_free_gene_pos_counts(&res);
+            value_error(err);
+        }
+        size_t G = 0;
+        for (uint32_t n : iv.n_genes) G += n;
+        // entries grouped by (bucket, gene), sorted by position
+        std::vector<uint64_t> order(res.n);
+        for (uint64_t i = 0; i < res.n; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+            if (res.bucket[a] != res.bucket[b]) return res.bucket[a] < res.bucket[b];
+            if (res.gene[a] != res.gene[b]) return res.gene[a] < res.gene[b];
+            return res.pos[a] < res.pos[b];
+        });
+        std::vector<uint64_t> first[2];
+        first[0].assign(G + 1, 0);
+        first[1].assign(G + 1, 0);
+        for (uint64_t i = 0; i < res.n; i++)
+            if (res.gene[i] < G) first[res.bucket[i] & 1][res.gene[i] + 1]++;
+        uint64_t n0 = 0;
+        for (size_t g = 0; g < G; g++) n0 += first[0][g + 1];
+        for (int b = 0; b < 2; b++) {
+            first[b][0] = b ? n0 : 0;
+            for (size_t g = 0; g < G; g++) first[b][g + 1] += first[b][g];
+        }
+        py::dict out[2];
+        bool fail = false;
+        for (int b = 0; b < 2 && !fail; b++) {
+            size_t base = 0;
+            for (size_t c = 0; c < iv.names.size() && !fail; c++) {
+                const auto& ids = iv.gene_ids[c];
+                if (res.scanned[c]) {
+                    py::dict last_of;  // id -> last gene_no of this contig
+                    for (size_t g = 0; g < ids.size(); g++) {
+                        PyObject* v = PyLong_FromSize_t(g);
+                        if (!v || PyDict_SetItem(last_of.ptr(), ids[g], v) != 0) {
+                            Py_XDECREF(v);
+                            mbfbam_free_gene_pos_counts(&res);
+                            throw py::error_already_set();
+                        }
+                        Py_DECREF(v);
+                    }
+                    PyObject *k, *v;
+                    Py_ssize_t pos = 0;
+                    while (PyDict_Next(last_of.ptr(), &pos, &k, &v)) {
+                        const size_t g = base + PyLong_AsSize_t(v);
+                        py::list lst;
+                        for (uint64_t i = first[b][g]; i < first[b][g + 1]; i++)
+                            lst.append(py::make_tuple(res.pos[order[i]], res.count[order[i]]));
+                        PyObject* old = PyDict_GetItemWithError(out[b].ptr(), k);
+                        if (old) {  // the same id on an earlier contig
+                            py::set seen;
+                            py::list ol = py::reinterpret_borrow<py::list>(old);
+                            for (auto t : ol) seen.add(t.cast<py::tuple>()[0]);
+                            for (auto t : lst) {
+                                if (seen.contains(t.cast<py::tuple>()[0])) fail = true;
+                                ol.append(t);
+                            }
+                            ol.attr("sort")();
+                        } else if (PyDict_SetItem(out[b].ptr(), k, lst.ptr()) != 0) {
+                            mbfbam_free_gene_pos_counts(&res);
+                            throw py::error_already_set();
+                        }
+                    }
+                }
+                base += ids.size();
+            }
+        }
+        mbfbam_free_gene_pos_counts(&res);
+        if (fail) value_error("still not disjoint");
+        return py::make_tuple(out[0], out[1]);
+    }
+
+    // duplicate_distribution.rs:44-86 -> {k: occurrences}
+    py::dict duplicate_distribution() {
+        mbfbam_dup_hist res{};
+        char err[512] = {0};
+        int rc;
+        {
+            py::gil_scoped_release rel;
+            rc = mbfbam_duplicate_distribution(r, devices.data(), (int32_t)devices.size(), shard_index, shard_count, &res, &last, err,
+                                               sizeof err);
+        }
+        if (rc) {
+            mbfbam_free_dup_hist(&res);
+            value_error(err);
+        }
+        py::dict out;
+        for (uint64_t i = 0; i < res.n; i++) out[py::int_(res.k[i])] = py::int_(res.count[i]);
+        mbfbam_free_dup_hist(&res);
+        return out;
+    }
+
     py::dict stats() const { return stats_dict(last); }
 };
 
@@ -538,6 +658,24 @@ PYBIND11_MODULE(mbf_bam, m) {
               return res;
           },
           py::arg("filename"), py::arg("index_filename") = py::none(), "python wrapper for py_count_introns (reference src/lib.rs:216)");
+    m.def("quantify_gene_reads",
+          [](const std::string& filename, py::object index_filename, const py::dict& intervals, const py::dict& gene_intervals) {
+              PyReader rd(filename, index_filename);
+              py::tuple res = rd.quantify_gene_reads(intervals, gene_intervals);
+              g_last_stats = rd.last;
+              return res;
+          },
+          py::arg("filename"), py::arg("index_filename"), py::arg("intervals"), py::arg("gene_intervals"),
+          "python wrapper for py_quantify_gene_reads (reference src/lib.rs:247)");
+    m.def("calculate_duplicate_distribution",
+          [](const std::string& filename, py::object index_filename) {
+              PyReader rd(filename, index_filename);
+              py::dict res = rd.duplicate_distribution();
+              g_last_stats = rd.last;
+              return res;
+          },
+          py::arg("filename"), py::arg("index_filename") = py::none(),
+          "python wrapper for py_calculate_duplicate_distribution (reference src/lib.rs:108)");
     m.def("last_stats", []() { return stats_dict(g_last_stats); }, "measurements of the most recent module-level call");
     m.def("device_count", []() { return mbfbam_device_count(); });
     m.def("release_device", [](int device) { mbfbam_release_device(device); }, py::arg("device") = 0,
@@ -603,5 +741,7 @@ PYBIND11_MODULE(mbf_bam, m) {
              py::arg("each_read_counts_once") = py::none())
         .def("assemble", &PyReader::assemble)
         .def("count_introns", &PyReader::count_introns)
+        .def("quantify_gene_reads", &PyReader::quantify_gene_reads, py::arg("intervals"), py::arg("gene_intervals"))
+        .def("calculate_duplicate_distribution", &PyReader::duplicate_distribution)
         .def("stats", &PyReader::stats);
 }

@@ -372,3 +372,175 @@ def count_introns(path, index_path=None):
             key = (U32, U32 - k)
             d[key] = d.get(key, 0) + 1
     return out
+
+
+def quantify_gene_reads(path, index_path, intervals, gene_intervals):
+    """reference src/lib.rs:247-264 -> src/count_reads/quantify.rs:20-75 (driver), :98-146 (per chunk).
+
+    ({gene_id: [(pos, n_reads_starting_there)]} congruent with the gene's strand, same for incongruent).
+    No NH logic, any flag; one alignment counts once per gene (quantify.rs:121-125).  Every gene of a scanned
+    contig gets a (possibly empty) list (to_hashmap, quantify.rs:148-157: a duplicated id within one contig keeps
+    the LAST gene_no).  The order inside a list is HashMap order in the reference; sorted by position here.
+    add_hashmaps (quantify.rs:189-203) panics on a (gene_id, pos) seen twice, which only equal ids on two
+    contigs can cause: ValueError here.  PARITY UNPINNED (no test in the reference)."""
+    hdr, recs = read_bam(path)
+    name2tid = {n: i for i, (n, _) in enumerate(hdr.refs)}
+    trees = {c: build_intervals(l) for c, l in intervals.items()}
+    gene_trees = {c: build_intervals(l) for c, l in gene_intervals.items()}
+    contigs = [(c, name2tid[c], hdr.refs[name2tid[c]][1]) for c in gene_trees if c in name2tid]
+    for c, _, _ in contigs:
+        if c not in trees:
+            raise ValueError("contig %r is in gene_intervals but not in intervals" % c)
+    chunks = make_chunks(contigs, {c: gene_trees[c][0] for c, _, _ in contigs})
+    by_tid = defaultdict(list)
+    for r in recs:
+        by_tid[r.tid].append(r)
+    out = ({}, {})
+    for chr_, tid, start, stop in chunks:
+        ivs, gene_ids = trees[chr_]
+        res = ([dict() for _ in gene_ids], [dict() for _ in gene_ids])
+        for r in by_tid.get(tid, ()):
+            upos = r.pos & U32
+            if upos < start or upos >= stop:          # quantify.rs:113
+                continue
+            seen = set()
+            for b0, b1 in cigar_blocks(r.pos, r.cigar):
+                for (s, e, gene_no, strand) in find(ivs, b0, b1):
+                    if gene_no in seen:
+                        continue
+                    seen.add(gene_no)
+                    rv = bool(r.flag & 0x10)
+                    congruent = (strand == 1 and not rv) or (strand != 1 and rv)   # quantify.rs:126-127
+                    d = res[0 if congruent else 1][gene_no]
+                    d[upos] = d.get(upos, 0) + 1
+        for b in (0, 1):
+            per_chunk = {}
+            for g, d in enumerate(res[b]):
+                per_chunk[gene_ids[g]] = d            # collect(): the last duplicate id wins
+            for gid, d in per_chunk.items():
+                tgt = out[b].setdefault(gid, {})
+                for pos, n in d.items():
+                    if pos in tgt:
+                        raise ValueError("still not disjoint")
+                    tgt[pos] = n
+    return tuple({gid: sorted(d.items()) for gid, d in o.items()} for o in out)
+
+
+def calculate_duplicate_distribution(path, index_path=None):
+    """reference src/lib.rs:108-116 -> src/duplicate_distribution.rs:44-86.
+
+    {k: number of distinct (contig, pos, is_reverse, SEQ) that occur exactly k times}.  The reference walks
+    fetch(tid, 0, target_len) of every contig and closes a group whenever `pos` changes (:63-71); in a coordinate
+    sorted file that equals grouping by (tid, pos).  seq().as_bytes() decodes l_seq bases, so the unused low
+    nibble of an odd-length SEQ is not part of the key.  PARITY UNPINNED."""
+    hdr, recs = read_bam(path)
+    groups = defaultdict(int)
+    for r in recs:
+        if r.tid < 0 or r.tid >= len(hdr.refs):
+            continue
+        if r.pos < 0 or r.pos >= hdr.refs[r.tid][1]:      # not returned by fetch(tid, 0, len)
+            continue
+        seq = r.seq if r.seq is not None else bytes((r.l_seq + 1) // 2)
+        if r.l_seq & 1:
+            seq = seq[:-1] + bytes([seq[-1] & 0xF0])
+        groups[(r.tid, r.pos, bool(r.flag & 0x10), r.l_seq, seq)] += 1
+    out = defaultdict(int)
+    for v in groups.values():
+        out[v] += 1
+    return dict(out)
+
+
+def aux_get_str(aux, tag):
+    """(found, bytes or None if the tag is not of type Z) -- rust-htslib Aux::String."""
+    import struct
+    p = 0
+    sizes = {b"A": 1, b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4, b"d": 8}
+    while p + 3 <= len(aux):
+        t = aux[p:p + 2]
+        ty = aux[p + 2:p + 3]
+        p += 3
+        if ty in (b"Z", b"H"):
+            e = aux.index(b"\0", p)
+            if t == tag:
+                return True, (aux[p:e] if ty == b"Z" else None)
+            p = e + 1
+        elif ty == b"B":
+            sub = aux[p:p + 1]
+            cnt = struct.unpack_from("<i", aux, p + 1)[0]
+            if t == tag:
+                return True, None
+            p += 5 + cnt * sizes[sub]
+        else:
+            if t == tag:
+                return True, None
+            p += sizes[ty]
+    return False, None
+
+
+def count_reads_primary_only_right_strand_only_by_barcode(path, index_path, intervals, gene_intervals,
+                                                          umi_strategy="straight"):
+    """reference src/lib.rs:184-211 -> src/count_reads/by_barcode.rs:18-92 (driver), :101-182 (per chunk).
+
+    (genes, barcodes, [(gene_idx, barcode_idx, count)]): per chunk and (gene_no, XC barcode) the number of
+    distinct XM UMIs summed over (pos, is_reverse) (:164-176), only reads that are not secondary and lie on the
+    gene's strand.  A chunk in which a right-strand hit lacks a string XC/XM tag returns Err and contributes
+    NOTHING (:46-68 `_ => {}`).  Index assignment and entry order follow HashMap iteration in the reference, i.e.
+    are arbitrary: here chunks in order, then (gene_no, barcode) sorted.  PARITY UNPINNED."""
+    if umi_strategy != "straight":
+        raise ValueError("invalid umi_strategy")
+    hdr, recs = read_bam(path)
+    name2tid = {n: i for i, (n, _) in enumerate(hdr.refs)}
+    trees = {c: build_intervals(l) for c, l in intervals.items()}
+    gene_trees = {c: build_intervals(l) for c, l in gene_intervals.items()}
+    contigs = [(c, name2tid[c], hdr.refs[name2tid[c]][1]) for c in gene_trees if c in name2tid]
+    for c, _, _ in contigs:
+        if c not in trees:
+            raise ValueError("contig %r is in gene_intervals but not in intervals" % c)
+    chunks = make_chunks(contigs, {c: gene_trees[c][0] for c, _, _ in contigs})
+    by_tid = defaultdict(list)
+    for r in recs:
+        by_tid[r.tid].append(r)
+    flat = []
+    for chr_, tid, start, stop in chunks:
+        ivs, gene_ids = trees[chr_]
+        positions = defaultdict(set)
+        failed = False
+        for r in by_tid.get(tid, ()):
+            upos = r.pos & U32
+            skipped = upos < start or upos >= stop
+            if r.flag & 0x100:                       # by_barcode.rs:127
+                continue
+            if skipped:
+                continue
+            rv = bool(r.flag & 0x10)
+            for b0, b1 in cigar_blocks(r.pos, r.cigar):
+                if b1 < start or b0 >= stop or (b0 < start and b1 >= start):   # by_barcode.rs:131
+                    continue
+                for (s, e, gene_no, strand) in find(ivs, b0, b1):
+                    if (strand == 1 and not rv) or (strand != 1 and rv):
+                        okc, bc = aux_get_str(r.aux, b"XC")
+                        if not okc or bc is None:
+                            failed = True
+                            break
+                        oku, umi = aux_get_str(r.aux, b"XM")
+                        if not oku or umi is None:
+                            failed = True
+                            break
+                        positions[(gene_no, bc, r.pos, rv)].add(umi)
+                if failed:
+                    break
+            if failed:
+                break
+        if failed:
+            continue
+        by_gb = defaultdict(int)
+        for (gene_no, bc, _p, _r), umis in positions.items():
+            by_gb[(gene_no, bc)] += len(umis)
+        for (gene_no, bc), n in sorted(by_gb.items()):
+            flat.append((gene_ids[gene_no], bc.decode(), n))
+    genes, barcodes, counts = {}, {}, []
+    for g, b, n in flat:
+        gi = genes.setdefault(g, len(genes))
+        bi = barcodes.setdefault(b, len(barcodes))
+        counts.append((gi, bi, n))
+    return list(genes), list(barcodes), counts
