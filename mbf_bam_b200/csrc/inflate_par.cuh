@@ -14,11 +14,19 @@
 //           the distance table (two-level: 9 / 8 root bits, second-level tables for longer codes -- a long code
 //           costs one more shared load instead of the canonical search's ~100 instructions)
 //   guess   lane i decodes from the first bit of sub-sequence i (lane 0 from the true start) until it has crossed
-//           into sub-sequence i+1 and publishes where it stopped
-//   sync    every lane whose predecessor stopped somewhere else restarts there; repeated until nobody moves.
+//           into sub-sequence i+1.  It keeps what it decodes: the tokens go to a lane-private scratch area in HBM
+//           (L2 resident), and every bit position where a token started is MARKED in a bitmap that parallels the
+//           staged words; it publishes where it stopped
+//   sync    every lane whose predecessor stopped somewhere else restarts there -- but only until it steps onto a
+//           marked position: from there on its path IS the guess path (a decoder's state is its bit position), so
+//           the guess run's tokens and exit are reused.  Measured on the bench files (sub-sequences of 1312 bits,
+//           122 tokens): the true chain meets the guess path after 10 tokens on average, 97 % within 12 words, and
+//           0.09 % of the lanes never do (they decode to the end of their stretch).  Repeated until nobody moves.
 //           Converged <=> every lane started where its predecessor stopped <=> the chain is the true one
 //           (induction from lane 0), whatever the data: speculation is verified, never trusted
-//   emit    token counts -> exclusive scan -> every lane decodes its sub-sequence once more and writes its tokens
+//   emit    token counts -> exclusive scan -> every lane copies [its sync run's tokens][the guess run's tokens from
+//           the merge point on] to the member's token list.  A token is decoded once (plus the short sync runs);
+//           the first form of this kernel decoded everything three times (guess, sync, emit)
 //
 // Stored blocks, members whose tables overflow the second-level pool, and anything that looks corrupt are
 // appended to a fallback list and decoded by k_tokens_bf, which also produces the precise error codes.
@@ -38,21 +46,26 @@ constexpr uint32_t E3_BAD = K_SPECIAL | E2_LINK;  // "no such code": a link to p
 constexpr uint32_t E3_TERM = K_SPECIAL;           // terminal: kind 3, consumes nothing
 constexpr uint32_t E2_LINKTMP = 0xF0000000u;    // during the build: | second-level bits so far (atomicMax; > E3_BAD)
 constexpr uint32_t PF_EOB = 1u << 31, PF_INV = 1u << 30, PF_DEAD = 1u << 29;  // flags beside a bit position
+constexpr uint32_t PF_MERGED = 1u << 28;  // (sync run only, never published) stopped on a marked position
 constexpr uint32_t PF_ANY = PF_EOB | PF_INV | PF_DEAD;
 constexpr int PT_SW_MIN = 5;        // shortest sub-sequence in words
+// tokens one run may keep: 2 bits per token over the longest sub-sequence (a match costs at least 2); a run that
+// would need more is reported as invalid and the member goes to the fallback kernel
+__host__ __device__ constexpr uint32_t par_scratch_cap(int sw_max) { return (uint32_t)sw_max * 16u; }
 
-template <int NT, int SW_MAX>
+template <int NT, int SW_MAX, bool ONEPASS = false>
 struct ParShared {
     uint32_t ll[1 << PT_ROOT_LL];
     uint32_t d[1 << PT_ROOT_D];
     uint32_t sub[PT_SUB_CAP];        // during header parsing: scratch of the code-length code
     uint32_t zero;                   // the "distance entry" of a literal: consumes nothing
     uint32_t cb[NT * SW_MAX + 16];   // staged compressed words
+    uint32_t mk[ONEPASS ? NT * SW_MAX + 16 : 1];  // bit b of mk[w]: the guess run of the lane owning word w started a token at bit b of cb[w]
     uint32_t exitb[NT + 1];          // exitb[i+1]: where lane i stopped | flags; exitb[0]: the true start
     uint32_t wsum[NT / 32];
     uint32_t run[2][16], first[2][16];
     uint16_t rev[320];               // bit-reversed code of every symbol (table build)
-    uint8_t lens[320];
+    alignas(4) uint8_t lens[320];
     uint32_t sub_alloc, first_flag;
     int bad;
     uint32_t hdr_bfinal, hdr_hlit, hdr_hdist, hdr_data_bp;
@@ -60,10 +73,22 @@ struct ParShared {
     uint32_t member;
 };
 
+// What k_par_headers found at the start of a member.
+struct ParHdr {
+    uint32_t data_bp;   // first bit of the block's data, relative to the member's first byte
+    uint16_t hlit;
+    uint8_t hdist;
+    uint8_t flags;      // bit 0: BFINAL; bit 1: the code lengths are in hdr_lens (else: parse in k_tokens_par)
+};
+constexpr uint32_t PAR_HDR_STRIDE = 320;
+
 struct ParArgs {
     TokenArgs t;
     uint32_t* fb_list;   // members for the fallback kernel
     uint32_t* fb_count;
+    uint32_t* scratch;   // gridDim.x * NT * 2 * par_scratch_cap(SW_MAX) token slots: per lane [guess run][sync run]
+    const ParHdr* hdr;          // per member: the first block header, parsed by k_par_headers
+    const uint8_t* hdr_lens;    // per member PAR_HDR_STRIDE bytes: literal/length code lengths, then the distance ones
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -180,8 +205,8 @@ struct SmemBits {
 
 // One deflate block header at bit position `bp` (member-relative; staged from word cw0).  Thread 0.
 // hdr_err != 0: stored block, bad header, or a header that leaves the staged words -> fallback kernel.
-template <int NT, int SW_MAX>
-__device__ void par_parse_header(ParShared<NT, SW_MAX>& S, uint32_t s_cb, uint32_t bp, uint32_t cw0, uint32_t staged_words,
+template <class PS>
+__device__ void par_parse_header(PS& S, uint32_t s_cb, uint32_t bp, uint32_t cw0, uint32_t staged_words,
                                  uint32_t member_bits) {
     SmemBits br;
     br.init(s_cb, bp - cw0 * 32u, min((staged_words - 2u) * 32u, member_bits - cw0 * 32u));
@@ -264,21 +289,44 @@ __device__ __forceinline__ uint32_t lds_if_special(uint32_t e, uint32_t addr) {
     return e;
 }
 
-template <bool EMIT>
-__device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t cw0_bits, uint32_t s_ll, uint32_t s_d, uint32_t s_sub,
-                                            uint32_t s_zero, uint32_t start_bp, uint32_t end_bp, uint32_t& n_out, uint32_t* tk) {
+// MODE PR_COUNT   decode and count (three-decode scheme: guess and sync runs)
+//      PR_EMIT    decode and write the tokens to tk[0], tk[1], ... (three-decode scheme: emit run)
+//      PR_GUESS   single-decode scheme, guess run: marks the bit position of every token it starts (s_mk parallels
+//                 s_cb) and keeps token k in tk[32 k] (a warp's lanes all write row k in trip k: one 128-byte line)
+//      PR_SYNC    single-decode scheme, sync run: as PR_GUESS without marking, but stops, without decoding, on the
+//                 first marked position (result | PF_MERGED; n_out = tokens before it)
+// A keeping run that fills `cap` token slots ends as invalid.
+enum { PR_COUNT = 0, PR_EMIT = 1, PR_GUESS = 2, PR_SYNC = 3 };
+template <int MODE>
+__device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t s_mk, uint32_t cw0_bits, uint32_t s_ll, uint32_t s_d,
+                                            uint32_t s_sub, uint32_t s_zero, uint32_t start_bp, uint32_t end_bp, uint32_t cap,
+                                            uint32_t& n_out, uint32_t* tk) {
+    constexpr bool KEEP = MODE == PR_GUESS || MODE == PR_SYNC;
+    constexpr uint32_t TK_STEP = KEEP ? 32u : 1u;
     uint32_t pos = start_bp - cw0_bits;  // bits from the first staged word
     uint32_t lim = end_bp - cw0_bits;    // set to 0 to leave the loop
     uint32_t a = s_cb + ((pos >> 5) << 2);
     uint32_t lo = lds_u32(a), hi = lds_u32(a + 4), nx = lds_u32(a + 8);
     a += 12;
     uint32_t n = 0, flags = 0;
+    uint32_t mk_word = 0xffffffffu, mk_acc = 0;  // PR_GUESS: the mark word being filled
     // One trip = one token, one straight-line instruction sequence whatever the token is: literal/length
     // lookup, second-level lookup (predicated load), distance lookup (a literal reads a zero word), second-level
     // lookup, predicated token store, window advance.  End of block and invalid codes are table entries of their
-    // own (kind bit 31 set): they end the loop through `lim`, not through a branch.
+    // own (kind bit 31 set): they end the loop through `lim`, not through a branch; so does a marked position.
     while (pos < lim) {
         const uint32_t bo = pos & 31u;
+        bool hit = false;
+        if (MODE == PR_SYNC) {
+            hit = ((lds_u32(s_mk + ((pos >> 5) << 2)) >> bo) & 1u) != 0;  // (needed only at the end of the trip)
+        } else if (MODE == PR_GUESS) {
+            // plain store of the word as far as it is known (the lane owns it; skipped words stay zero): shared
+            // atomics queue in front of the table lookups
+            const uint32_t wi = pos >> 5;
+            mk_acc = (wi == mk_word ? mk_acc : 0u) | (1u << bo);
+            mk_word = wi;
+            sts_u32(s_mk + (wi << 2), mk_acc);
+        }
         const uint32_t w = __funnelshift_r(lo, hi, bo);
         uint32_t e = lds_u32(s_ll + ((w & ((1u << PT_ROOT_LL) - 1u)) << 2));
         e = lds_if_special(e, s_sub + ((((e >> 10) & 0x3ffu) + ((w >> PT_ROOT_LL) & ~(0xffffffffu << ((e >> 5) & 15u)))) << 2));
@@ -290,18 +338,20 @@ __device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t cw0_bits, ui
         uint32_t d = lds_u32(m ? s_d + ((w2 & ((1u << PT_ROOT_D) - 1u)) << 2) : s_zero);
         d = lds_if_special(d, s_sub + ((((d >> 10) & 0x3ffu) + ((w2 >> PT_ROOT_D) & ~(0xffffffffu << ((d >> 5) & 15u)))) << 2));
         const uint32_t c2 = d & 31u;
-        const bool stop = (int32_t)(e | d) < 0;  // end of block (kind 2), no such code (kind 3: consumes nothing)
-        if (EMIT) {
+        const bool end = (int32_t)(e | d) < 0;  // end of block (kind 2), no such code (kind 3: consumes nothing)
+        const bool stop = end || hit;
+        if (MODE != PR_COUNT) {
             const uint32_t val = ((e >> 10) & 0xffffu) + ((w & ~(0xffffffffu << c1)) >> ((e >> 5) & 15u));
             const uint32_t dist = ((d >> 10) & 0xffffu) + ((w2 & ~(0xffffffffu << c2)) >> ((d >> 5) & 15u));
             if (!stop) __stcg(tk, m ? (0x80000000u | (val << 16) | ((dist - 1u) & 0x7fffu)) : val);
-            tk += stop ? 0 : 1;
+            tk += stop ? 0u : TK_STEP;
         }
         n += stop ? 0u : 1u;
-        flags = stop ? (((e | d) & (1u << 30)) ? PF_INV : PF_EOB) : flags;
-        lim = stop ? 0u : lim;
+        const bool full = KEEP && n >= cap;
+        flags = hit ? PF_MERGED : (end ? (((e | d) & (1u << 30)) ? PF_INV : PF_EOB) : (full ? PF_INV : flags));
+        lim = (stop || full) ? 0u : lim;
         const uint32_t adv = bo1 + c2;  // <= 79
-        pos += c1 + c2;
+        pos += hit ? 0u : c1 + c2;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "setp.ge.u32 p, %4, 32;\n\t"
@@ -317,16 +367,156 @@ __device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t cw0_bits, ui
     return (cw0_bits + pos) | flags;
 }
 
+// Single-decode scheme, emit: the warp moves its 32 lanes' tokens from the transposed scratch (token k of lane j at
+// [32 k + j]) to the lanes' places in the member's token list, 32 x 32 tokens at a time through a shared tile, so
+// that both the loads and the stores are whole lines.  Lane j contributes rows [from, to) of `src`, written to
+// dst[0 .. to - from).  `tile`: 32 x 33 words of shared memory owned by the warp.
+__device__ __forceinline__ void par_copy_warp(uint32_t* tile, const uint32_t* src, uint32_t from, uint32_t to, uint32_t* dst,
+                                              int lane) {
+    const uint32_t lo_row = __reduce_min_sync(0xffffffffu, from < to ? from : 0xffffffffu);
+    const uint32_t hi_row = __reduce_max_sync(0xffffffffu, from < to ? to : 0u);
+    for (uint32_t r0 = lo_row; r0 < hi_row; r0 += 32) {
+        __syncwarp();
+        const uint32_t rows = min(32u, hi_row - r0);
+        for (uint32_t r = 0; r < rows; r++) tile[r * 33 + lane] = __ldcg(src + (size_t)(r0 + r) * 32 + lane);
+        __syncwarp();
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            const uint32_t fj = __shfl_sync(0xffffffffu, from, j), tj = __shfl_sync(0xffffffffu, to, j);
+            const unsigned long long dj = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)dst, j);
+            const uint32_t row = r0 + lane;  // lane k handles row r0 + k of column j
+            if (row >= fj && row < tj) __stcg(reinterpret_cast<uint32_t*>((uintptr_t)dj) + (row - fj), tile[lane * 33 + j]);
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
-template <int NT, int SW_MAX>
+// Header pre-pass: ONE THREAD per member reads the first block header (BTYPE 1 or 2) and leaves the ~300 code
+// lengths in HBM.  The code-length stream is a serial chain of ~100 Huffman symbols; inside k_tokens_par it kept
+// one thread busy and 127 waiting for a quarter of the kernel's time.  Here 32 members advance per warp
+// instruction and nobody waits.  Anything irregular (stored block, over-subscribed or incomplete code-length
+// code, lengths running past their count, a header longer than the member) is left to k_tokens_par's own parser,
+// which decides between decoding, the fallback kernel and an error -- this kernel never reports one.
+constexpr int PAR_HDR_THREADS = 64;
+__global__ void __launch_bounds__(PAR_HDR_THREADS) k_par_headers(TokenArgs a, ParHdr* hdr, uint8_t* hdr_lens) {
+    __shared__ uint8_t cl_lut_s[PAR_HDR_THREADS][128];  // (symbol << 3 | length) of the code-length code; 0 = no code
+    const uint32_t b = blockIdx.x * PAR_HDR_THREADS + threadIdx.x;
+    if (b >= *a.n_blocks) return;
+    uint8_t* const lut = cl_lut_s[threadIdx.x];
+    const uint8_t* p = a.cbuf + a.cpos[b];
+    const uint32_t clen = a.clen[b];
+    const uint32_t mis = (uint32_t)((uintptr_t)p & 3u);
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(p - mis);
+    const uint32_t limit = (mis + clen) * 8u;  // bits (word relative) that belong to the member
+    ParHdr h;
+    h.data_bp = 0; h.hlit = 0; h.hdist = 0; h.flags = 0;
+    uint32_t rel = mis * 8u, cur = 0xffffffffu, lo = 0, hi = 0;
+    auto peek = [&]() {
+        const uint32_t wi = rel >> 5;
+        if (wi != cur) { lo = __ldg(words + wi); hi = __ldg(words + wi + 1); cur = wi; }  // (the trailer follows the data)
+        return __funnelshift_r(lo, hi, rel & 31u);
+    };
+    auto take = [&](uint32_t n) { const uint32_t v = peek() & ((1u << n) - 1u); rel += n; return v; };
+    uint32_t* const out = reinterpret_cast<uint32_t*>(hdr_lens + (size_t)b * PAR_HDR_STRIDE);
+    bool ok = false;
+    const uint32_t bfinal = take(1), btype = take(2);
+    if (btype == 1u) {
+        for (int i = 0; i < 36; i++) out[i] = 0x08080808u;
+        for (int i = 36; i < 64; i++) out[i] = 0x09090909u;
+        for (int i = 64; i < 70; i++) out[i] = 0x07070707u;
+        for (int i = 70; i < 72; i++) out[i] = 0x08080808u;
+        for (int i = 72; i < 80; i++) out[i] = 0x05050505u;
+        h.hlit = 288; h.hdist = 32;
+        ok = true;
+    } else if (btype == 2u) {
+        const uint32_t hlit = take(5) + 257u, hdist = take(5) + 1u, hclen = take(4) + 4u;
+        uint32_t cl_lo = 0, cl_hi = 0;  // 19 lengths of 3 bits: symbol s at bits 3s (lo: 0..9, hi: 10..18)
+        for (uint32_t i = 0; i < hclen; i++) {
+            const uint32_t sy = MBF_TBL(CL_ORDER, i), v = take(3);
+            if (sy < 10u) cl_lo |= v << (3u * sy); else cl_hi |= v << (3u * (sy - 10u));
+        }
+        auto cl_of = [&](uint32_t sy) { return sy < 10u ? (cl_lo >> (3u * sy)) & 7u : (cl_hi >> (3u * (sy - 10u))) & 7u; };
+        uint32_t kraft = 0;
+        for (uint32_t sy = 0; sy < 19u; sy++) { const uint32_t l = cl_of(sy); if (l) kraft += 128u >> l; }
+        ok = hlit <= 286u && hdist <= 30u && kraft == 128u;  // a complete code only
+        if (ok) {
+            uint32_t code = 0;
+            for (uint32_t l = 1; l <= 7u; l++) {  // canonical codes in order of (length, symbol)
+                for (uint32_t sy = 0; sy < 19u; sy++) {
+                    if (cl_of(sy) != l) continue;
+                    const uint32_t r = __brev(code) >> (32u - l);
+                    for (uint32_t k = r; k < 128u; k += 1u << l) lut[k] = (uint8_t)((sy << 3) | l);
+                    code++;
+                }
+                code <<= 1;
+            }
+            const uint32_t nn = hlit + hdist;
+            uint32_t i = 0, prev = 0, acc = 0;
+            auto put = [&](uint32_t v) {
+                acc |= v << (8u * (i & 3u));
+                if ((i & 3u) == 3u) { out[i >> 2] = acc; acc = 0; }
+                i++;
+            };
+            uint32_t len256 = 0;
+            while (i < nn && ok) {
+                const uint32_t w = peek();
+                const uint32_t e = lut[w & 127u];
+                const uint32_t cb = e & 7u, s2 = e >> 3;
+                if (s2 < 16u) {
+                    rel += cb;
+                    if (i == 256u) len256 = s2;
+                    put(s2);
+                    prev = s2;
+                } else {
+                    uint32_t rep, val = 0;
+                    if (s2 == 16u) {
+                        if (i == 0) { ok = false; break; }
+                        val = prev;
+                        rep = 3u + ((w >> cb) & 3u);
+                        rel += cb + 2u;
+                    } else if (s2 == 17u) {
+                        rep = 3u + ((w >> cb) & 7u);
+                        rel += cb + 3u;
+                    } else {
+                        rep = 11u + ((w >> cb) & 127u);
+                        rel += cb + 7u;
+                    }
+                    if (i + rep > nn) { ok = false; break; }
+                    if (i <= 256u && 256u < i + rep) len256 = val;
+                    for (uint32_t k = 0; k < rep; k++) put(val);
+                    prev = val;
+                }
+                if (rel > limit) ok = false;
+            }
+            if (ok && (i & 3u)) out[i >> 2] = acc;
+            if (len256 == 0) ok = false;  // no end-of-block code
+            h.hlit = (uint16_t)hlit; h.hdist = (uint8_t)hdist;
+        }
+    }
+    if (rel > limit) ok = false;
+    h.data_bp = rel - mis * 8u;
+    h.flags = (uint8_t)((bfinal ? 1u : 0u) | (ok ? 2u : 0u));
+    hdr[b] = h;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int NT, int SW_MAX, bool ONEPASS>
 __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
     extern __shared__ __align__(16) uint8_t par_smem[];
-    ParShared<NT, SW_MAX>& S = *reinterpret_cast<ParShared<NT, SW_MAX>*>(par_smem);
+    typedef ParShared<NT, SW_MAX, ONEPASS> PS;
+    PS& S = *reinterpret_cast<PS*>(par_smem);
+    static_assert(!ONEPASS || 2 * (NT * SW_MAX + 16) >= (NT / 32) * 32 * 33, "the staged-word and mark areas double as the copy tiles");
+    static_assert(offsetof(PS, mk) == offsetof(PS, cb) + sizeof(uint32_t) * (NT * SW_MAX + 16), "cb and mk are one contiguous area");
     constexpr uint32_t CB_WORDS = NT * SW_MAX + 16;
     const TokenArgs& a = pa.t;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const uint32_t s_cb = smem_addr(S.cb), s_ll = smem_addr(S.ll), s_d = smem_addr(S.d), s_sub = smem_addr(S.sub),
+    const uint32_t s_cb = smem_addr(S.cb), s_mk = smem_addr(S.mk), s_ll = smem_addr(S.ll), s_d = smem_addr(S.d), s_sub = smem_addr(S.sub),
                    s_zero = smem_addr(&S.zero);
+    constexpr uint32_t CAP = par_scratch_cap(SW_MAX);
+    // transposed token scratch of the warp: [guess run | latest sync run][CAP rows][32 lanes]
+    uint32_t* const g_tok = pa.scratch + ((size_t)blockIdx.x * (NT / 32) + wid) * 2 * CAP * 32;
+    uint32_t* const s_tok = g_tok + (size_t)CAP * 32;
     const uint32_t n_blocks = *a.n_blocks;
     unsigned long long my_tokens = 0;
 
@@ -352,9 +542,21 @@ __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
             __syncthreads();  // the previous block's emit pass has read the staged words
             uint32_t cw0 = bp >> 5;
             uint32_t staged = min(CB_WORDS, nwords + 2u - min(cw0, nwords + 2u));
-            for (uint32_t i = t; i < CB_WORDS; i += NT) S.cb[i] = i < staged ? __ldg(words + cw0 + i) : 0u;
+            for (uint32_t i = t; i < CB_WORDS; i += NT) { S.cb[i] = i < staged ? __ldg(words + cw0 + i) : 0u; if (ONEPASS) S.mk[i] = 0u; }
             __syncthreads();
-            if (t == 0) par_parse_header<NT, SW_MAX>(S, s_cb, bp, cw0, max(staged, 3u), member_bits);
+            const ParHdr ph = pa.hdr[b];
+            if (bp == mis * 8u && (ph.flags & 2u)) {  // the member's first header was parsed by k_par_headers
+                const uint32_t nn4 = ((uint32_t)ph.hlit + ph.hdist + 3u) >> 2;
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(pa.hdr_lens + (size_t)b * PAR_HDR_STRIDE);
+                for (uint32_t i = t; i < nn4; i += NT) reinterpret_cast<uint32_t*>(S.lens)[i] = __ldg(src + i);
+                if (t == 0) {
+                    S.hdr_err = 0; S.sub_alloc = 1; S.bad = 0; S.zero = 0;
+                    S.hdr_bfinal = ph.flags & 1u; S.hdr_hlit = ph.hlit; S.hdr_hdist = ph.hdist;
+                    S.hdr_data_bp = mis * 8u + ph.data_bp;
+                }
+            } else if (t == 0) {
+                par_parse_header(S, s_cb, bp, cw0, max(staged, 3u), member_bits);
+            }
             __syncthreads();
             if (S.hdr_err) { fallback = true; break; }
             const uint32_t bfinal = S.hdr_bfinal, hlit = S.hdr_hlit, hdist = S.hdr_hdist;
@@ -374,12 +576,14 @@ __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
             // ---------------------------------------------------------------- waves of NT sub-sequences
             bool eob = false;
             bool first_wave = true;
+            uint32_t waves = 0;
             while (!eob) {
+                if (++waves > 4096u) { fallback = true; break; }  // (every wave consumes at least one word: a guard, as below)
                 if (!first_wave) {  // the first wave uses what was staged with the header
                     __syncthreads();
                     cw0 = bp >> 5;
                     staged = min(CB_WORDS, nwords + 2u - min(cw0, nwords + 2u));
-                    for (uint32_t i = t; i < CB_WORDS; i += NT) S.cb[i] = i < staged ? __ldg(words + cw0 + i) : 0u;
+                    for (uint32_t i = t; i < CB_WORDS; i += NT) { S.cb[i] = i < staged ? __ldg(words + cw0 + i) : 0u; if (ONEPASS) S.mk[i] = 0u; }
                     __syncthreads();
                 }
                 first_wave = false;
@@ -396,23 +600,53 @@ __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
                 uint32_t my_start = t == 0 ? bp : wave_base + (uint32_t)t * sw * 32u;
                 // (the last lane stops at the end of what is staged, not at the end of its nominal stretch)
                 const uint32_t my_end = wave_base + min((uint32_t)(t + 1) * sw, avail) * 32u;
-                uint32_t n = 0, res = PF_DEAD;
-                if (active) res = par_run<false>(s_cb, cw0_bits, s_ll, s_d, s_sub, s_zero, my_start, my_end, n, nullptr);
+                uint32_t cur_start = my_start;      // where the path this lane currently stands for begins
+                uint32_t n_g = 0, n_s = 0, g_from = 0;  // (single decode) tokens of the guess run; of the sync run; first guess token in use
+                uint32_t res_g = PF_DEAD, res = PF_DEAD;
+                uint32_t n = 0;
+                // ---- guess: every lane decodes its stretch from the first bit
+                if (ONEPASS) {  // ... keeps the tokens and marks the token starts
+                    if (active) res = res_g = par_run<PR_GUESS>(s_cb, s_mk, cw0_bits, s_ll, s_d, s_sub, s_zero, my_start, my_end, CAP, n_g, g_tok + lane);
+                } else {
+                    if (active) res = par_run<PR_COUNT>(s_cb, s_mk, cw0_bits, s_ll, s_d, s_sub, s_zero, my_start, my_end, 0, n, nullptr);
+                }
                 if (t == 0) { S.exitb[0] = bp; S.first_flag = NT; }
                 S.exitb[t + 1] = res;
                 __syncthreads();
-                // ---- synchronise: restart wherever the predecessor really stopped
+                // ---- synchronise: restart wherever the predecessor really stopped (single decode: only until the
+                // path meets the guess path).  Exits are functions of starts and lane 0 never moves, so this ends
+                // after at most NT rounds; the counter is a guard against a hang should that reasoning ever fail.
+                uint32_t rounds = 0;
                 for (;;) {
                     const uint32_t prev = S.exitb[t];
-                    const bool chg = active && !(prev & PF_ANY) && prev != my_start;
+                    const bool chg = active && !(prev & PF_ANY) && prev != cur_start;
                     if (!__syncthreads_or(chg)) break;
+                    if (++rounds > (uint32_t)NT + 2u) { fallback = true; break; }
                     if (chg) {
-                        my_start = prev;
-                        res = par_run<false>(s_cb, cw0_bits, s_ll, s_d, s_sub, s_zero, my_start, my_end, n, nullptr);
+                        cur_start = prev;
+                        if (ONEPASS) {
+                            const uint32_t r = par_run<PR_SYNC>(s_cb, s_mk, cw0_bits, s_ll, s_d, s_sub, s_zero, prev, my_end, CAP, n_s, s_tok + lane);
+                            if (r & PF_MERGED) {
+                                // guess tokens before the meeting point = marks of this lane below it
+                                const uint32_t mp = (r & ~(PF_ANY | PF_MERGED)) - cw0_bits;
+                                const uint32_t fw = (w0 - cw0) + (uint32_t)t * sw, mw = mp >> 5;
+                                uint32_t c = __popc(S.mk[mw] & ((1u << (mp & 31u)) - 1u));
+                                for (uint32_t k = fw; k < mw; k++) c += __popc(S.mk[k]);
+                                g_from = c;
+                                res = res_g;
+                            } else {
+                                g_from = n_g;  // never met: the sync run's tokens are the lane's tokens
+                                res = r;
+                            }
+                        } else {
+                            res = par_run<PR_COUNT>(s_cb, s_mk, cw0_bits, s_ll, s_d, s_sub, s_zero, prev, my_end, 0, n, nullptr);
+                        }
                         S.exitb[t + 1] = res;
                     }
                     __syncthreads();
                 }
+                if (fallback) break;
+                if (ONEPASS) n = n_s + (n_g - g_from);
                 // ---- the chain is true up to the first flagged lane
                 if (active && (res & (PF_EOB | PF_INV))) atomicMin(&S.first_flag, (uint32_t)t);
                 __syncthreads();
@@ -438,9 +672,16 @@ __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
                     total += v;
                 }
                 if (ntok + total > isize) { fallback = true; break; }  // more tokens than output bytes: corrupt
-                if ((uint32_t)t <= last && n) {
+                if (ONEPASS) {
+                    // the staged words are spent: their area becomes the warps' copy tiles
+                    uint32_t* const tile = reinterpret_cast<uint32_t*>(par_smem + offsetof(PS, cb)) + wid * (32 * 33);
+                    uint32_t* const dst = tk + ntok + before + incl - mine;
+                    const bool mine_counts = (uint32_t)t <= last;
+                    par_copy_warp(tile, s_tok, 0u, mine_counts ? n_s : 0u, dst, lane);
+                    par_copy_warp(tile, g_tok, g_from, mine_counts ? n_g : g_from, dst + n_s, lane);
+                } else if ((uint32_t)t <= last && n) {
                     uint32_t n2;
-                    par_run<true>(s_cb, cw0_bits, s_ll, s_d, s_sub, s_zero, my_start, my_end, n2, tk + ntok + before + incl - mine);
+                    par_run<PR_EMIT>(s_cb, s_mk, cw0_bits, s_ll, s_d, s_sub, s_zero, cur_start, my_end, 0, n2, tk + ntok + before + incl - mine);
                 }
                 ntok += total;
                 bp = last_res & ~PF_ANY;

@@ -184,7 +184,7 @@ struct Pipeline {
     WinBufs wb[2];
     DevBuf U[2];
     size_t U_cap[2] = {0, 0};  // data bytes (without prefix/slack); the two buffers grow independently
-    DevBuf d_meta, d_chain, d_carry, d_tscratch, d_tok[2], d_ntok[2], d_fb[2];
+    DevBuf d_meta, d_chain, d_carry, d_tscratch, d_tok[2], d_ntok[2], d_fb[2], d_pscratch[2], d_phdr[2], d_phlens[2];
     PinnedBuf h_meta_front, h_meta_main;
     int sm_count = 148;
     bool sync_debug = false;
@@ -599,8 +599,8 @@ struct Pipeline {
     }
 
     // K1.  Pass 1 (Huffman decode -> tokens): MBF_BAM_INFLATE_D = 400 (default) k_tokens_par<128,41>, 401
-    // <256,21>, 402 <128,33>, 403 <64,41> (one CTA per member, lanes share the tables; members it cannot
-    // handle go to k_tokens_bf<8>); 302/304/308/316 = k_tokens_bf for every member with 2/4/8/16 decoders per
+    // <256,21>, 402 <128,33>, 403 <64,41>, 410-412 its single-decode form (one CTA per member, lanes share the
+    // tables; members it cannot handle go to k_tokens_bf<8>); 302/304/308/316 = k_tokens_bf for every member with 2/4/8/16 decoders per
     // warp (the round-1 production kernel).  Pass 2 (LZ77): k_lz_resolve.
     void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks, cudaStream_t si) {
         const uint32_t mode_d = env_u32("MBF_BAM_INFLATE_D", 400);
@@ -626,14 +626,23 @@ struct Pipeline {
             uint32_t grid = std::min<uint32_t>((n_members + dl - 1) / dl, (uint32_t)(sm_count * per_sm));
             kernel<<<std::max(1u, grid), 32, smem, si>>>(ta);
         };
-        auto launch_par = [&](auto kernel, int nt, size_t smem) {
+        auto launch_par = [&](auto kernel, int nt, int sw_max, size_t smem) {
             CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 1;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem));
             const uint32_t cap = env_u32("MBF_BAM_PAR_PER_SM", 0);
             if (cap) per_sm = std::min<int>(per_sm, (int)cap);
             const uint32_t grid = std::min<uint32_t>(n_blocks, (uint32_t)(sm_count * std::max(1, per_sm)));
-            ParArgs pa{ta, d_fb[bi].as<uint32_t>(), &dmeta(bi)->fb_count};
+            // lane-private token scratch of the guess and sync runs (touched: ~1 KB per lane, L2 resident)
+            d_pscratch[bi].ensure((size_t)grid * nt * 2 * par_scratch_cap(sw_max) * 4 + 256);  // (sw_max 0: three-decode scheme, unused)
+            // first block header of every member, one thread each
+            d_phdr[bi].ensure((size_t)(n_blocks + 64) * sizeof(ParHdr));
+            d_phlens[bi].ensure((size_t)(n_blocks + 64) * PAR_HDR_STRIDE);
+            k_par_headers<<<(n_blocks + PAR_HDR_THREADS - 1) / PAR_HDR_THREADS, PAR_HDR_THREADS, 0, si>>>(ta, d_phdr[bi].as<ParHdr>(),
+                                                                                                    d_phlens[bi].as<uint8_t>());
+            launched("k_par_headers", si);
+            ParArgs pa{ta, d_fb[bi].as<uint32_t>(), &dmeta(bi)->fb_count, d_pscratch[bi].as<uint32_t>(), d_phdr[bi].as<ParHdr>(),
+                       d_phlens[bi].as<uint8_t>()};
             kernel<<<std::max(1u, grid), nt, smem, si>>>(pa);
             launched("k_tokens_par", si);
             // the members it handed over (stored blocks, exotic tables, corrupt streams): usually none
@@ -644,16 +653,21 @@ struct Pipeline {
             launched("k_tokens_bf(fallback)", si);
         };
         switch (mode_d) {
-            case 400: launch_par(k_tokens_par<128, 41>, 128, sizeof(ParShared<128, 41>)); break;
-            case 401: launch_par(k_tokens_par<256, 21>, 256, sizeof(ParShared<256, 21>)); break;
-            case 402: launch_par(k_tokens_par<128, 33>, 128, sizeof(ParShared<128, 33>)); break;
-            case 403: launch_par(k_tokens_par<64, 41>, 64, sizeof(ParShared<64, 41>)); break;
+            // three-decode scheme (guess, sync, emit runs all decode)
+            case 400: launch_par(k_tokens_par<128, 41, false>, 128, 0, sizeof(ParShared<128, 41, false>)); break;
+            case 401: launch_par(k_tokens_par<256, 21, false>, 256, 0, sizeof(ParShared<256, 21, false>)); break;
+            case 402: launch_par(k_tokens_par<128, 33, false>, 128, 0, sizeof(ParShared<128, 33, false>)); break;
+            case 403: launch_par(k_tokens_par<64, 41, false>, 64, 0, sizeof(ParShared<64, 41, false>)); break;
+            // single-decode scheme (the guess run keeps its tokens and marks its path; sync runs stop where they meet it)
+            case 410: launch_par(k_tokens_par<128, 41, true>, 128, 41, sizeof(ParShared<128, 41, true>)); break;
+            case 411: launch_par(k_tokens_par<128, 33, true>, 128, 33, sizeof(ParShared<128, 33, true>)); break;
+            case 412: launch_par(k_tokens_par<128, 21, true>, 128, 21, sizeof(ParShared<128, 21, true>)); break;
             case 302: launch_bf(k_tokens_bf<2, true>, (int)sizeof(TokensShared32<2>), 2, n_blocks); launched("k_tokens_bf", si); break;
             case 304: launch_bf(k_tokens_bf<4, true>, (int)sizeof(TokensShared32<4>), 4, n_blocks); launched("k_tokens_bf", si); break;
             case 308: launch_bf(k_tokens_bf<8, true>, (int)sizeof(TokensShared32<8>), 8, n_blocks); launched("k_tokens_bf", si); break;
             case 316: launch_bf(k_tokens_bf<16, true>, (int)sizeof(TokensShared32<16>), 16, n_blocks); launched("k_tokens_bf", si); break;
             default:
-                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 400-403 or 302, 304, 308, 316");
+                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 400-403, 410-412 or 302, 304, 308, 316");
         }
         CK(cudaEventRecord(w.t[7], si));
         CK(cudaEventRecord(w.ev_cfree, si));  // pass 2 reads tokens only: the next H2D into this buffer may start

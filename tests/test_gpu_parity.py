@@ -306,15 +306,26 @@ def test_baseline_config_shapes(mb, tmp_path, cfg, reads):
     assert got_u["_total"] > 0 and got_u["_outside"] > 0
 
 
-def test_alternate_inflate_kernels_agree(mb, tmp_path, monkeypatch):
-    """Every pass-1 variant (MBF_BAM_INFLATE_D: the CTA-per-member kernel in four shapes, the lane-per-member
-    kernel with 2..16 decoders per warp) must give the same bytes as zlib."""
-    path, *_ = make_case(tmp_path, 17, n_reads=30_000, random_seq=True)
-    data = open(path, "rb").read()
-    want = b"".join(p for _, _, p in bamio.iter_bgzf_blocks(data))
-    for d in ("400", "401", "402", "403", "302", "304", "308", "316"):
-        monkeypatch.setenv("MBF_BAM_INFLATE_D", d)
-        assert mb.inflate_buffer(data) == want, d
+@pytest.mark.parametrize("d", ["400", "401", "402", "403", "410", "411", "412", "302", "304", "308", "316"])
+def test_alternate_inflate_kernels_agree(mb, tmp_path, monkeypatch, d):
+    """Every pass-1 variant (MBF_BAM_INFLATE_D: the CTA-per-member kernel in its three-decode and single-decode forms
+    and several shapes, the lane-per-member kernel with 2..16 decoders per warp) must give the same bytes as zlib, on
+    members with one and several deflate blocks, fixed and dynamic codes, tiny and full-size members."""
+    monkeypatch.setenv("MBF_BAM_INFLATE_D", d)
+    for k, kw in enumerate([dict(), dict(sync_every=700), dict(strategy=zlib.Z_FIXED), dict(level=1, payload_limit=3000),
+                            dict(level=9, split_records=True), dict(strategy=zlib.Z_HUFFMAN_ONLY)]):
+        path, *_ = make_case(tmp_path, 170 + k, n_reads=30_000, random_seq=(k % 2 == 0), **kw)
+        data = open(path, "rb").read()
+        want = b"".join(p for _, _, p in bamio.iter_bgzf_blocks(data))
+        assert mb.inflate_buffer(data) == want, (d, kw)
+    # highly compressible: long runs, two-bit tokens, members of a few hundred bytes of compressed data
+    payload = (b"\0" * 150_000 + b"ab" * 60_000 + bytes(range(256)) * 300 + b"x" * 65_000) * 3
+    p = tmp_path / "runs.bgzf"
+    with open(p, "wb") as fh:
+        w = bamio.BgzfWriter(fh)
+        w.write(payload, atomic=False)
+        w.close()
+    assert mb.inflate_buffer(p.read_bytes()) == payload, d
 
 
 def test_pinned_file_mapping_gives_same_result(mb, tmp_path):
