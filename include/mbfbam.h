@@ -214,6 +214,24 @@ int mbfbam_duplicate_distribution(mbfbam_reader* r, const int32_t* devices, int3
                                   size_t errlen);
 void mbfbam_free_dup_hist(mbfbam_dup_hist* x);
 
+/* Replaces py_count_reads_primary_only_right_strand_only_by_barcode (src/count_reads/by_barcode.rs:18-92, :101-182;
+ * wrapper src/lib.rs:184-211), umi_strategy "straight": per chunk and (gene, XC barcode) the number of distinct XM UMIs,
+ * summed over (pos, is_reverse), of the reads that are not secondary and lie on the gene's strand.  One entry per
+ * (chunk, gene, barcode), sorted by chunk, gene slot, barcode bytes; a chunk in which a right-strand hit lacks a string
+ * XC or XM tag contributes nothing, as in the reference.  Keys are 128-bit fingerprints on the device (DESIGN.md,
+ * deviations); barcodes longer than 44 bytes are an error.  job->mode and each_read_counts_once are ignored. */
+typedef struct mbfbam_barcode_counts {
+    uint64_t n;
+    uint32_t* gene;      /* global gene slot as in the mbfbam_counts struct */
+    uint32_t* chunk;     /* index into the chunk table of job->gene_intervals */
+    uint32_t* count;
+    uint64_t* bc_off;    /* n + 1 offsets into bc_bytes */
+    char* bc_bytes;
+} mbfbam_barcode_counts;
+int mbfbam_count_by_barcode(mbfbam_reader* r, const mbfbam_count_job* job, mbfbam_barcode_counts* out, mbfbam_stats* stats,
+                            char* err, size_t errlen);
+void mbfbam_free_barcode_counts(mbfbam_barcode_counts* x);
+
 /* ChunkedGenome (src/count_reads/chunked_genome.rs:17-43,72-119): writes up to `cap`
  * chunks (tid,start,stop) and returns the total count.  gene_intervals == NULL gives
  * new_without_tree().  Exposed for tests and for sharding decisions made by the host. */

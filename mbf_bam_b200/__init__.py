@@ -10,6 +10,8 @@ star-imports the native module; reference src/lib.rs:286-299 lists its functions
     quantify_gene_reads(filename, index_filename, intervals, gene_intervals)
                                    -> (congruent, incongruent) {gene_id: [(pos, n_reads)]}
     calculate_duplicate_distribution(filename, index_filename=None) -> {k: occurrences}
+    count_reads_primary_only_right_strand_only_by_barcode(filename, index_filename, intervals, gene_intervals,
+                                   umi_strategy) -> (genes, barcodes, [(gene_idx, barcode_idx, n_umis)])
 
 The native module is built in-tree by `__graft_entry__.build()` (or `make -C mbf_bam_b200/csrc`).
 There is no CPU implementation behind these names: importing works anywhere, calling needs a GPU.
@@ -21,6 +23,7 @@ try:
         calculate_duplicate_distribution,
         cigar_expand,
         count_introns,
+        count_reads_primary_only_right_strand_only_by_barcode,
         count_reads_stranded,
         count_reads_unstranded,
         count_reads_weighted,

@@ -39,6 +39,7 @@ enum WinErr : uint32_t {
     WERR_NH_TYPE = 105,     // NH tag present but not an integer type
     WERR_AUX = 106,         // malformed aux area
     WERR_CAPACITY = 107,    // a device buffer was too small (host retries with a larger one)
+    WERR_BARCODE_LEN = 109, // XC barcode longer than BARCODE_MAX bytes
     WERR_USIZE = 108,       // the window's blocks inflate past the 32-bit offset range (host retries with smaller windows)
     WERR_INFLATE = 200,     // + InflateError
 };
@@ -1068,5 +1069,198 @@ __global__ void __launch_bounds__(256) k_dup_hist(const ulonglong2* map, uint32_
         }
     }
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// count_reads_primary_only_right_strand_only_by_barcode (reference src/count_reads/by_barcode.rs:101-182).
+// Per chunk the reference keeps {(gene_no, XC barcode, pos, is_reverse) -> set of XM UMIs} over the reads that are
+// not secondary and lie on the gene's strand, then emits (gene_no, barcode, sum of the set sizes).  Here:
+//   * every (gene, barcode, pos, is_reverse, UMI) becomes a 128-bit fingerprint in the job-wide set (`set`, the one
+//     the multi-mapper keys use); `pos` fixes the chunk, so the set needs no chunk id
+//   * a fingerprint seen for the first time adds 1 to the entry (chunk, gene, barcode) of the 16-byte-slot map
+//     (keyed by a 96-bit fingerprint of the triple)
+//   * a triple seen for the first time appends one BarcodeRec {fingerprint, gene, chunk, barcode bytes} to a list, from
+//     which the host recovers what the map's fingerprints stand for
+//   * a right-strand hit of a read without a string XC / XM makes the reference drop the whole chunk
+//     (by_barcode.rs:46-68 `_ => {}`): chunk_err[chunk] = 1, the host drops the chunk's entries
+// Two passes per window like the intron job: pass 1 counts the right-strand hits (the bound for all three
+// structures), pass 2 inserts.
+constexpr uint32_t BARCODE_MAX = 44;  // bytes of a barcode kept in a BarcodeRec; longer ones: WERR_BARCODE_LEN
+struct BarcodeRec {
+    unsigned long long key;   // map key
+    uint32_t tag;             // map tag
+    uint32_t gene;            // global gene slot
+    uint32_t chunk;           // global chunk id of the job's chunk table
+    uint32_t len;
+    uint8_t bc[BARCODE_MAX];
+};
+static_assert(sizeof(BarcodeRec) == 72, "BarcodeRec layout");
+
+// String aux tag (rust-htslib Aux::String: types Z and H).  1 found, 0 absent, -1 present with another type, -2 malformed.
+__device__ __forceinline__ int aux_find_str(const uint8_t* p, const uint8_t* e, uint8_t t0, uint8_t t1, const uint8_t** sp,
+                                            uint32_t* slen) {
+    while (p + 3 <= e) {
+        const bool match = p[0] == t0 && p[1] == t1;
+        const uint8_t t = p[2];
+        p += 3;
+        uint32_t sz;
+        switch (t) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'd': sz = 8; break;
+            case 'Z': case 'H': {
+                const uint8_t* s0 = p;
+                while (p < e && *p) p++;
+                if (p >= e) return -2;
+                if (match) { *sp = s0; *slen = (uint32_t)(p - s0); return 1; }
+                p++;
+                continue;
+            }
+            case 'B': {
+                if (match) return -1;
+                if (p + 5 > e) return -2;
+                const uint8_t st = p[0];
+                const uint32_t cnt = ldu32(p + 1);
+                const uint32_t es = (st == 'c' || st == 'C') ? 1u : (st == 's' || st == 'S') ? 2u : 4u;
+                unsigned long long adv = 5ull + (unsigned long long)cnt * es;
+                if (adv > (unsigned long long)(e - p)) return -2;
+                p += adv;
+                continue;
+            }
+            default: return -2;
+        }
+        if (p + sz > e) return -2;
+        if (match) return -1;
+        p += sz;
+    }
+    return 0;
+}
+
+// insert into the open-addressing set (empty = 0,0); true if the key was not there
+__device__ __forceinline__ bool set_insert(ulonglong2* set, uint32_t mask, ulonglong2 key) {
+    if (key.x == 0 && key.y == 0) key.y = 1;
+    uint32_t p = (uint32_t)key.x & mask;
+    for (;;) {
+        const ulonglong2 old = cas128(set + p, make_ulonglong2(0, 0), key);
+        if (old.x == 0 && old.y == 0) return true;
+        if (old.x == key.x && old.y == key.y) return false;
+        p = (p + 1) & mask;
+    }
+}
+
+// map_add that tells whether it created the entry
+__device__ __forceinline__ bool map_add_new(ulonglong2* map, uint32_t mask, unsigned long long key, uint32_t tag, uint32_t n) {
+    unsigned long long h = fmix64(key ^ ((unsigned long long)tag * 0x9E3779B97F4A7C15ull));
+    uint32_t i = (uint32_t)h & mask;
+    for (;;) {
+        ulonglong2 cur;
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(cur.x), "=l"(cur.y) : "l"(map + i));
+        if (cur.x == ~0ull && cur.y == ~0ull) {
+            ulonglong2 mine = make_ulonglong2(key, (unsigned long long)tag | ((unsigned long long)n << 32));
+            ulonglong2 old = cas128(map + i, make_ulonglong2(~0ull, ~0ull), mine);
+            if (old.x == ~0ull && old.y == ~0ull) return true;
+            cur = old;
+        }
+        if (cur.x == key && (uint32_t)cur.y == tag) {
+            atomicAdd(((uint32_t*)(map + i)) + 3, n);
+            return false;
+        }
+        i = (i + 1) & mask;
+    }
+}
+
+struct BarcodeCtx {
+    CountCtx c;                  // record source, interval tables, chunk table, owned chunk range
+    int count_only;              // pass 1
+    ulonglong2* set;
+    uint32_t set_mask;
+    unsigned long long* set_size;
+    ulonglong2* map;
+    uint32_t map_mask;
+    BarcodeRec* list;
+    unsigned long long* list_n;  // records appended so far (job wide)
+    unsigned long long list_cap;
+    uint32_t* chunk_err;         // per global chunk
+    uint32_t* job_err;           // first WinErr of a pass 2 (the window's own error word is read before pass 2 runs)
+};
+
+__global__ void __launch_bounds__(256) k_barcode_hits(BarcodeCtx bc) {
+    const CountCtx& c = bc.c;
+    const uint32_t n = c.meta->n_records;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t my_hits = 0, my_owned = 0, my_new = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        RecView v;
+        if (!rec_view(c.U, c.rec_off[i], v)) { set_err(c.meta, WERR_RECORD, i); continue; }
+        const int slot = (v.tid >= 0 && v.tid < c.n_ref) ? c.tid2slot[v.tid] : -1;
+        if (slot < 0) continue;
+        const uint32_t clo = c.slot_chunk_off[slot], chi = c.slot_chunk_off[slot + 1];
+        const uint32_t ci = upper_bound_u32(c.chunk_stop, clo, chi, v.upos);  // first stop > pos
+        if (!(ci < chi && ci >= c.chunk_lo && ci < c.chunk_hi)) continue;
+        my_owned++;
+        if (v.flag & 0x100u) continue;  // by_barcode.rs:127 is_secondary
+        const uint32_t cstop = c.chunk_stop[ci];
+        const uint32_t iv_lo = c.slot_iv_off[slot], iv_hi = c.slot_iv_off[slot + 1];
+        const bool rev = (v.flag & 0x10u) != 0;
+        int have = 0;  // 0: tags not looked up yet, 1: ok, -1: chunk failed
+        const uint8_t *xc = nullptr, *xm = nullptr;
+        uint32_t xc_len = 0, xm_len = 0;
+        // by_barcode.rs:131: with pos >= chunk.start only `block start >= chunk.stop` can drop a block
+        enumerate_hits(c, v, iv_lo, iv_hi, true, cstop, [&](uint32_t gw) {
+            const bool plus = (gw >> 31) != 0;
+            if (!((plus && !rev) || (!plus && rev))) return true;  // by_barcode.rs:139
+            my_hits++;
+            if (bc.count_only) return true;
+            if (have == 0) {
+                have = 1;
+                const int r1 = aux_find_str(v.aux, v.end, 'X', 'C', &xc, &xc_len);
+                const int r2 = r1 == 1 ? aux_find_str(v.aux, v.end, 'X', 'M', &xm, &xm_len) : 0;
+                if (r1 == -2 || r2 == -2) atomicCAS(bc.job_err, 0u, (uint32_t)WERR_AUX);
+                if (r1 != 1 || r2 != 1) have = -1;
+                else if (xc_len > BARCODE_MAX) { atomicCAS(bc.job_err, 0u, (uint32_t)WERR_BARCODE_LEN); have = -1; }
+            }
+            if (have < 0) {
+                bc.chunk_err[ci] = 1u;  // `?` leaves the chunk's function: the chunk yields nothing
+                return false;
+            }
+            const uint32_t gene = gw & 0x7fffffffu;
+            // (gene, pos, is_reverse, barcode, UMI)
+            ulonglong2 f = qname_fingerprint(xc, xc_len, v.upos, gene | (rev ? 0x80000000u : 0u));
+            const ulonglong2 fu = qname_fingerprint(xm, xm_len, xc_len, 0x5bd1e995u);
+            f.x = fmix64(f.x ^ rotl64(fu.x, 17));
+            f.y = fmix64(f.y + fu.y);
+            if (!set_insert(bc.set, bc.set_mask, f)) return true;
+            my_new++;
+            // (chunk, gene, barcode)
+            const ulonglong2 g = qname_fingerprint(xc, xc_len, ci, gene);
+            unsigned long long key = g.x;
+            uint32_t tag = (uint32_t)g.y;
+            if (key == ~0ull && tag == 0xffffffffu) tag = 0;
+            if (map_add_new(bc.map, bc.map_mask, key, tag, 1)) {
+                const unsigned long long at = atomicAdd(bc.list_n, 1ull);
+                if (at < bc.list_cap) {
+                    BarcodeRec& r = bc.list[at];
+                    r.key = key; r.tag = tag; r.gene = gene; r.chunk = ci; r.len = xc_len;
+                    for (uint32_t k = 0; k < xc_len; k++) r.bc[k] = xc[k];
+                }
+            }
+            return true;
+        });
+    }
+    if (bc.count_only) {
+        my_hits = __reduce_add_sync(0xffffffffu, my_hits);
+        my_owned = __reduce_add_sync(0xffffffffu, my_owned);
+        if (lane == 0) {
+            if (my_hits) atomicAdd(&c.meta->cigar_ops, my_hits);
+            if (my_owned) atomicAdd(&c.meta->owned_records, my_owned);
+        }
+    } else {
+        my_new = __reduce_add_sync(0xffffffffu, my_new);
+        if (lane == 0 && my_new) atomicAdd(bc.set_size, (unsigned long long)my_new);
+    }
+}
+
 
 }  // namespace mbf

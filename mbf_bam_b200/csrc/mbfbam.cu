@@ -147,7 +147,7 @@ struct MemSource : Source {
     void read(uint64_t off, size_t len, uint8_t* dst) const override { memcpy(dst, p + off, len); }
 };
 
-enum JobKind { JOB_COUNT, JOB_INTRONS, JOB_INFLATE, JOB_QUANTIFY, JOB_DUPS };
+enum JobKind { JOB_COUNT, JOB_INTRONS, JOB_INFLATE, JOB_QUANTIFY, JOB_DUPS, JOB_BARCODE };
 
 struct WinBufs {
     PinnedBuf h_c;
@@ -207,6 +207,10 @@ struct Pipeline {
     // ---- duplicate-distribution job (shares d_map / map_cap with the intron job)
     DupCtx dc{};
     DevBuf d_ref_len, d_dup_dense, d_dup_big, d_dup_nbig;
+    // ---- by-barcode job (uses d_set / d_map too)
+    DevBuf d_bclist, d_bclist_n, d_chunk_err;
+    uint64_t bclist_cap = 0, bclist_ub = 0;
+    size_t bc_n_chunks = 0;  // d_chunk_err holds bc_n_chunks flags, then the job's error word
     // ---- inflate-only job
     uint8_t* out_host = nullptr;
     uint64_t out_cap = 0, out_len = 0;
@@ -289,6 +293,7 @@ struct Pipeline {
         if (set_cap) CK(cudaMemsetAsync(d_set.p, 0, set_cap * 16, s_main));
         map_ub = 0;
         if (map_cap) CK(cudaMemsetAsync(d_map.p, 0xff, map_cap * 16, s_main));
+        bclist_ub = 0;
         n_genes = n_count_words = 0;
         out_host = nullptr;
         out_cap = out_len = 0;
@@ -518,6 +523,7 @@ struct Pipeline {
             case WERR_CARRY: what = "BAM record larger than 4 MiB"; break;
             case WERR_NH_TYPE: what = "NH tag is not an integer"; break;
             case WERR_AUX: what = "malformed aux data"; break;
+            case WERR_BARCODE_LEN: what = "XC barcode longer than 44 bytes"; break;
             case WERR_CAPACITY: what = "too many BGZF blocks in one window (raise MBF_BAM_WINDOW_MB?)"; break;
             default: if (m.err >= WERR_INFLATE) what = "corrupt DEFLATE stream in BGZF block"; break;
         }
@@ -589,6 +595,7 @@ struct Pipeline {
             if (kind == JOB_COUNT) launch_count(bi, 0);
             else if (kind == JOB_QUANTIFY) launch_quantify(bi, 1);
             else if (kind == JOB_INTRONS) launch_introns(bi, 1);
+            else if (kind == JOB_BARCODE) launch_barcode(bi, 1);
             // JOB_DUPS: one insert per record, bounded by n_records: everything happens in the second half
             CK(cudaEventRecord(w.t[5], s_main));
         }
@@ -728,6 +735,47 @@ struct Pipeline {
         c.owned_total = d_scalar.as<unsigned long long>() + 1;
         k_dup_insert<<<count_grid(), 256, 0, s_main>>>(c);
         launched("k_dup_insert", s_main);
+    }
+
+    // by_barcode: pass 1 counts the right-strand hits of the window, pass 2 inserts them
+    void launch_barcode(int bi, int count_only) {
+        WinBufs& w = wb[bi];
+        BarcodeCtx b{};
+        b.c = cc;
+        b.c.U = U[bi].as<uint8_t>();
+        b.c.rec_off = w.rec_off.as<uint32_t>();
+        b.c.meta = dmeta(bi);
+        b.count_only = count_only;
+        b.set = d_set.as<ulonglong2>();
+        b.set_mask = (uint32_t)(set_cap - 1);
+        b.set_size = d_set_size.as<unsigned long long>();
+        b.map = d_map.as<ulonglong2>();
+        b.map_mask = (uint32_t)(map_cap - 1);
+        b.list = d_bclist.as<BarcodeRec>();
+        b.list_n = d_bclist_n.as<unsigned long long>();
+        b.list_cap = bclist_cap;
+        b.chunk_err = d_chunk_err.as<uint32_t>();
+        b.job_err = d_chunk_err.as<uint32_t>() + bc_n_chunks;
+        k_barcode_hits<<<count_grid(), 256, 0, s_main>>>(b);
+        launched("k_barcode_hits", s_main);
+    }
+
+    // room for `extra` more (chunk, gene, barcode) records; contents are kept
+    void ensure_bclist(uint64_t extra) {
+        if (bclist_ub + extra <= bclist_cap) { bclist_ub += extra; return; }
+        CK(cudaStreamSynchronize(s_main));
+        unsigned long long live = 0;
+        CK(cudaMemcpy(&live, d_bclist_n.p, 8, cudaMemcpyDeviceToHost));
+        bclist_ub = live + extra;
+        if (bclist_ub <= bclist_cap) return;
+        uint64_t ncap = std::max<uint64_t>(1u << 16, bclist_cap);
+        while (ncap < bclist_ub) ncap <<= 1;
+        DevBuf nb;
+        nb.ensure(ncap * sizeof(BarcodeRec));
+        if (live) CK(cudaMemcpy(nb.p, d_bclist.p, (size_t)live * sizeof(BarcodeRec), cudaMemcpyDeviceToDevice));
+        std::swap(d_bclist.p, nb.p);
+        std::swap(d_bclist.cap, nb.cap);
+        bclist_cap = ncap;
     }
 
     void launch_introns(int bi, int count_only) {
@@ -871,6 +919,14 @@ struct Pipeline {
             if (m.cigar_ops) {
                 ensure_map((uint64_t)m.cigar_ops + 64);
                 launch_quantify(bi, 0);
+            }
+        } else if (kind == JOB_BARCODE) {
+            st.n_records_owned += m.owned_records;
+            if (m.cigar_ops) {
+                ensure_set((uint64_t)m.cigar_ops);
+                ensure_map((uint64_t)m.cigar_ops + 64);
+                ensure_bclist((uint64_t)m.cigar_ops);
+                launch_barcode(bi, 0);
             }
         } else if (kind == JOB_DUPS) {
             if (m.n_records) {
@@ -1435,6 +1491,74 @@ void quantify_on_device(mbfbam_reader* rd, const CountTables& T, int device, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// count_reads_primary_only_right_strand_only_by_barcode (reference src/count_reads/by_barcode.rs:18-92, :101-182)
+struct BarcodeEntry {
+    uint32_t gene, chunk, count;
+    std::string barcode;
+};
+struct BarcodePart {
+    std::vector<BarcodeEntry> entries;
+    mbfbam_stats st{};
+};
+
+void barcode_on_device(mbfbam_reader* rd, const CountTables& T, int device, int shard, int nshards, int read_threads,
+                       uint64_t prior_jobs, BarcodePart& out) {
+    const Reader& r = rd->r;
+    ShardPlan plan;
+    plan.chunks = T.chunks;
+    plan_shard(r, plan, shard, nshards);
+    const double ms_pin = maybe_pin(rd, plan.ranges, prior_jobs);
+    FileSource src(&r, rd->fmap);
+    DevSlot& slot = dev_slot(device);
+    std::lock_guard<std::mutex> lk(slot.mu);
+    Pipeline& p = slot_pipeline(slot, device);
+    p.read_threads = read_threads;
+    const size_t n_chunks = std::max<size_t>(1, T.chunks.size());
+    run_with_retry(p, plan.ranges, [&](Pipeline& p) {
+        p.begin_job(&src, JOB_BARCODE, range_bytes(plan.ranges));
+        p.mode = MBFBAM_MODE_STRANDED;
+        p.d_scalar.ensure(16);
+        p.d_set_size.ensure(8);
+        CK(cudaMemsetAsync(p.d_set_size.p, 0, 8, p.s_main));
+        p.d_bclist_n.ensure(8);
+        CK(cudaMemsetAsync(p.d_bclist_n.p, 0, 8, p.s_main));
+        p.d_chunk_err.ensure((n_chunks + 1) * 4);
+        CK(cudaMemsetAsync(p.d_chunk_err.p, 0, (n_chunks + 1) * 4, p.s_main));
+        p.bc_n_chunks = n_chunks;
+        upload_count_tables(p, T, plan, false);
+        CK(cudaStreamSynchronize(p.s_main));
+        p.ensure_set(1024);
+        p.ensure_map(1024);
+        p.ensure_bclist(1024);
+        p.st.n_chunks = plan.hi - plan.lo;
+    });
+    // (chunk, gene, barcode) fingerprints -> counts, and what the fingerprints stand for
+    const std::vector<ulonglong2> slots = p.download_map();
+    unsigned long long n_rec = 0;
+    CK(cudaMemcpy(&n_rec, p.d_bclist_n.p, 8, cudaMemcpyDeviceToHost));
+    if (n_rec > p.bclist_cap) throw Error(MBFBAM_ERR_CUDA, "barcode list overflow");
+    std::vector<BarcodeRec> recs((size_t)n_rec);
+    if (n_rec) CK(cudaMemcpy(recs.data(), p.d_bclist.p, (size_t)n_rec * sizeof(BarcodeRec), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> cerr(n_chunks + 1);
+    CK(cudaMemcpy(cerr.data(), p.d_chunk_err.p, (n_chunks + 1) * 4, cudaMemcpyDeviceToHost));
+    if (cerr[n_chunks] == WERR_BARCODE_LEN) throw Error(MBFBAM_ERR_UNSUPPORTED, "XC barcode longer than 44 bytes");
+    if (cerr[n_chunks]) throw Error(MBFBAM_ERR_FORMAT, "malformed aux data");
+    p.st.d2h_bytes += (size_t)n_rec * sizeof(BarcodeRec) + n_chunks * 4 + 8;
+    if (slots.size() != recs.size()) throw Error(MBFBAM_ERR_CUDA, "barcode map and list disagree");
+    std::map<std::pair<unsigned long long, uint32_t>, uint32_t> cnt;
+    for (const ulonglong2& s : slots) cnt[{s.x, (uint32_t)s.y}] = (uint32_t)(s.y >> 32);
+    for (const BarcodeRec& b : recs) {
+        if (b.chunk < n_chunks && cerr[b.chunk]) continue;  // the reference drops a chunk whose scan returned Err
+        auto it = cnt.find({b.key, b.tag});
+        if (it == cnt.end()) throw Error(MBFBAM_ERR_CUDA, "barcode record without a map entry");
+        out.entries.push_back({b.gene, b.chunk, it->second, std::string((const char*)b.bc, std::min<uint32_t>(b.len, BARCODE_MAX))});
+    }
+    p.st.ms_pin = ms_pin;
+    p.st.n_devices = 1;
+    out.st = p.st;
+}
+
+// ------------------------------------------------------------------------------------------------
 // calculate_duplicate_distribution (reference src/duplicate_distribution.rs:44-86)
 struct DupPart {
     std::vector<unsigned long long> dense;  // DUP_DENSE counters
@@ -1859,6 +1983,69 @@ int mbfbam_duplicate_distribution(mbfbam_reader* rd, const int32_t* devices, int
         st.ms_total = now_ms() - t0;
         if (stats) *stats = st;
     });
+}
+
+int mbfbam_count_by_barcode(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_barcode_counts* out, mbfbam_stats* stats,
+                            char* err, size_t errlen) {
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (out) memset(out, 0, sizeof *out);
+    return guarded(err, errlen, [&] {
+        const double t0 = now_ms();
+        const Reader& r = rd->r;
+        if (!job || !job->intervals || !job->gene_intervals || !out) throw Error(MBFBAM_ERR_ARG, "null argument");
+        int ndev_have = 0;
+        if (cudaGetDeviceCount(&ndev_have) != cudaSuccess || ndev_have == 0)
+            throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
+        const std::vector<int> devs = job_devices(job->devices, job->n_devices, job->device);
+        mbfbam_count_job j2 = *job;
+        j2.each_read_counts_once = 0;
+        CountTables T;
+        build_count_tables(r, &j2, T);
+        const int nsh = std::max(1, job->shard_count), sh = job->shard_index;
+        if (sh < 0 || sh >= nsh) throw Error(MBFBAM_ERR_ARG, "bad shard index/count");
+        const uint64_t prior = rd->fmap ? rd->fmap->jobs.fetch_add(1) : 0;
+        std::vector<BarcodePart> parts(devs.size());
+        const int rt = default_read_threads(devs.size());
+        fan_out(devs.size(), [&](size_t k) {
+            barcode_on_device(rd, T, devs[k], sh * (int)devs.size() + (int)k, nsh * (int)devs.size(), rt, prior, parts[k]);
+        });
+        std::vector<const BarcodeEntry*> all;
+        mbfbam_stats st{};
+        size_t bytes = 0;
+        for (const BarcodePart& pt : parts) {
+            for (const BarcodeEntry& e : pt.entries) { all.push_back(&e); bytes += e.barcode.size(); }
+            merge_stats(st, pt.st);
+        }
+        // chunks in order, then (gene, barcode): the reference's order is HashMap iteration, i.e. arbitrary
+        std::sort(all.begin(), all.end(), [](const BarcodeEntry* a, const BarcodeEntry* b) {
+            if (a->chunk != b->chunk) return a->chunk < b->chunk;
+            if (a->gene != b->gene) return a->gene < b->gene;
+            return a->barcode < b->barcode;
+        });
+        const size_t n = all.size();
+        out->gene = (uint32_t*)malloc((n + 1) * 4);
+        out->chunk = (uint32_t*)malloc((n + 1) * 4);
+        out->count = (uint32_t*)malloc((n + 1) * 4);
+        out->bc_off = (uint64_t*)malloc((n + 1) * 8);
+        out->bc_bytes = (char*)malloc(bytes + 1);
+        size_t off = 0;
+        for (size_t i = 0; i < n; i++) {
+            out->gene[i] = all[i]->gene; out->chunk[i] = all[i]->chunk; out->count[i] = all[i]->count;
+            out->bc_off[i] = off;
+            memcpy(out->bc_bytes + off, all[i]->barcode.data(), all[i]->barcode.size());
+            off += all[i]->barcode.size();
+        }
+        out->bc_off[n] = off;
+        out->n = n;
+        st.ms_total = now_ms() - t0;
+        if (stats) *stats = st;
+    });
+}
+
+void mbfbam_free_barcode_counts(mbfbam_barcode_counts* x) {
+    if (!x) return;
+    free(x->gene); free(x->chunk); free(x->count); free(x->bc_off); free(x->bc_bytes);
+    memset(x, 0, sizeof *x);
 }
 
 void mbfbam_free_dup_hist(mbfbam_dup_hist* x) {

@@ -10,6 +10,7 @@
 //   count_reads_weighted     not in the reference
 //   quantify_gene_reads      src/lib.rs:247-264 + quantify.rs:20-75
 //   calculate_duplicate_distribution   src/lib.rs:108-116
+//   count_reads_primary_only_right_strand_only_by_barcode   src/lib.rs:184-211 + by_barcode.rs:18-92
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -590,6 +591,61 @@ struct PyReader {
         return py::make_tuple(out[0], out[1]);
     }
 
+    // by_barcode.rs:18-92: (genes, barcodes, [(gene_idx, barcode_idx, count)]), one entry per (chunk, gene_no, barcode).
+    // Indices are handed out in order of first appearance; the reference walks HashMaps, so its order is arbitrary --
+    // here: chunks in order, then gene slot, then barcode bytes.
+    py::tuple count_by_barcode(const py::dict& intervals, const py::dict& gene_intervals, const std::string& umi_strategy) {
+        if (umi_strategy != "straight") value_error("invalid umi_strategy");  // src/lib.rs:198-201
+        Flat iv, gv;
+        flatten(intervals, iv);
+        flatten(gene_intervals, gv);
+        mbfbam_count_job job{};
+        job.intervals = &iv.c;
+        job.gene_intervals = &gv.c;
+        job.mode = MBFBAM_MODE_STRANDED;
+        job.device = devices[0];
+        job.n_devices = (int32_t)devices.size();
+        job.devices = devices.data();
+        job.shard_index = shard_index;
+        job.shard_count = shard_count;
+        mbfbam_barcode_counts res{};
+        char err[512] = {0};
+        int rc;
+        {
+            py::gil_scoped_release rel;
+            rc = mbfbam_count_by_barcode(r, &job, &res, &last, err, sizeof err);
+        }
+        if (rc) {
+            mbfbam_free_barcode_counts(&res);
+            value_error(err);
+        }
+        std::vector<PyObject*> slot_id;  // global gene slot -> the caller's gene id object (borrowed)
+        for (const auto& ids : iv.gene_ids)
+            for (PyObject* o : ids) slot_id.push_back(o);
+        py::dict gene_idx, bc_idx;
+        py::list genes, barcodes, counts;
+        try {
+            for (uint64_t i = 0; i < res.n; i++) {
+                if (res.gene[i] >= slot_id.size()) value_error("gene slot out of range");
+                py::object g = py::reinterpret_borrow<py::object>(slot_id[res.gene[i]]);
+                py::object b = py::reinterpret_steal<py::object>(
+                    PyUnicode_DecodeUTF8(res.bc_bytes + res.bc_off[i], (Py_ssize_t)(res.bc_off[i + 1] - res.bc_off[i]), nullptr));
+                if (!b) {
+                    PyErr_Clear();
+                    value_error("XC barcode is not valid UTF-8");  // the reference unwraps from_utf8 (by_barcode.rs:57)
+                }
+                if (!gene_idx.contains(g)) { gene_idx[g] = py::int_(genes.size()); genes.append(g); }
+                if (!bc_idx.contains(b)) { bc_idx[b] = py::int_(barcodes.size()); barcodes.append(b); }
+                counts.append(py::make_tuple(gene_idx[g], bc_idx[b], res.count[i]));
+            }
+        } catch (...) {
+            mbfbam_free_barcode_counts(&res);
+            throw;
+        }
+        mbfbam_free_barcode_counts(&res);
+        return py::make_tuple(genes, barcodes, counts);
+    }
+
     // duplicate_distribution.rs:44-86 -> {k: occurrences}
     py::dict duplicate_distribution() {
         mbfbam_dup_hist res{};
@@ -676,6 +732,16 @@ PYBIND11_MODULE(mbf_bam, m) {
           },
           py::arg("filename"), py::arg("index_filename") = py::none(),
           "python wrapper for py_calculate_duplicate_distribution (reference src/lib.rs:108)");
+    m.def("count_reads_primary_only_right_strand_only_by_barcode",
+          [](const std::string& filename, py::object index_filename, const py::dict& intervals, const py::dict& gene_intervals,
+             const std::string& umi_strategy) {
+              PyReader rd(filename, index_filename);
+              py::tuple res = rd.count_by_barcode(intervals, gene_intervals, umi_strategy);
+              g_last_stats = rd.last;
+              return res;
+          },
+          py::arg("filename"), py::arg("index_filename"), py::arg("intervals"), py::arg("gene_intervals"), py::arg("umi_strategy"),
+          "python wrapper for py_count_reads_primary_only_right_strand_only_by_barcode (reference src/lib.rs:184)");
     m.def("last_stats", []() { return stats_dict(g_last_stats); }, "measurements of the most recent module-level call");
     m.def("device_count", []() { return mbfbam_device_count(); });
     m.def("release_device", [](int device) { mbfbam_release_device(device); }, py::arg("device") = 0,
@@ -743,5 +809,7 @@ PYBIND11_MODULE(mbf_bam, m) {
         .def("count_introns", &PyReader::count_introns)
         .def("quantify_gene_reads", &PyReader::quantify_gene_reads, py::arg("intervals"), py::arg("gene_intervals"))
         .def("calculate_duplicate_distribution", &PyReader::duplicate_distribution)
+        .def("count_reads_primary_only_right_strand_only_by_barcode", &PyReader::count_by_barcode, py::arg("intervals"),
+             py::arg("gene_intervals"), py::arg("umi_strategy"))
         .def("stats", &PyReader::stats);
 }

@@ -451,7 +451,7 @@ def calculate_duplicate_distribution(path, index_path=None):
 
 
 def aux_get_str(aux, tag):
-    """(found, bytes or None if the tag is not of type Z) -- rust-htslib Aux::String."""
+    """(found, bytes or None if the tag is not of type Z/H) -- rust-htslib Aux::String."""
     import struct
     p = 0
     sizes = {b"A": 1, b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4, b"d": 8}
@@ -462,7 +462,7 @@ def aux_get_str(aux, tag):
         if ty in (b"Z", b"H"):
             e = aux.index(b"\0", p)
             if t == tag:
-                return True, (aux[p:e] if ty == b"Z" else None)
+                return True, aux[p:e]      # rust-htslib 0.24 aux(): Z and H both give Aux::String
             p = e + 1
         elif ty == b"B":
             sub = aux[p:p + 1]

@@ -1,5 +1,6 @@
-"""quantify_gene_reads and calculate_duplicate_distribution.  CPU part: the Python restatement
-against hand-computed answers (the reference holds no test for either function: parity unpinned); GPU part: the
+"""quantify_gene_reads, calculate_duplicate_distribution and
+count_reads_primary_only_right_strand_only_by_barcode.  CPU part: the Python restatement
+against hand-computed answers (the reference holds no test for any of them: parity unpinned); GPU part: the
 device path, through the C ABI, against the restatement."""
 import os
 import random
@@ -216,6 +217,143 @@ def test_duplicate_distribution_hand_case_windows_and_shards(mb, tmp_path, monke
             for k, v in rd.calculate_duplicate_distribution().items():
                 total[k] = total.get(k, 0) + v
         assert total == want
+    finally:
+        monkeypatch.delenv("MBF_BAM_WINDOW_MB")
+        mb.release_device(0)
+
+
+# ------------------------------------------------------------------------------------------------ by barcode
+from synth.bamio import aux_str  # noqa: E402
+
+BY_BARCODE = "count_reads_primary_only_right_strand_only_by_barcode"
+
+
+def barcode_case(tmp_path, seed, n_reads=4000, bad_chunks=True, **kw):
+    """single-cell-like tags: XC from a small set of barcodes, XM UMIs from a tiny alphabet so that (pos, UMI) repeat"""
+    from synth import small
+
+    write_kw = {k: kw.pop(k) for k in list(kw) if k in ("level", "split_records", "payload_limit")}
+    rng = random.Random(seed)
+    contigs, recs, iv, giv = small.simple_case(seed, n_reads=n_reads, **kw)
+    barcodes = [("".join(rng.choice("ACGT") for _ in range(rng.choice([8, 12, 12, 16])))).encode() for _ in range(25)]
+    out = []
+    for r in recs:
+        tags = aux_str(b"XC", rng.choice(barcodes)) + aux_str(b"XM", "".join(rng.choice("AC") for _ in range(3)).encode())
+        if rng.random() < 0.5:
+            r.aux = tags + r.aux
+        else:
+            r.aux = r.aux + tags
+        out.append(r)
+        if rng.random() < 0.3:   # PCR duplicates and near-duplicates at the same position
+            for _ in range(rng.randint(1, 3)):
+                d = Rec(r.tid, r.pos, r.qname + b"d", r.flag ^ rng.choice([0, 0, 16]), r.mapq, list(r.cigar), r.l_seq,
+                        aux_str(b"XM", "".join(rng.choice("AC") for _ in range(3)).encode()) + aux_str(b"XC", rng.choice(barcodes[:4])))
+                out.append(d)
+    if bad_chunks:
+        # chunks that the reference drops: a right-strand hit without XC / with an integer XC / without XM
+        for tid, (name, _) in enumerate(contigs):
+            g = iv[name][3]
+            if g[1] == 1:
+                flag = 0
+            else:
+                flag = 16
+            pos = g[2][0]
+            if tid == 0:
+                out.append(Rec(tid, pos, b"noxc", flag, 255, [(0, 30)], 30, aux_str(b"XM", b"AAA")))
+            elif tid == 1:
+                out.append(Rec(tid, pos, b"intxc", flag, 255, [(0, 30)], 30, aux_int(b"XC", 7) + aux_str(b"XM", b"AAA")))
+            else:
+                out.append(Rec(tid, pos, b"noxm", flag, 255, [(0, 30)], 30, aux_str(b"XC", b"ACGTACGT")))
+    # a read without tags that hits nothing on its strand is harmless
+    out.append(Rec(0, 7, b"plain", 0, 255, [(0, 3)], 3, b""))
+    out.sort(key=lambda r: (r.tid if r.tid >= 0 else 1 << 30, r.pos))
+    path = os.path.join(str(tmp_path), "bc_%d.bam" % seed)
+    bamio.write_bam(path, contigs, out, **write_kw)
+    return path, contigs, out, iv, giv
+
+
+def test_by_barcode_hand_case(tmp_path):
+    """reference src/count_reads/by_barcode.rs:101-182 by hand."""
+    contigs = [("c1", 2_500_000)]
+    iv = {"c1": [("gP", 1, [100], [200]), ("gM", -1, [150], [400]), ("gFar", 1, [1_200_000], [1_200_100])]}
+    giv = iv
+    tag = lambda bc, umi: aux_str(b"XC", bc) + aux_str(b"XM", umi)
+    recs = [
+        Rec(0, 120, b"a", 0, 255, [(0, 50)], 50, tag(b"AAAA", b"u1")),      # forward: gP (+) counts, gM (-) is the wrong strand
+        Rec(0, 120, b"b", 0, 255, [(0, 50)], 50, tag(b"AAAA", b"u1")),      # same (gene, barcode, pos, strand, UMI): once
+        Rec(0, 120, b"c", 0, 255, [(0, 50)], 50, tag(b"AAAA", b"u2")),      # second UMI
+        Rec(0, 121, b"d", 0, 255, [(0, 50)], 50, tag(b"AAAA", b"u1")),      # other position: counts again
+        Rec(0, 121, b"e", 0, 255, [(0, 50)], 50, tag(b"CCCC", b"u1")),      # other barcode
+        Rec(0, 121, b"f", 0x100, 255, [(0, 50)], 50, tag(b"CCCC", b"u9")),  # secondary: ignored
+        Rec(0, 160, b"g", 16, 255, [(0, 50)], 50, tag(b"AAAA", b"u1")),     # reverse: gM only
+        Rec(0, 160, b"h", 16, 255, [(0, 10), (3, 100), (0, 10)], 20, tag(b"AAAA", b"u1")),  # two blocks in gM: one set entry
+        Rec(0, 500, b"i", 0, 255, [(0, 50)], 50, b""),                      # no tags, no hit: harmless
+        Rec(0, 1_200_010, b"j", 0, 255, [(0, 50)], 50, tag(b"GGGG", b"u1")),  # second chunk
+        Rec(0, 1_200_020, b"k", 0, 255, [(0, 50)], 50, aux_str(b"XC", b"GGGG")),  # ... which fails: XM missing -> nothing from chunk 2
+    ]
+    p = str(tmp_path / "b.bam")
+    bamio.write_bam(p, contigs, recs)
+    genes, barcodes, counts = getattr(py_oracle, BY_BARCODE)(p, None, iv, giv, "straight")
+    got = sorted((genes[g], barcodes[b], n) for g, b, n in counts)
+    assert got == [("gM", "AAAA", 1), ("gP", "AAAA", 3), ("gP", "CCCC", 1)]
+    with pytest.raises(ValueError):
+        getattr(py_oracle, BY_BARCODE)(p, None, iv, giv, "hamming")
+
+
+@pytest.mark.gpu
+def test_by_barcode_hand_case_on_device(mb, tmp_path):
+    contigs = [("c1", 2_500_000)]
+    iv = {"c1": [("gP", 1, [100], [200]), ("gM", -1, [150], [400]), ("gFar", 1, [1_200_000], [1_200_100])]}
+    tag = lambda bc, umi: aux_str(b"XC", bc) + aux_str(b"XM", umi)
+    recs = [Rec(0, 120, b"a", 0, 255, [(0, 50)], 50, tag(b"AAAA", b"u1")), Rec(0, 120, b"b", 0, 255, [(0, 50)], 50, tag(b"AAAA", b"u1")),
+            Rec(0, 120, b"c", 0, 255, [(0, 50)], 50, tag(b"AAAA", b"u2")), Rec(0, 121, b"d", 0, 255, [(0, 50)], 50, tag(b"AAAA", b"u1")),
+            Rec(0, 121, b"e", 0, 255, [(0, 50)], 50, tag(b"CCCC", b"u1")), Rec(0, 121, b"f", 0x100, 255, [(0, 50)], 50, tag(b"CCCC", b"u9")),
+            Rec(0, 160, b"g", 16, 255, [(0, 50)], 50, tag(b"AAAA", b"u1")),
+            Rec(0, 160, b"h", 16, 255, [(0, 10), (3, 100), (0, 10)], 20, tag(b"AAAA", b"u1")),
+            Rec(0, 500, b"i", 0, 255, [(0, 50)], 50, b""), Rec(0, 1_200_010, b"j", 0, 255, [(0, 50)], 50, tag(b"GGGG", b"u1")),
+            Rec(0, 1_200_020, b"k", 0, 255, [(0, 50)], 50, aux_str(b"XC", b"GGGG"))]
+    p = str(tmp_path / "b.bam")
+    bamio.write_bam(p, contigs, recs)
+    fn = getattr(mb, BY_BARCODE)
+    genes, barcodes, counts = fn(p, None, iv, iv, "straight")
+    assert sorted((genes[g], barcodes[b], n) for g, b, n in counts) == [("gM", "AAAA", 1), ("gP", "AAAA", 3), ("gP", "CCCC", 1)]
+    assert (genes, barcodes, counts) == getattr(py_oracle, BY_BARCODE)(p, None, iv, iv, "straight")
+    with pytest.raises(ValueError, match="invalid umi_strategy"):
+        fn(p, None, iv, iv, "hamming")
+    # a barcode longer than the device keeps is an error, not a silent truncation
+    recs[0] = Rec(0, 120, b"a", 0, 255, [(0, 50)], 50, tag(b"A" * 60, b"u1"))
+    bamio.write_bam(p, contigs, recs)
+    with pytest.raises(ValueError, match="barcode"):
+        fn(p, None, iv, iv, "straight")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,kw", [(61, {}), (62, dict(exon_mode=False, genes_per_contig=150, n_contigs=3)),
+                                     (63, dict(paired=True, split_records=True)), (64, dict(bad_chunks=False, level=1))])
+def test_by_barcode_matches_oracle(mb, tmp_path, seed, kw):
+    path, contigs, recs, iv, giv = barcode_case(tmp_path, seed, n_reads=6000, **kw)
+    want = getattr(py_oracle, BY_BARCODE)(path, None, iv, giv, "straight")
+    assert len(want[2]) > 50
+    assert getattr(mb, BY_BARCODE)(path, None, iv, giv, "straight") == want
+
+
+@pytest.mark.gpu
+def test_by_barcode_many_windows_and_shards(mb, tmp_path, monkeypatch):
+    path, contigs, recs, iv, giv = barcode_case(tmp_path, 65, n_reads=50000, n_contigs=3, random_seq=True)
+    want = getattr(py_oracle, BY_BARCODE)(path, None, iv, giv, "straight")
+    as_set = lambda res: sorted((res[0][g], res[1][b], n) for g, b, n in res[2])
+    monkeypatch.setenv("MBF_BAM_WINDOW_MB", "1")
+    mb.release_device(0)
+    try:
+        assert getattr(mb, BY_BARCODE)(path, None, iv, giv, "straight") == want
+        assert mb.last_stats()["n_windows"] > 2
+        parts = []
+        for s in range(3):   # chunk-range shards: entries are per chunk, so the shard lists concatenate
+            rd = mb.Reader(path)
+            rd.set_device(0)
+            rd.set_shard(s, 3)
+            parts += as_set(getattr(rd, BY_BARCODE)(iv, giv, "straight"))
+        assert sorted(parts) == as_set(want)
     finally:
         monkeypatch.delenv("MBF_BAM_WINDOW_MB")
         mb.release_device(0)
