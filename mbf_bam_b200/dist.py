@@ -135,3 +135,72 @@ def count_introns(filename, index_filename=None, group=None, device: Optional[in
     part = _part(rd) if _part is not None else rd.count_introns()
     _last_stats = rd.stats()
     return merge_introns(part, group)
+
+
+def merge_quantify(part, group=None):
+    """reference src/count_reads/quantify.rs:189-203 add_hashmaps over the ranks: per gene id the position lists of the
+    shards are disjoint (a position belongs to one chunk) and are concatenated"""
+    dist = _dist()
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, part, group=group)
+    out = ({}, {})
+    for p in parts:
+        for b in (0, 1):
+            for gene, lst in p[b].items():
+                out[b].setdefault(gene, []).extend(lst)
+    return tuple({g: sorted(l) for g, l in o.items()} for o in out)
+
+
+def merge_hist(part: dict, group=None) -> dict:
+    """reference src/duplicate_distribution.rs:8-14 add_hashmaps over the ranks"""
+    dist = _dist()
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, part, group=group)
+    out: dict = {}
+    for p in parts:
+        for k, v in p.items():
+            out[k] = out.get(k, 0) + v
+    return out
+
+
+def merge_by_barcode(part, group=None):
+    """reference src/count_reads/by_barcode.rs:74-92 over the ranks' entry lists, in rank (= chunk) order"""
+    dist = _dist()
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, part, group=group)
+    genes, barcodes, counts = {}, {}, []
+    for g_names, b_names, entries in parts:
+        for gi, bi, n in entries:
+            g = genes.setdefault(g_names[gi], len(genes))
+            b = barcodes.setdefault(b_names[bi], len(barcodes))
+            counts.append((g, b, n))
+    return list(genes), list(barcodes), counts
+
+
+def quantify_gene_reads(filename, index_filename, intervals, gene_intervals, group=None, device: Optional[int] = None, _part=None):
+    """reference src/lib.rs:247-264, sharded over the ranks of `group`"""
+    global _last_stats
+    rd = _reader(filename, index_filename, group, device)
+    part = _part(rd) if _part is not None else rd.quantify_gene_reads(intervals, gene_intervals)
+    _last_stats = rd.stats()
+    return merge_quantify(part, group)
+
+
+def calculate_duplicate_distribution(filename, index_filename=None, group=None, device: Optional[int] = None, _part=None):
+    """reference src/lib.rs:108-116, sharded over the ranks of `group`"""
+    global _last_stats
+    rd = _reader(filename, index_filename, group, device)
+    part = _part(rd) if _part is not None else rd.calculate_duplicate_distribution()
+    _last_stats = rd.stats()
+    return merge_hist(part, group)
+
+
+def count_reads_primary_only_right_strand_only_by_barcode(filename, index_filename, intervals, gene_intervals, umi_strategy,
+                                                          group=None, device: Optional[int] = None, _part=None):
+    """reference src/lib.rs:184-211, sharded over the ranks of `group`"""
+    global _last_stats
+    rd = _reader(filename, index_filename, group, device)
+    part = _part(rd) if _part is not None else rd.count_reads_primary_only_right_strand_only_by_barcode(
+        intervals, gene_intervals, umi_strategy)
+    _last_stats = rd.stats()
+    return merge_by_barcode(part, group)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT, make_case
-from oracle import c_oracle
+from oracle import c_oracle, py_oracle
 
 
 def test_shard_plan_partitions_the_chunk_table(built, tmp_path):
@@ -130,6 +130,23 @@ def _rank_main(rank, world, port, path, iv, giv, out_q):
     whole_box = []
     res["introns"] = mbd.count_introns(path, _part=lambda rd: (lambda pw: (whole_box.append(pw[1]), pw[0])[1])(introns_part(rd)))
     res["introns_whole"] = whole_box[0]
+    # the 8(f) rows: the Python restatement's whole-job result, cut into per-rank parts, stands in for the device parts
+    from oracle import py_oracle
+
+    q_whole = py_oracle.quantify_gene_reads(path, None, iv, giv)
+    q_part = tuple({g: [t for t in lst if (t[0] // 1000) % world == rank] for g, lst in d.items()} for d in q_whole)
+    res["quantify"] = mbd.quantify_gene_reads(path, None, iv, giv, _part=lambda rd: q_part)
+    h_whole = py_oracle.calculate_duplicate_distribution(path)
+    h_part = {k: v // world + (1 if rank < v % world else 0) for k, v in h_whole.items()}
+    res["dups"] = mbd.calculate_duplicate_distribution(path, _part=lambda rd: {k: v for k, v in h_part.items() if v})
+    fn = "count_reads_primary_only_right_strand_only_by_barcode"
+    b_whole = getattr(py_oracle, fn)(path, None, iv, giv, "straight")
+    half = len(b_whole[2]) // 2
+    mine = b_whole[2][:half] if rank == 0 else b_whole[2][half:]
+    g_loc, b_loc, e_loc = {}, {}, []
+    for gi, bi, n in mine:   # rank-local index space, as a shard's own call would return it
+        e_loc.append((g_loc.setdefault(b_whole[0][gi], len(g_loc)), b_loc.setdefault(b_whole[1][bi], len(b_loc)), n))
+    res["barcode"] = getattr(mbd, fn)(path, None, iv, giv, "straight", _part=lambda rd: (list(g_loc), list(b_loc), e_loc))
     out_q.put((rank, res))
     dist.destroy_process_group()
 
@@ -139,7 +156,9 @@ def test_two_rank_merge_over_gloo(built, tmp_path):
     intron maps gathered and merged, EVERY rank gets the whole-job dicts; must equal the single-process oracle."""
     import torch.multiprocessing as mp
 
-    path, contigs, recs, iv, giv = make_case(tmp_path, 42, n_reads=8_000, n_contigs=3)
+    from test_next_rows import barcode_case  # XC/XM tags, duplicates, and chunks the by-barcode counter drops
+
+    path, contigs, recs, iv, giv = barcode_case(tmp_path, 42, n_reads=8_000, n_contigs=3)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -159,3 +178,7 @@ def test_two_rank_merge_over_gloo(built, tmp_path):
         for a, b in zip(res["weighted"], want_w):
             assert set(a) == set(b) and all(abs(a[k] - b[k]) <= 1e-9 * max(1.0, abs(b[k])) for k in a)
         assert res["introns"] == res["introns_whole"] == c_oracle.count_introns(path)
+        assert res["quantify"] == py_oracle.quantify_gene_reads(path, None, iv, giv)
+        assert res["dups"] == py_oracle.calculate_duplicate_distribution(path)
+        assert len(res["barcode"][2]) > 20
+        assert res["barcode"] == getattr(py_oracle, "count_reads_primary_only_right_strand_only_by_barcode")(path, None, iv, giv, "straight")
