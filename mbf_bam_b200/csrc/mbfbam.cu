@@ -18,6 +18,7 @@
 #include <atomic>
 #include <chrono>
 #include <thread>
+#include <list>
 #include <map>
 #include <memory>
 #include <functional>
@@ -956,7 +957,8 @@ struct Pipeline {
         //  * streamed jobs grow x1.5 per window until W: the bytes of window k+1 are staged while the GPU
         //    works on window k, so a window must not take longer to stage than its predecessor takes to
         //    process (a full-size second window would leave the GPU idle for ~10 ms).
-        const bool ramp = !src->resident(device) && !(ranges.size() && src->host_pinned(ranges[0].cbeg, 1));
+        const bool ramp = (!src->resident(device) && !(ranges.size() && src->host_pinned(ranges[0].cbeg, 1))) ||
+                          (!src->resident(device) && env_u32("MBF_BAM_RAMP_PINNED", 0) != 0);
         size_t ri = 0;
         uint64_t pos = ranges.empty() ? 0 : ranges[0].cbeg;
         bool first_of_range = true;
@@ -1323,6 +1325,44 @@ void build_count_tables(const Reader& r, const mbfbam_count_job* job, CountTable
     T.slot_iv_off[T.slot_iv.size()] = (uint32_t)T.ivs.size();
 }
 
+// The tables are a pure function of (BAM header, intervals, gene_intervals, each_read_counts_once), and callers count
+// many files and functions against one annotation: the last few results are kept, keyed by the CONTENT of the inputs
+// (a byte-for-byte copy is compared on lookup, so a hit is exact).  Building takes ~6 ms for 20 k genes / 60 k
+// intervals (the replay of bio's tree for the chunk edges is most of it); a lookup ~0.1 ms.
+std::shared_ptr<const CountTables> cached_count_tables(const Reader& r, const mbfbam_count_job* job) {
+    std::string key;
+    auto put = [&](const void* p, size_t n) { key.append((const char*)p, n); };
+    auto put_iv = [&](const mbfbam_intervals* iv) {
+        put(&iv->n_contigs, 4);
+        for (int c = 0; c < iv->n_contigs; c++) { key.append(iv->contig_names[c]); key.push_back('\0'); }
+        const size_t n = (size_t)iv->iv_offsets[iv->n_contigs];
+        put(iv->n_genes, (size_t)iv->n_contigs * 4);
+        put(iv->iv_offsets, ((size_t)iv->n_contigs + 1) * 8);
+        put(iv->iv_start, n * 4); put(iv->iv_end, n * 4); put(iv->iv_gene, n * 4); put(iv->iv_strand, n);
+    };
+    const int32_t once = job->each_read_counts_once ? 1 : 0;
+    put(&once, 4);
+    for (size_t t = 0; t < r.names.size(); t++) { key.append(r.names[t]); key.push_back('\0'); put(&r.lens[t], 4); }
+    put_iv(job->intervals);
+    put_iv(job->gene_intervals);
+    static std::mutex mu;
+    static std::list<std::pair<std::string, std::shared_ptr<const CountTables>>> cache;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto it = cache.begin(); it != cache.end(); ++it)
+            if (it->first.size() == key.size() && it->first == key) {
+                cache.splice(cache.begin(), cache, it);
+                return cache.front().second;
+            }
+    }
+    auto T = std::make_shared<CountTables>();
+    build_count_tables(r, job, *T);
+    std::lock_guard<std::mutex> lk(mu);
+    cache.emplace_front(std::move(key), T);
+    while (cache.size() > 4) cache.pop_back();
+    return T;
+}
+
 void upload_count_tables(Pipeline& p, const CountTables& T, const ShardPlan& plan, bool with_rank) {
     CountCtx& c = p.cc;
     c.tid2slot = upload(p.d_tid2slot, T.tid2slot, p.s_main);
@@ -1350,10 +1390,14 @@ struct CountPart {
 void count_on_device(mbfbam_reader* rd, const CountTables& T, const mbfbam_count_job* job, int device, int shard, int nshards,
                      int read_threads, uint64_t prior_jobs, CountPart& out) {
     const Reader& r = rd->r;
+    const double t_a = now_ms();
     ShardPlan plan;
     plan.chunks = T.chunks;
     plan_shard(r, plan, shard, nshards);
+    const double t_b = now_ms();
     const double ms_pin = maybe_pin(rd, plan.ranges, prior_jobs);
+    const double t_c = now_ms();
+    double t_setup = 0, t_run = 0;
     const size_t G = T.G;
     const size_t n_words = (job->mode == MBFBAM_MODE_WEIGHTED ? (size_t)NH_DENSE * 2 : 2) * std::max<size_t>(G, 1);
     FileSource src(&r, rd->fmap);
@@ -1378,7 +1422,9 @@ void count_on_device(mbfbam_reader* rd, const CountTables& T, const mbfbam_count
         c.wspill = p.d_wspill.as<double>();
         CK(cudaStreamSynchronize(p.s_main));  // the tables are read by kernels on other streams too
         p.st.n_chunks = plan.hi - plan.lo;
+        t_setup = now_ms();
     });
+    t_run = now_ms();
     out.h.resize(n_words);
     CK(cudaMemcpy(out.h.data(), p.d_counts.p, n_words * 8, cudaMemcpyDeviceToHost));
     p.st.d2h_bytes += n_words * 8;
@@ -1391,6 +1437,9 @@ void count_on_device(mbfbam_reader* rd, const CountTables& T, const mbfbam_count
     p.st.ms_pin = ms_pin;
     p.st.n_devices = 1;
     out.st = p.st;
+    if (env_u32("MBF_BAM_TRACE", 0))
+        fprintf(stderr, "[mbfbam] device %d: plan %.2f ms, pin check %.2f ms, lock+setup %.2f ms, run %.2f ms (gpu %.2f), results %.2f ms\n",
+                device, t_b - t_a, t_c - t_b, t_setup - t_c, t_run - t_setup, p.st.ms_gpu_all, now_ms() - t_run);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1772,8 +1821,9 @@ int mbfbam_count_reads(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_co
         if (cudaGetDeviceCount(&ndev_have) != cudaSuccess || ndev_have == 0)
             throw Error(MBFBAM_ERR_CUDA, "no CUDA device available; mbf_bam_b200 has no CPU path");
         const std::vector<int> devs = job_devices(job->devices, job->n_devices, job->device);
-        CountTables T;
-        build_count_tables(r, job, T);
+        const std::shared_ptr<const CountTables> Tp = cached_count_tables(r, job);
+        const CountTables& T = *Tp;
+        const double t_tables = now_ms();
         if (out->scanned) {
             memset(out->scanned, 0, (size_t)iv->n_contigs);
             for (int c : T.slot_iv) out->scanned[c] = 1;
@@ -1787,6 +1837,7 @@ int mbfbam_count_reads(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_co
         fan_out(devs.size(), [&](size_t k) {
             count_on_device(rd, T, job, devs[k], sh * (int)devs.size() + (int)k, nsh * (int)devs.size(), rt, prior, parts[k]);
         });
+        const double t_dev = now_ms();
         // gather on the host (dense vectors are summed; multi-mapper sets are chunk-local, so shards
         // never share a set)
         const size_t G = T.G;
@@ -1822,6 +1873,8 @@ int mbfbam_count_reads(mbfbam_reader* rd, const mbfbam_count_job* job, mbfbam_co
             }
         }
         st.ms_total = now_ms() - t0;
+        if (env_u32("MBF_BAM_TRACE", 0))
+            fprintf(stderr, "[mbfbam] count_reads: tables %.2f ms, devices %.2f ms, gather %.2f ms\n", t_tables - t0, t_dev - t_tables, now_ms() - t_dev);
         if (stats) *stats = st;
     });
 }
@@ -1861,15 +1914,18 @@ int mbfbam_count_introns_multi(mbfbam_reader* rd, const int32_t* devices, int32_
             for (size_t t = 0; t < n_ref; t++) out->contig_seen[t] |= pt.seen[t];
             merge_stats(st, pt.st);
         }
-        std::sort(all.begin(), all.end(), [](const IntronEntry& a, const IntronEntry& b) {
-            if (a.tid != b.tid) return a.tid < b.tid;
-            if (a.start != b.start) return a.start < b.start;
-            return a.stop < b.stop;
-        });
-        size_t n = 0;
-        for (size_t i = 0; i < all.size(); i++) {
-            if (n && all[n - 1].tid == all[i].tid && all[n - 1].start == all[i].start && all[n - 1].stop == all[i].stop) all[n - 1].count += all[i].count;
-            else all[n++] = all[i];
+        size_t n = all.size();
+        if (parts.size() > 1) {  // (one device: the map's keys are unique already)
+            std::sort(all.begin(), all.end(), [](const IntronEntry& a, const IntronEntry& b) {
+                if (a.tid != b.tid) return a.tid < b.tid;
+                if (a.start != b.start) return a.start < b.start;
+                return a.stop < b.stop;
+            });
+            n = 0;
+            for (size_t i = 0; i < all.size(); i++) {
+                if (n && all[n - 1].tid == all[i].tid && all[n - 1].start == all[i].start && all[n - 1].stop == all[i].stop) all[n - 1].count += all[i].count;
+                else all[n++] = all[i];
+            }
         }
         out->tid = (int32_t*)malloc((n + 1) * 4);
         out->start = (uint32_t*)malloc((n + 1) * 4);
@@ -1907,8 +1963,8 @@ int mbfbam_quantify_gene_reads(mbfbam_reader* rd, const mbfbam_count_job* job, m
         const std::vector<int> devs = job_devices(job->devices, job->n_devices, job->device);
         mbfbam_count_job j2 = *job;
         j2.each_read_counts_once = 0;
-        CountTables T;
-        build_count_tables(r, &j2, T);
+        const std::shared_ptr<const CountTables> Tp = cached_count_tables(r, &j2);
+        const CountTables& T = *Tp;
         const int nsh = std::max(1, job->shard_count), sh = job->shard_index;
         if (sh < 0 || sh >= nsh) throw Error(MBFBAM_ERR_ARG, "bad shard index/count");
         const uint64_t prior = rd->fmap ? rd->fmap->jobs.fetch_add(1) : 0;
@@ -1999,8 +2055,8 @@ int mbfbam_count_by_barcode(mbfbam_reader* rd, const mbfbam_count_job* job, mbfb
         const std::vector<int> devs = job_devices(job->devices, job->n_devices, job->device);
         mbfbam_count_job j2 = *job;
         j2.each_read_counts_once = 0;
-        CountTables T;
-        build_count_tables(r, &j2, T);
+        const std::shared_ptr<const CountTables> Tp = cached_count_tables(r, &j2);
+        const CountTables& T = *Tp;
         const int nsh = std::max(1, job->shard_count), sh = job->shard_index;
         if (sh < 0 || sh >= nsh) throw Error(MBFBAM_ERR_ARG, "bad shard index/count");
         const uint64_t prior = rd->fmap ? rd->fmap->jobs.fetch_add(1) : 0;

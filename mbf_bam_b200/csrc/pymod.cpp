@@ -483,12 +483,22 @@ struct PyReader {
         std::vector<py::dict> per(res.n_targets > 0 ? (size_t)res.n_targets : 0);
         for (int32_t t = 0; t < res.n_targets; t++)
             if (res.contig_seen[t]) out[py::str(mbfbam_target_name(r, t))] = per[(size_t)t];
-        for (uint64_t i = 0; i < res.n; i++) {
+        // every (tid, start, stop) appears once in the result (include/mbfbam.h): plain inserts, plain CPython calls --
+        // a whole-transcriptome file yields 10^5..10^7 keys and this loop is then most of the call
+        bool failed = false;
+        for (uint64_t i = 0; i < res.n && !failed; i++) {
             py::dict& d = per[(size_t)res.tid[i]];
-            py::tuple key = py::make_tuple(res.start[i], res.stop[i]);
-            if (d.contains(key)) d[key] = py::int_(py::cast<uint64_t>(d[key]) + res.count[i]);
-            else d[key] = py::int_(res.count[i]);
-            if (!res.contig_seen[res.tid[i]]) out[py::str(mbfbam_target_name(r, res.tid[i]))] = d;
+            PyObject* a = PyLong_FromUnsignedLong(res.start[i]);
+            PyObject* b = PyLong_FromUnsignedLong(res.stop[i]);
+            PyObject* v = PyLong_FromUnsignedLongLong(res.count[i]);
+            PyObject* key = (a && b) ? PyTuple_Pack(2, a, b) : nullptr;
+            if (!key || !v || PyDict_SetItem(d.ptr(), key, v) != 0) failed = true;
+            Py_XDECREF(a); Py_XDECREF(b); Py_XDECREF(v); Py_XDECREF(key);
+            if (!failed && !res.contig_seen[res.tid[i]]) out[py::str(mbfbam_target_name(r, res.tid[i]))] = d;
+        }
+        if (failed) {
+            mbfbam_free_introns(&res);
+            throw py::error_already_set();
         }
         mbfbam_free_introns(&res);
         return out;

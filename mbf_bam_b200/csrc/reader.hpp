@@ -329,6 +329,7 @@ struct SortedIntervals {
     std::vector<uint32_t> start, end, pmax, gene;  // gene = local gene_no
     std::vector<int8_t> strand;
     std::vector<uint32_t> rank;  // position in bio's find() iteration order (only when asked for)
+    std::vector<uint32_t> orig;  // index of the interval in the contig's list (insertion order)
 };
 
 // bio 0.25 IntervalTree (Cargo.lock:100-101; source not vendored, restated from SURVEY.md App. B.2): an AVL tree
@@ -387,13 +388,17 @@ inline std::vector<uint32_t> bio_tree_ranks(const uint32_t* starts, size_t n) {
             if (child < 0) { child = (int32_t)i; break; }
             cur = child;
         }
-        // repair bottom-up; a rotation changes the subtree root, which the parent must point to
+        // repair bottom-up; a rotation changes the subtree root, which the parent must point to.  bio repairs every
+        // node of the path; a node whose subtree keeps its root and its height leaves everything above it as it
+        // was, so the walk may stop there (same tree, a fifth of the work)
         for (size_t d = path.size(); d-- > 0;) {
             const int32_t x = path[d];
+            const int old_h = nd[(size_t)x].h;
             const int32_t nr = repair(x);
             if (d == 0) root = nr;
             else if (went_left[d - 1]) nd[(size_t)path[d - 1]].l = nr;
             else nd[(size_t)path[d - 1]].r = nr;
+            if (nr == x && nd[(size_t)x].h == old_h) break;
         }
     }
     std::vector<uint32_t> rank(n, 0);
@@ -411,28 +416,34 @@ inline std::vector<uint32_t> bio_tree_ranks(const uint32_t* starts, size_t n) {
 }
 
 inline SortedIntervals sort_intervals(const mbfbam_intervals* iv, int c, bool with_rank = false) {
-    uint64_t a = iv->iv_offsets[c], b = iv->iv_offsets[c + 1];
-    std::vector<uint32_t> order((size_t)(b - a));
-    for (size_t i = 0; i < order.size(); i++) order[i] = (uint32_t)i;
-    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-        if (iv->iv_start[a + x] != iv->iv_start[a + y]) return iv->iv_start[a + x] < iv->iv_start[a + y];
-        if (iv->iv_end[a + x] != iv->iv_end[a + y]) return iv->iv_end[a + x] < iv->iv_end[a + y];
-        return x < y;
-    });
+    const uint64_t a = iv->iv_offsets[c], b = iv->iv_offsets[c + 1];
+    const size_t n = (size_t)(b - a);
+    // (start, end, list index) packed into sortable keys: 64 bits of (start, end), ties by list index
+    struct Key { uint64_t se; uint32_t idx; };
+    std::vector<Key> keys(n);
+    bool sorted = true;
+    for (size_t i = 0; i < n; i++) {
+        keys[i] = {((uint64_t)iv->iv_start[a + i] << 32) | iv->iv_end[a + i], (uint32_t)i};
+        if (i && keys[i].se < keys[i - 1].se) sorted = false;
+    }
+    if (!sorted) std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) { return x.se != y.se ? x.se < y.se : x.idx < y.idx; });
     SortedIntervals s;
+    s.start.resize(n); s.end.resize(n); s.pmax.resize(n); s.gene.resize(n); s.strand.resize(n); s.orig.resize(n);
     std::vector<uint32_t> ranks;
-    if (with_rank) ranks = bio_tree_ranks(iv->iv_start + a, order.size());
+    if (with_rank) { ranks = bio_tree_ranks(iv->iv_start + a, n); s.rank.resize(n); }
     uint32_t m = 0;
-    for (uint32_t o : order) {
-        uint32_t st = iv->iv_start[a + o], en = iv->iv_end[a + o];
+    for (size_t k = 0; k < n; k++) {
+        const uint32_t o = keys[k].idx;
+        const uint32_t st = iv->iv_start[a + o], en = iv->iv_end[a + o];
         if (st > en) throw Error(MBFBAM_ERR_ARG, "interval start > end");  // bio panics here
-        s.start.push_back(st);
-        s.end.push_back(en);
-        s.gene.push_back(iv->iv_gene[a + o]);
-        s.strand.push_back(iv->iv_strand[a + o]);
-        if (with_rank) s.rank.push_back(ranks[o]);
+        s.start[k] = st;
+        s.end[k] = en;
+        s.gene[k] = iv->iv_gene[a + o];
+        s.strand[k] = iv->iv_strand[a + o];
+        s.orig[k] = o;
+        if (with_rank) s.rank[k] = ranks[o];
         m = std::max(m, en);
-        s.pmax.push_back(m);
+        s.pmax[k] = m;
     }
     return s;
 }
@@ -440,18 +451,30 @@ inline SortedIntervals sort_intervals(const mbfbam_intervals* iv, int c, bool wi
 // chunked_genome.rs:93-109: push the chunk's right edge past a gene interval covering it.  When several
 // cover it the reference takes the FIRST entry bio's find(stop..stop+1) yields, i.e. the covering interval of
 // least rank in the tree's iteration order (bio_tree_ranks above).
-inline uint32_t extend_stop(const SortedIntervals& g, uint32_t stop) {
+// The ranks are only needed where two or more intervals cover an edge, so the tree is replayed (20 k inserts take
+// milliseconds) only for contigs where that happens: `ranks()` fills g.rank on first use.
+template <class R>
+inline uint32_t extend_stop(SortedIntervals& g, uint32_t stop, R&& ranks) {
     for (;;) {
         size_t hi = (size_t)(std::upper_bound(g.start.begin(), g.start.end(), stop) - g.start.begin());  // start <= stop
-        uint32_t best_rank = 0xffffffffu, best_end = 0;
+        size_t n_cover = 0, only = 0;
         for (size_t i = hi; i-- > 0;) {
             if (g.pmax[i] <= stop) break;
-            if (g.end[i] > stop && g.rank[i] < best_rank) {
-                best_rank = g.rank[i];
-                best_end = g.end[i];
+            if (g.end[i] > stop) { n_cover++; only = i; }
+        }
+        if (n_cover == 0) return stop;
+        uint32_t best_end = g.end[only];
+        if (n_cover > 1) {
+            if (g.rank.empty()) ranks();
+            uint32_t best_rank = 0xffffffffu;
+            for (size_t i = hi; i-- > 0;) {
+                if (g.pmax[i] <= stop) break;
+                if (g.end[i] > stop && g.rank[i] < best_rank) {
+                    best_rank = g.rank[i];
+                    best_end = g.end[i];
+                }
             }
         }
-        if (best_rank == 0xffffffffu) return stop;
         stop = best_end + 1;
     }
 }
@@ -467,12 +490,17 @@ inline std::vector<Chunk> make_chunks(const Reader& r, const mbfbam_intervals* g
             auto it = r.name2tid.find(genes->contig_names[c]);
             if (it == r.name2tid.end()) continue;  // chunked_genome.rs:21-25
             tid = it->second;
-            g = sort_intervals(genes, c, true);
+            g = sort_intervals(genes, c, false);
         }
         uint32_t len = r.lens[(size_t)tid], start = 0;
         do {
             uint32_t stop = start + CHUNK_SIZE;
-            if (genes) stop = extend_stop(g, stop);
+            if (genes)
+                stop = extend_stop(g, stop, [&] {
+                    const std::vector<uint32_t> rk = bio_tree_ranks(genes->iv_start + genes->iv_offsets[c], g.orig.size());
+                    g.rank.resize(g.orig.size());
+                    for (size_t i = 0; i < g.orig.size(); i++) g.rank[i] = rk[g.orig[i]];
+                });
             out.push_back({tid, start, stop});
             start = stop;
         } while (start < len);

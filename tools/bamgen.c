@@ -291,6 +291,28 @@ static const exon_t* junction_exon(int c, uint32_t p) {
     return NULL;
 }
 
+/* Spliced reads sit on junctions, and junctions are shared by many reads (RNA-seq: ~10^5 distinct junctions for 10^7-10^8
+ * spliced reads): move a read that is to be spliced onto the nearest exon end (of an exon with a successor) that keeps it
+ * inside its bin [lo, hi) and within 50 kb of where it was; `off` in [1, L-1] is how much of the read lies before the
+ * junction.  Returns 0 when there is no such exon: the read then stays unspliced. */
+static int snap_to_junction(int c, uint32_t pos, uint32_t lo, uint32_t hi, uint32_t off, uint32_t* out) {
+    exon_t* ex = cexons[c]; uint32_t ne = n_cexons[c];
+    uint32_t a = 0, b = ne;
+    while (a < b) { uint32_t m = (a + b) / 2; if (ex[m].s <= pos) a = m + 1; else b = m; }
+    uint32_t from = a > 12 ? a - 12 : 0, to = a + 24 < ne ? a + 24 : ne;
+    uint32_t best = 0xffffffffu, best_d = 50000u;
+    for (uint32_t i = from; i < to; i++) {
+        if (ex[i].idx + 1 >= genes[ex[i].gene].n_exons || ex[i].e <= off) continue;
+        uint32_t np = ex[i].e - off;
+        if (np < lo || np >= hi || np + off <= ex[i].s) continue;  /* the part before the junction stays inside the exon */
+        uint32_t d = np > pos ? np - pos : pos - np;
+        if (d < best_d) { best_d = d; best = np; }
+    }
+    if (best == 0xffffffffu) return 0;
+    *out = best;
+    return 1;
+}
+
 static int build_cigar(int c, read_t* r, uint32_t* cg, uint32_t* reflen, rng_t* rg) {
     int L = opt_readlen;
     if (r->kind == 3) { *reflen = 0; return 0; }
@@ -372,7 +394,13 @@ static void run_task(task_t* t) {
             r.flag = rev ? 16 : 0;
             if (u < opt_edge * 0.1) { r.kind = 3; r.flag |= 4; r.mapq = 0; }
             else if (u < opt_edge) r.kind = 2;
-            else if (u < opt_edge + opt_spliced) r.kind = 1;
+            else if (u < opt_edge + opt_spliced) {
+                uint32_t np;
+                if (snap_to_junction(c, r.pos, lo, hi < maxpos ? hi : maxpos, 1u + (uint32_t)((x >> 36) % (uint32_t)(opt_readlen - 1)), &np)) {
+                    r.pos = np;
+                    r.kind = 1;
+                }
+            }
             rs[k++] = r;
         }
     }

@@ -18,5 +18,10 @@ else:
     rd.count_reads(1, iv, giv)  # warm the pipeline buffers
 f, r = rd.count_reads(1, iv, giv)
 st = rd.stats()
+import json  # noqa: E402
+
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+with open(os.path.join(ROOT, "gpurun_out", "profile_stats.json"), "w") as fh:
+    json.dump({k: st[k] for k in ("n_records", "n_bgzf_blocks", "compressed_bytes", "uncompressed_bytes", "n_tokens", "n_windows")}, fh)
 print("records", st["n_records"], "launches", st["n_kernel_launches"], "fwd", f["_total"], "rev", r["_total"],
       {k: round(v, 2) for k, v in st.items() if k.startswith("ms_")})
