@@ -14,19 +14,22 @@
 //           the distance table (two-level: 9 / 8 root bits, second-level tables for longer codes -- a long code
 //           costs one more shared load instead of the canonical search's ~100 instructions)
 //   guess   lane i decodes from the first bit of sub-sequence i (lane 0 from the true start) until it has crossed
-//           into sub-sequence i+1.  It keeps what it decodes: the tokens go to a lane-private scratch area in HBM
-//           (L2 resident), and every bit position where a token started is MARKED in a bitmap that parallels the
-//           staged words; it publishes where it stopped
-//   sync    every lane whose predecessor stopped somewhere else restarts there -- but only until it steps onto a
-//           marked position: from there on its path IS the guess path (a decoder's state is its bit position), so
-//           the guess run's tokens and exit are reused.  Measured on the bench files (sub-sequences of 1312 bits,
-//           122 tokens): the true chain meets the guess path after 10 tokens on average, 97 % within 12 words, and
-//           0.09 % of the lanes never do (they decode to the end of their stretch).  Repeated until nobody moves.
-//           Converged <=> every lane started where its predecessor stopped <=> the chain is the true one
-//           (induction from lane 0), whatever the data: speculation is verified, never trusted
-//   emit    token counts -> exclusive scan -> every lane copies [its sync run's tokens][the guess run's tokens from
-//           the merge point on] to the member's token list.  A token is decoded once (plus the short sync runs);
-//           the first form of this kernel decoded everything three times (guess, sync, emit)
+//           into sub-sequence i+1, counts its tokens and publishes where it stopped.  On the way it leaves a
+//           CHECKPOINT behind every 256-bit boundary of its stretch: the first token start after the boundary and the
+//           number of tokens before it
+//   sync    every lane whose predecessor stopped somewhere else restarts there -- but only until it steps exactly onto
+//           a checkpoint: from there on its path IS the guess path (a decoder's state is its bit position), so the
+//           guess run's count and exit are reused.  Measured on the bench files (tools/selfsync_sim.cpp and a variant of
+//           it; sub-sequences of 1312 bits = 122 tokens): the true chain meets the guess path after 10 tokens on
+//           average, 97 % within 12 words, and 0.09 % of the lanes never do (they decode to the end of their stretch).
+//           Repeated until nobody moves.  Converged <=> every lane started where its predecessor stopped <=> the
+//           chain is the true one (induction from lane 0), whatever the data: speculation is verified, never trusted
+//   emit    token counts -> exclusive scan -> every lane decodes its stretch once more and writes its tokens
+//           (three-decode scheme, the default).  Single-decode scheme (ONEPASS): the guess and sync runs keep their
+//           tokens in a transposed scratch area in HBM (token k of lane j at [32 k + j]: a warp's lanes write whole
+//           lines) and emit is a copy, [the sync run's tokens][the guess run's tokens from the checkpoint on], through
+//           shared-memory tiles.  It issues 15 % fewer instructions and is no faster (measured): every trip
+//           then carries the token arithmetic and a store
 //
 // Stored blocks, members whose tables overflow the second-level pool, and anything that looks corrupt are
 // appended to a fallback list and decoded by k_tokens_bf, which also produces the precise error codes.
@@ -49,6 +52,10 @@ constexpr uint32_t PF_EOB = 1u << 31, PF_INV = 1u << 30, PF_DEAD = 1u << 29;  //
 constexpr uint32_t PF_MERGED = 1u << 28;  // (sync run only, never published) stopped on a marked position
 constexpr uint32_t PF_ANY = PF_EOB | PF_INV | PF_DEAD;
 constexpr int PT_SW_MIN = 5;        // shortest sub-sequence in words
+// Three-decode scheme: the guess run remembers, for every 256 bits of its stretch, the first token start behind that
+// boundary and how many tokens came before it (one word per checkpoint); a sync run that steps exactly onto a
+// checkpoint has met the guess path and stops there.
+__host__ __device__ constexpr int par_ncp(int sw_max) { return (sw_max * 32 + 255) >> 8; }
 // tokens one run may keep: 2 bits per token over the longest sub-sequence (a match costs at least 2); a run that
 // would need more is reported as invalid and the member goes to the fallback kernel
 __host__ __device__ constexpr uint32_t par_scratch_cap(int sw_max) { return (uint32_t)sw_max * 16u; }
@@ -60,7 +67,7 @@ struct ParShared {
     uint32_t sub[PT_SUB_CAP];        // during header parsing: scratch of the code-length code
     uint32_t zero;                   // the "distance entry" of a literal: consumes nothing
     uint32_t cb[NT * SW_MAX + 16];   // staged compressed words
-    uint32_t mk[ONEPASS ? NT * SW_MAX + 16 : 1];  // bit b of mk[w]: the guess run of the lane owning word w started a token at bit b of cb[w]
+    uint32_t mk[NT * par_ncp(SW_MAX)];  // par_ncp(SW_MAX) checkpoints per lane
     uint32_t exitb[NT + 1];          // exitb[i+1]: where lane i stopped | flags; exitb[0]: the true start
     uint32_t wsum[NT / 32];
     uint32_t run[2][16], first[2][16];
@@ -289,19 +296,23 @@ __device__ __forceinline__ uint32_t lds_if_special(uint32_t e, uint32_t addr) {
     return e;
 }
 
-// MODE PR_COUNT   decode and count (three-decode scheme: guess and sync runs)
-//      PR_EMIT    decode and write the tokens to tk[0], tk[1], ... (three-decode scheme: emit run)
-//      PR_GUESS   single-decode scheme, guess run: marks the bit position of every token it starts (s_mk parallels
-//                 s_cb) and keeps token k in tk[32 k] (a warp's lanes all write row k in trip k: one 128-byte line)
-//      PR_SYNC    single-decode scheme, sync run: as PR_GUESS without marking, but stops, without decoding, on the
-//                 first marked position (result | PF_MERGED; n_out = tokens before it)
+// MODE PR_COUNT    decode and count
+//      PR_EMIT     decode and write the tokens to tk[0], tk[1], ... (three-decode scheme: emit run)
+//      PR_COUNT_CP guess run: count, and leave a checkpoint (position | tokens before it << 12, in the lane's words at
+//                  s_mk) at the first token start behind every 256-bit boundary of the stretch
+//      PR_SYNC_CP  sync run: count until the position equals a checkpoint (result | PF_MERGED, n_out = tokens before it,
+//                  aux = the guess run's tokens before it) or the stretch ends
+//      PR_GUESS    single-decode scheme: PR_COUNT_CP that also keeps token k in tk[32 k] (a warp's lanes all write row k
+//                  in trip k: one 128-byte line)
+//      PR_SYNC     single-decode scheme: PR_SYNC_CP that also keeps its tokens
 // A keeping run that fills `cap` token slots ends as invalid.
-enum { PR_COUNT = 0, PR_EMIT = 1, PR_GUESS = 2, PR_SYNC = 3 };
+enum { PR_COUNT = 0, PR_EMIT = 1, PR_GUESS = 2, PR_SYNC = 3, PR_COUNT_CP = 4, PR_SYNC_CP = 5 };
 template <int MODE>
 __device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t s_mk, uint32_t cw0_bits, uint32_t s_ll, uint32_t s_d,
                                             uint32_t s_sub, uint32_t s_zero, uint32_t start_bp, uint32_t end_bp, uint32_t cap,
-                                            uint32_t& n_out, uint32_t* tk) {
+                                            uint32_t& n_out, uint32_t* tk, uint32_t base_rel = 0, uint32_t* aux = nullptr) {
     constexpr bool KEEP = MODE == PR_GUESS || MODE == PR_SYNC;
+    constexpr bool CP = MODE != PR_COUNT && MODE != PR_EMIT;
     constexpr uint32_t TK_STEP = KEEP ? 32u : 1u;
     uint32_t pos = start_bp - cw0_bits;  // bits from the first staged word
     uint32_t lim = end_bp - cw0_bits;    // set to 0 to leave the loop
@@ -309,7 +320,7 @@ __device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t s_mk, uint32
     uint32_t lo = lds_u32(a), hi = lds_u32(a + 4), nx = lds_u32(a + 8);
     a += 12;
     uint32_t n = 0, flags = 0;
-    uint32_t mk_word = 0xffffffffu, mk_acc = 0;  // PR_GUESS: the mark word being filled
+    uint32_t cp_j = 0, cp_v = 0;                 // PR_COUNT_CP / PR_SYNC_CP: 256-bit region of the stretch, its checkpoint
     // One trip = one token, one straight-line instruction sequence whatever the token is: literal/length
     // lookup, second-level lookup (predicated load), distance lookup (a literal reads a zero word), second-level
     // lookup, predicated token store, window advance.  End of block and invalid codes are table entries of their
@@ -317,15 +328,14 @@ __device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t s_mk, uint32
     while (pos < lim) {
         const uint32_t bo = pos & 31u;
         bool hit = false;
-        if (MODE == PR_SYNC) {
-            hit = ((lds_u32(s_mk + ((pos >> 5) << 2)) >> bo) & 1u) != 0;  // (needed only at the end of the trip)
-        } else if (MODE == PR_GUESS) {
-            // plain store of the word as far as it is known (the lane owns it; skipped words stay zero): shared
-            // atomics queue in front of the table lookups
-            const uint32_t wi = pos >> 5;
-            mk_acc = (wi == mk_word ? mk_acc : 0u) | (1u << bo);
-            mk_word = wi;
-            sts_u32(s_mk + (wi << 2), mk_acc);
+        if (CP) {
+            const uint32_t rel = pos - base_rel, j = rel >> 8;  // (tokens are shorter than 256 bits: no region is skipped)
+            if (j != cp_j) {
+                cp_j = j;
+                if (MODE == PR_COUNT_CP || MODE == PR_GUESS) sts_u32(s_mk + (j << 2) - 4u, rel | (n << 12));
+                else cp_v = lds_u32(s_mk + (j << 2) - 4u);
+            }
+            if (MODE == PR_SYNC_CP || MODE == PR_SYNC) hit = (cp_v & 0xfffu) == rel;
         }
         const uint32_t w = __funnelshift_r(lo, hi, bo);
         uint32_t e = lds_u32(s_ll + ((w & ((1u << PT_ROOT_LL) - 1u)) << 2));
@@ -340,7 +350,7 @@ __device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t s_mk, uint32
         const uint32_t c2 = d & 31u;
         const bool end = (int32_t)(e | d) < 0;  // end of block (kind 2), no such code (kind 3: consumes nothing)
         const bool stop = end || hit;
-        if (MODE != PR_COUNT) {
+        if (MODE == PR_EMIT || KEEP) {
             const uint32_t val = ((e >> 10) & 0xffffu) + ((w & ~(0xffffffffu << c1)) >> ((e >> 5) & 15u));
             const uint32_t dist = ((d >> 10) & 0xffffu) + ((w2 & ~(0xffffffffu << c2)) >> ((d >> 5) & 15u));
             if (!stop) __stcg(tk, m ? (0x80000000u | (val << 16) | ((dist - 1u) & 0x7fffu)) : val);
@@ -364,6 +374,7 @@ __device__ __forceinline__ uint32_t par_run(uint32_t s_cb, uint32_t s_mk, uint32
         if (adv >= 64u) { lo = hi; hi = nx; nx = lds_u32(a); a += 4; }  // a token of more than 32 bits: rare
     }
     n_out = n;
+    if (MODE == PR_SYNC_CP || MODE == PR_SYNC) *aux = cp_v >> 12;
     return (cw0_bits + pos) | flags;
 }
 
@@ -502,18 +513,19 @@ __global__ void __launch_bounds__(PAR_HDR_THREADS) k_par_headers(TokenArgs a, Pa
 
 // ------------------------------------------------------------------------------------------------
 template <int NT, int SW_MAX, bool ONEPASS>
-__global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
+__global__ void __launch_bounds__(NT, 896 / NT) k_tokens_par(ParArgs pa) {
     extern __shared__ __align__(16) uint8_t par_smem[];
     typedef ParShared<NT, SW_MAX, ONEPASS> PS;
     PS& S = *reinterpret_cast<PS*>(par_smem);
-    static_assert(!ONEPASS || 2 * (NT * SW_MAX + 16) >= (NT / 32) * 32 * 33, "the staged-word and mark areas double as the copy tiles");
-    static_assert(offsetof(PS, mk) == offsetof(PS, cb) + sizeof(uint32_t) * (NT * SW_MAX + 16), "cb and mk are one contiguous area");
+    static_assert(!ONEPASS || NT * SW_MAX + 16 >= (NT / 32) * 32 * 33, "the staged-word area doubles as the copy tiles");
     constexpr uint32_t CB_WORDS = NT * SW_MAX + 16;
     const TokenArgs& a = pa.t;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const uint32_t s_cb = smem_addr(S.cb), s_mk = smem_addr(S.mk), s_ll = smem_addr(S.ll), s_d = smem_addr(S.d), s_sub = smem_addr(S.sub),
                    s_zero = smem_addr(&S.zero);
     constexpr uint32_t CAP = par_scratch_cap(SW_MAX);
+    constexpr int NCP = par_ncp(SW_MAX);
+    const uint32_t s_cp = s_mk + (uint32_t)t * NCP * 4u;  // (three decodes) this lane's checkpoints
     // transposed token scratch of the warp: [guess run | latest sync run][CAP rows][32 lanes]
     uint32_t* const g_tok = pa.scratch + ((size_t)blockIdx.x * (NT / 32) + wid) * 2 * CAP * 32;
     uint32_t* const s_tok = g_tok + (size_t)CAP * 32;
@@ -542,7 +554,7 @@ __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
             __syncthreads();  // the previous block's emit pass has read the staged words
             uint32_t cw0 = bp >> 5;
             uint32_t staged = min(CB_WORDS, nwords + 2u - min(cw0, nwords + 2u));
-            for (uint32_t i = t; i < CB_WORDS; i += NT) { S.cb[i] = i < staged ? __ldg(words + cw0 + i) : 0u; if (ONEPASS) S.mk[i] = 0u; }
+            for (uint32_t i = t; i < CB_WORDS; i += NT) S.cb[i] = i < staged ? __ldg(words + cw0 + i) : 0u;
             __syncthreads();
             const ParHdr ph = pa.hdr[b];
             if (bp == mis * 8u && (ph.flags & 2u)) {  // the member's first header was parsed by k_par_headers
@@ -583,7 +595,7 @@ __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
                     __syncthreads();
                     cw0 = bp >> 5;
                     staged = min(CB_WORDS, nwords + 2u - min(cw0, nwords + 2u));
-                    for (uint32_t i = t; i < CB_WORDS; i += NT) { S.cb[i] = i < staged ? __ldg(words + cw0 + i) : 0u; if (ONEPASS) S.mk[i] = 0u; }
+                    for (uint32_t i = t; i < CB_WORDS; i += NT) S.cb[i] = i < staged ? __ldg(words + cw0 + i) : 0u;
                     __syncthreads();
                 }
                 first_wave = false;
@@ -601,15 +613,19 @@ __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
                 // (the last lane stops at the end of what is staged, not at the end of its nominal stretch)
                 const uint32_t my_end = wave_base + min((uint32_t)(t + 1) * sw, avail) * 32u;
                 uint32_t cur_start = my_start;      // where the path this lane currently stands for begins
+                const uint32_t base_rel = ((w0 - cw0) + (uint32_t)t * sw) * 32u;  // the lane's stretch in staged-word bit positions
                 uint32_t n_g = 0, n_s = 0, g_from = 0;  // (single decode) tokens of the guess run; of the sync run; first guess token in use
                 uint32_t res_g = PF_DEAD, res = PF_DEAD;
                 uint32_t n = 0;
                 // ---- guess: every lane decodes its stretch from the first bit
-                if (ONEPASS) {  // ... keeps the tokens and marks the token starts
-                    if (active) res = res_g = par_run<PR_GUESS>(s_cb, s_mk, cw0_bits, s_ll, s_d, s_sub, s_zero, my_start, my_end, CAP, n_g, g_tok + lane);
-                } else {
-                    if (active) res = par_run<PR_COUNT>(s_cb, s_mk, cw0_bits, s_ll, s_d, s_sub, s_zero, my_start, my_end, 0, n, nullptr);
+                // ... counts (single decode: and keeps its tokens), and leaves checkpoints for the sync runs
+#pragma unroll
+                for (int k = 0; k < NCP; k++) S.mk[t * NCP + k] = 0u;
+                if (active) {
+                    if (ONEPASS) res = res_g = par_run<PR_GUESS>(s_cb, s_cp, cw0_bits, s_ll, s_d, s_sub, s_zero, my_start, my_end, CAP, n_g, g_tok + lane, base_rel);
+                    else res = res_g = par_run<PR_COUNT_CP>(s_cb, s_cp, cw0_bits, s_ll, s_d, s_sub, s_zero, my_start, my_end, 0, n_g, nullptr, base_rel);
                 }
+                n = n_g;
                 if (t == 0) { S.exitb[0] = bp; S.first_flag = NT; }
                 S.exitb[t + 1] = res;
                 __syncthreads();
@@ -624,29 +640,22 @@ __global__ void __launch_bounds__(NT) k_tokens_par(ParArgs pa) {
                     if (++rounds > (uint32_t)NT + 2u) { fallback = true; break; }
                     if (chg) {
                         cur_start = prev;
-                        if (ONEPASS) {
-                            const uint32_t r = par_run<PR_SYNC>(s_cb, s_mk, cw0_bits, s_ll, s_d, s_sub, s_zero, prev, my_end, CAP, n_s, s_tok + lane);
-                            if (r & PF_MERGED) {
-                                // guess tokens before the meeting point = marks of this lane below it
-                                const uint32_t mp = (r & ~(PF_ANY | PF_MERGED)) - cw0_bits;
-                                const uint32_t fw = (w0 - cw0) + (uint32_t)t * sw, mw = mp >> 5;
-                                uint32_t c = __popc(S.mk[mw] & ((1u << (mp & 31u)) - 1u));
-                                for (uint32_t k = fw; k < mw; k++) c += __popc(S.mk[k]);
-                                g_from = c;
-                                res = res_g;
-                            } else {
-                                g_from = n_g;  // never met: the sync run's tokens are the lane's tokens
-                                res = r;
-                            }
+                        uint32_t g_before = 0;
+                        const uint32_t r = ONEPASS ? par_run<PR_SYNC>(s_cb, s_cp, cw0_bits, s_ll, s_d, s_sub, s_zero, prev, my_end, CAP, n_s, s_tok + lane, base_rel, &g_before)
+                                                   : par_run<PR_SYNC_CP>(s_cb, s_cp, cw0_bits, s_ll, s_d, s_sub, s_zero, prev, my_end, 0, n_s, nullptr, base_rel, &g_before);
+                        if (r & PF_MERGED) {  // from the checkpoint on the path is the guess path
+                            g_from = g_before;
+                            res = res_g;
                         } else {
-                            res = par_run<PR_COUNT>(s_cb, s_mk, cw0_bits, s_ll, s_d, s_sub, s_zero, prev, my_end, 0, n, nullptr);
+                            g_from = n_g;  // never met: the sync run's tokens are the lane's tokens
+                            res = r;
                         }
+                        n = n_s + (n_g - g_from);
                         S.exitb[t + 1] = res;
                     }
                     __syncthreads();
                 }
                 if (fallback) break;
-                if (ONEPASS) n = n_s + (n_g - g_from);
                 // ---- the chain is true up to the first flagged lane
                 if (active && (res & (PF_EOB | PF_INV))) atomicMin(&S.first_flag, (uint32_t)t);
                 __syncthreads();

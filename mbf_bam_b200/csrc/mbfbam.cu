@@ -607,7 +607,7 @@ struct Pipeline {
     }
 
     // K1.  Pass 1 (Huffman decode -> tokens): MBF_BAM_INFLATE_D = 400 (default) k_tokens_par<128,41>, 401
-    // <256,21>, 402 <128,33>, 403 <64,41>, 410-412 its single-decode form (one CTA per member, lanes share the
+    // <256,21>, 402 <128,33>, 403 <64,41>, 410/411 its single-decode form (one CTA per member, lanes share the
     // tables; members it cannot handle go to k_tokens_bf<8>); 302/304/308/316 = k_tokens_bf for every member with 2/4/8/16 decoders per
     // warp (the round-1 production kernel).  Pass 2 (LZ77): k_lz_resolve.
     void launch_inflate(WinBufs& w, const BlockArrays& b, int bi, uint32_t n_blocks, cudaStream_t si) {
@@ -666,16 +666,15 @@ struct Pipeline {
             case 401: launch_par(k_tokens_par<256, 21, false>, 256, 0, sizeof(ParShared<256, 21, false>)); break;
             case 402: launch_par(k_tokens_par<128, 33, false>, 128, 0, sizeof(ParShared<128, 33, false>)); break;
             case 403: launch_par(k_tokens_par<64, 41, false>, 64, 0, sizeof(ParShared<64, 41, false>)); break;
-            // single-decode scheme (the guess run keeps its tokens and marks its path; sync runs stop where they meet it)
+            // single-decode scheme (the guess run keeps its tokens; emit is a copy instead of a third decode)
             case 410: launch_par(k_tokens_par<128, 41, true>, 128, 41, sizeof(ParShared<128, 41, true>)); break;
             case 411: launch_par(k_tokens_par<128, 33, true>, 128, 33, sizeof(ParShared<128, 33, true>)); break;
-            case 412: launch_par(k_tokens_par<128, 21, true>, 128, 21, sizeof(ParShared<128, 21, true>)); break;
             case 302: launch_bf(k_tokens_bf<2, true>, (int)sizeof(TokensShared32<2>), 2, n_blocks); launched("k_tokens_bf", si); break;
             case 304: launch_bf(k_tokens_bf<4, true>, (int)sizeof(TokensShared32<4>), 4, n_blocks); launched("k_tokens_bf", si); break;
             case 308: launch_bf(k_tokens_bf<8, true>, (int)sizeof(TokensShared32<8>), 8, n_blocks); launched("k_tokens_bf", si); break;
             case 316: launch_bf(k_tokens_bf<16, true>, (int)sizeof(TokensShared32<16>), 16, n_blocks); launched("k_tokens_bf", si); break;
             default:
-                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 400-403, 410-412 or 302, 304, 308, 316");
+                throw Error(MBFBAM_ERR_ARG, "MBF_BAM_INFLATE_D must be 400-403, 410, 411 or 302, 304, 308, 316");
         }
         CK(cudaEventRecord(w.t[7], si));
         CK(cudaEventRecord(w.ev_cfree, si));  // pass 2 reads tokens only: the next H2D into this buffer may start
