@@ -2,7 +2,7 @@
 // in HBM; per window the launch sequence is
 //   k_win_begin -> k_scan<count> -> k_excl_scan -> k_scan<emit> -> k_blocks_finalize -> k_excl_scan
 //   -> k_tokens_par (+ k_tokens_bf for the members it hands over) -> k_lz_resolve   (inflate_par.cuh, inflate_twopass.cuh)
-//   -> k_frame_walk<count> -> k_frame_fix -> k_excl_scan -> k_frame_walk<emit> -> k_carry_copy
+//   -> k_frame_walk<count> -> k_frame_fix -> k_excl_scan -> k_frame_emit (| k_frame_walk<emit>) -> k_carry_copy
 //   -> k_count_reads<MODE> | k_count_introns -> k_mm_insert
 // Everything reads its sizes from a device-resident WinMeta, so the host never has to wait for a
 // kernel before it can enqueue the next one (it reads WinMeta only for capacity decisions).
@@ -323,6 +323,9 @@ struct FrameArgs {
     uint32_t* rec_base;   // exclusive scan of blk_nrec
     uint32_t* rec_off;    // out (EMIT)
     uint32_t rec_cap;
+    uint32_t* rec_tmp;    // count walk: offsets of the records of member b at [start_b / 36 ...) (a record is >= 36 bytes,
+                          // so the members' runs cannot collide); k_frame_emit compacts them into rec_off
+    uint32_t tmp_cap;
 };
 
 __device__ __forceinline__ uint32_t walk_block(const uint8_t* U, uint32_t pos, uint32_t limit, uint32_t u_end,
@@ -355,13 +358,28 @@ __global__ void __launch_bounds__(128) k_frame_walk(FrameArgs a) {
         else start = a.blk.uoff[b];
         uint32_t limit = b + 1 < nb ? a.blk.uoff[b + 1] : u_end;
         uint32_t n = 0;
-        uint32_t end = walk_block(a.U, start, limit, u_end, &n, EMIT ? a.rec_off : nullptr, a.rec_cap,
-                                  EMIT ? a.rec_base[b] : 0u);
+        if (EMIT && !a.meta->frame_bad) return;  // the provisional offsets are good: k_frame_emit copies them
+        uint32_t end = walk_block(a.U, start, limit, u_end, &n, EMIT ? a.rec_off : a.rec_tmp, EMIT ? a.rec_cap : a.tmp_cap,
+                                  EMIT ? a.rec_base[b] : start / 36u);
         if (!EMIT) {
             a.blk_start[b] = start;
             a.blk_end[b] = end;
             a.blk_nrec[b] = n;
         }
+    }
+}
+
+// The count walk left member b's record offsets at rec_tmp[blk_start[b] / 36 ...]: one warp per member copies them
+// to their final places (coalesced both ways) -- unless some walker had started off a record boundary
+// (meta->frame_bad: htsjdk-style files), in which case k_frame_walk<emit> walks the corrected chain again.
+__global__ void __launch_bounds__(128) k_frame_emit(FrameArgs a) {
+    if (a.meta->frame_bad) return;
+    const uint32_t nb = a.meta->n_blocks;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += (gridDim.x * blockDim.x) >> 5) {
+        const uint32_t n = a.blk_nrec[b], from = a.blk_start[b] / 36u, to = a.rec_base[b];
+        for (uint32_t i = lane; i < n; i += 32)
+            if (to + i < a.rec_cap) a.rec_off[to + i] = a.rec_tmp[from + i];
     }
 }
 

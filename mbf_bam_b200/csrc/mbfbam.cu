@@ -155,7 +155,7 @@ struct WinBufs {
     DevBuf d_c;
     DevBuf tile_count, tile_base, cand_pos, cand_bsize;
     DevBuf cpos, clen, isize, uoff;
-    DevBuf blk_start, blk_end, blk_nrec, rec_base, rec_off;
+    DevBuf blk_start, blk_end, blk_nrec, rec_base, rec_off, rec_tmp;
     DevBuf mm_fp, mm_slot;
     uint32_t mm_cap = 0;
     const uint8_t* c_ptr = nullptr;  // device pointer of this window's bytes (d_c or a view of the preload)
@@ -353,6 +353,7 @@ struct Pipeline {
         std::swap(U[bi].cap, nb.cap);
         U_cap[bi] = cap;
         wb[bi].rec_off.ensure((cap / 36 + 64) * 4);
+        wb[bi].rec_tmp.ensure(((cap + U_PREFIX + 65536) / 36 + 64) * 4);
     }
 
     // ---------------------------------------------------------------- front stage
@@ -579,7 +580,7 @@ struct Pipeline {
         } else {
             FrameArgs fa{U[bi].as<uint8_t>(), b, nullptr, dmeta(bi), w.blk_start.as<uint32_t>(), w.blk_end.as<uint32_t>(),
                          w.blk_nrec.as<uint32_t>(), w.rec_base.as<uint32_t>(), w.rec_off.as<uint32_t>(),
-                         (uint32_t)(w.rec_off.cap / 4)};
+                         (uint32_t)(w.rec_off.cap / 4), w.rec_tmp.as<uint32_t>(), (uint32_t)(w.rec_tmp.cap / 4)};
             fa.carry = d_carry.as<uint32_t>();
             uint32_t fgrid = std::max(1u, (m.n_blocks + 127) / 128);
             k_frame_walk<false><<<fgrid, 128, 0, s_main>>>(fa);
@@ -588,7 +589,9 @@ struct Pipeline {
             launched("k_frame_fix", s_main);
             k_excl_scan<<<1, 1024, 0, s_main>>>(fa.blk_nrec, fa.rec_base, &dmeta(bi)->n_blocks, 0, 0, &dmeta(bi)->n_records, nullptr, 0);
             launched("k_excl_scan(records)", s_main);
-            k_frame_walk<true><<<fgrid, 128, 0, s_main>>>(fa);
+            k_frame_emit<<<std::max(1u, (m.n_blocks + 3) / 4), 128, 0, s_main>>>(fa);
+            launched("k_frame_emit", s_main);
+            k_frame_walk<true><<<fgrid, 128, 0, s_main>>>(fa);  // (returns at once unless a walker was off a record boundary)
             launched("k_frame_walk<emit>", s_main);
             k_carry_copy<<<1, 256, 0, s_main>>>(U[bi].as<uint8_t>(), U[bi ^ 1].as<uint8_t>(), d_carry.as<uint32_t>(), dmeta(bi));
             launched("k_carry_copy", s_main);
