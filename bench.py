@@ -354,7 +354,9 @@ def main():
         step()
         barrier()
         t_first.append(time.perf_counter() - t0)
-    e2e_total, e2e_sts, e2e_last, clocks = timed(step, args.steps, args.warmup)
+    # (at least two more untimed steps whatever --warmup says: the page-locking of the mapping, ~0.4 s per GB once per
+    #  process and file, belongs to the fourth job and must not fall into the timed region)
+    e2e_total, e2e_sts, e2e_last, clocks = timed(step, args.steps, max(args.warmup, 2))
 
     def greduce(x, op=None):
         if dist is None:
