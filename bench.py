@@ -420,6 +420,10 @@ def main():
         return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
                 "traffic": int(tr["dram_bytes_per_algorithmic_byte"] * alg_bytes / W) if tr else None,
                 "traffic_source": tr.get("source") if tr else None,
+                # the same kernel alone on the GPU (ncu, one launch): the CUDA-event spans above contain the time a
+                # launch waits for SMs held by the kernels of neighbouring windows, which dominates for the short kernels
+                "achieved_alone": tr.get("achieved_alone_gbs") if tr else None,
+                "frac_alone": (tr["achieved_alone_gbs"] / peak) if tr and tr.get("achieved_alone_gbs") and peak else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes / W), "launches_per_call": int(W),
                 "ms_per_call": ms, "note": note}
 

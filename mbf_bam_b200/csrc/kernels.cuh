@@ -648,6 +648,34 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* arr, uint32_
     }
     return lo;
 }
+// first index in [lo,hi) with arr[i] >= x, searched outward from `hint` (galloping, then bisection): records arrive
+// sorted by position, so the answer for a thread's next record lies a few entries from the last one and costs 2-4
+// loads instead of the log2(n) of a cold bisection
+__device__ __forceinline__ uint32_t lower_bound_near(const uint32_t* arr, uint32_t lo, uint32_t hi, uint32_t x, uint32_t hint) {
+    uint32_t p = min(max(hint, lo), hi), l, h, step = 1;
+    if (p < hi && __ldg(arr + p) < x) {  // everything up to p is below x
+        l = p + 1;
+        h = hi;
+        for (;;) {
+            const uint32_t q = l + step - 1;
+            if (q >= hi) break;
+            if (__ldg(arr + q) < x) { l = q + 1; step <<= 1; } else { h = q; break; }
+        }
+    } else {  // everything from p on is at or above x
+        h = p;
+        l = lo;
+        for (;;) {
+            if (h - lo < step) break;
+            const uint32_t q = h - step;
+            if (__ldg(arr + q) >= x) { h = q; step <<= 1; } else { l = q + 1; break; }
+        }
+    }
+    while (l < h) {
+        const uint32_t mid = l + ((h - l) >> 1);
+        if (__ldg(arr + mid) < x) l = mid + 1; else h = mid;
+    }
+    return l;
+}
 // first index in [lo,hi) with arr[i] > x
 __device__ __forceinline__ uint32_t upper_bound_u32(const uint32_t* arr, uint32_t lo, uint32_t hi, uint32_t x) {
     while (lo < hi) {
@@ -691,14 +719,17 @@ __device__ __forceinline__ bool rec_view(const uint8_t* U, uint32_t off, RecView
 // cb(gene_word) returns false to stop.  `filter_stop`: unstranded block filter (counters.rs:52).
 // each_read_counts_once (c.iv_rank != null; counters.rs:83-92,173-182): only the first hit of the first
 // block that has one counts -- "first" in bio's iteration order, i.e. the overlapping interval of least rank.
+// `hint`: where the previous record's search ended (0xffffffff: no idea, plain bisection); updated.
 template <class CB>
 __device__ __forceinline__ void enumerate_hits(const CountCtx& c, const RecView& v, uint32_t iv_lo, uint32_t iv_hi,
-                                               bool use_filter, uint32_t chunk_stop, CB&& cb) {
+                                               bool use_filter, uint32_t chunk_stop, uint32_t& hint, CB&& cb) {
     const bool once = c.iv_rank != nullptr;
     cigar_walk(v.cigar, v.n_cig, v.upos,
                [&](uint32_t b0, uint32_t b1) {
                    if (use_filter && b0 >= chunk_stop) return true;
-                   uint32_t hi = lower_bound_u32(c.iv_start, iv_lo, iv_hi, b1);  // start < b1 below hi
+                   const uint32_t hi = hint == 0xffffffffu ? lower_bound_u32(c.iv_start, iv_lo, iv_hi, b1)
+                                                           : lower_bound_near(c.iv_start, iv_lo, iv_hi, b1, hint);  // start < b1 below hi
+                   if (hint != 0xffffffffu) hint = hi;
                    uint32_t best_rank = 0xffffffffu, best_gw = 0;
                    for (uint32_t k = hi; k-- > iv_lo;) {
                        if (__ldg(c.iv_pmax + k) <= b0) break;
@@ -726,22 +757,32 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_count_reads(CountCtx c) {
     const uint32_t n = c.meta->n_records;
     const int lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t my_outside = 0, my_owned = 0, my_hits = 0;
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += stride) {
+    // Every warp takes a contiguous run of records (positions ascend within it), so the interval and chunk searches of
+    // a thread start from where its previous record's ended.
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5, w_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t per_warp = (((n + n_warps - 1) / n_warps) + 31u) & ~31u;
+    const uint32_t w_beg = min(n, w_id * per_warp), w_end = min(n, w_beg + per_warp);
+    uint32_t hint_iv = 0, hint_ci = 0xffffffffu;
+    int hint_slot = -1;
+    for (uint32_t base = w_beg; base < w_end; base += 32) {
         const uint32_t i = base + lane;
         uint32_t keys[SEEN_K];
         int nk = 0;
         bool counted_direct = false;  // nh==1 (or weighted) keys go to counters; else to the mm list
         uint32_t wclass = 0;          // weighted: NH class index
-        if (i < n) {
+        if (i < w_end) {
             RecView v;
             bool ok = rec_view(c.U, c.rec_off[i], v);
             int slot = (v.tid >= 0 && v.tid < c.n_ref) ? c.tid2slot[v.tid] : -1;
             if (!ok) { set_err(c.meta, WERR_RECORD, i); slot = -1; }
             if (slot >= 0) {
                 const uint32_t clo = c.slot_chunk_off[slot], chi = c.slot_chunk_off[slot + 1];
-                const uint32_t ci = upper_bound_u32(c.chunk_stop, clo, chi, v.upos);  // first stop > pos
+                if (slot != hint_slot) { hint_slot = slot; hint_iv = c.slot_iv_off[slot]; hint_ci = 0xffffffffu; }
+                uint32_t ci = hint_ci;  // first stop > pos: usually the previous record's chunk
+                if (!(ci >= clo && ci < chi && v.upos < __ldg(c.chunk_stop + ci) && (ci == clo || __ldg(c.chunk_stop + ci - 1) <= v.upos)))
+                    ci = upper_bound_u32(c.chunk_stop, clo, chi, v.upos);
+                hint_ci = ci;
                 if (ci < chi && ci >= c.chunk_lo && ci < c.chunk_hi) {
                     my_owned++;
                     const uint32_t cstop = c.chunk_stop[ci];
@@ -750,7 +791,7 @@ __global__ void __launch_bounds__(256) k_count_reads(CountCtx c) {
                     bool hit = false, have_nh = false;
                     long long nh = 1;
                     uint32_t h_index = 0;
-                    enumerate_hits(c, v, iv_lo, iv_hi, MODE == 0, cstop, [&](uint32_t gw) {
+                    enumerate_hits(c, v, iv_lo, iv_hi, MODE == 0, cstop, hint_iv, [&](uint32_t gw) {
                         if (MODE == 3) {  // quantify: no NH logic at all (quantify.rs:117-140)
                             have_nh = true;
                             counted_direct = true;
@@ -784,7 +825,8 @@ __global__ void __launch_bounds__(256) k_count_reads(CountCtx c) {
                         // by re-enumerating the earlier hits, then handle the key right here.
                         bool seen = false;
                         uint32_t j = 0;
-                        enumerate_hits(c, v, iv_lo, iv_hi, MODE == 0, cstop, [&](uint32_t gw2) {
+                        uint32_t no_hint = 0xffffffffu;
+                        enumerate_hits(c, v, iv_lo, iv_hi, MODE == 0, cstop, no_hint, [&](uint32_t gw2) {
                             if (j++ >= my_index) return false;
                             uint32_t b2 = 0;
                             if (MODE != 0) {
@@ -1226,7 +1268,8 @@ __global__ void __launch_bounds__(256) k_barcode_hits(BarcodeCtx bc) {
         const uint8_t *xc = nullptr, *xm = nullptr;
         uint32_t xc_len = 0, xm_len = 0;
         // by_barcode.rs:131: with pos >= chunk.start only `block start >= chunk.stop` can drop a block
-        enumerate_hits(c, v, iv_lo, iv_hi, true, cstop, [&](uint32_t gw) {
+        uint32_t no_hint = 0xffffffffu;
+        enumerate_hits(c, v, iv_lo, iv_hi, true, cstop, no_hint, [&](uint32_t gw) {
             const bool plus = (gw >> 31) != 0;
             if (!((plus && !rev) || (!plus && rev))) return true;  // by_barcode.rs:139
             my_hits++;

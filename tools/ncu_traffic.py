@@ -58,7 +58,9 @@ for key, prefix in match.items():
         dram += val(r, "dram__bytes_read.sum") * unit_scale("dram__bytes_read.sum") + val(r, "dram__bytes_write.sum") * unit_scale("dram__bytes_write.sum")
         ms += val(r, "gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(rows[1][col["gpu__time_duration.sum"]], 1.0)
     a = alg[key] * members
+    if key == "k_scan":  # its own window: one CTA per 4 KiB tile, every byte tested by both passes
+        a = 2.0 * 4096.0 * val(next(x for x in ls if x[col["Kernel Name"]] == names[0]), "launch__grid_size")
     res[key] = {"dram_bytes_per_launch": int(dram), "algorithmic_bytes_per_launch": int(a), "dram_bytes_per_algorithmic_byte": dram / a,
-                "ms_alone_under_ncu": ms, "members_in_launch": int(members), "kernels": names, "source": source}
+                "ms_alone_under_ncu": ms, "achieved_alone_gbs": a / (ms / 1e3) / 1e9 if ms > 0 else None, "members_in_launch": int(members), "kernels": names, "source": source}
 json.dump(res, sys.stdout, indent=1)
 print()
