@@ -395,6 +395,10 @@ def test_property_gpu_vs_python_oracle(mb, tmp_path):
         assert mb.count_reads_stranded(path, None, iv, giv, True) == py_oracle.count_reads_stranded(path, None, iv, giv, True)
         assert_weighted_close(mb.count_reads_weighted(path, None, iv, giv), py_oracle.count_reads_weighted(path, None, iv, giv))
         assert mb.count_introns(path) == py_oracle.count_introns(path)
+        assert mb.quantify_gene_reads(path, None, iv, giv) == py_oracle.quantify_gene_reads(path, None, iv, giv)
+        assert mb.calculate_duplicate_distribution(path) == py_oracle.calculate_duplicate_distribution(path)
+        fn = "count_reads_primary_only_right_strand_only_by_barcode"   # (no XC/XM tags here: chunks with a right-strand hit drop out)
+        assert getattr(mb, fn)(path, None, iv, giv, "straight") == getattr(py_oracle, fn)(path, None, iv, giv, "straight")
         os.unlink(path)
         os.unlink(path + ".bai")
 
