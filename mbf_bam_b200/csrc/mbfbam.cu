@@ -1166,9 +1166,9 @@ void plan_shard(const Reader& r, ShardPlan& p, int shard, int nshards) {
     for (size_t i = 0; i < n; i++) {
         const Chunk& c = p.chunks[i];
         double wt = 1.0;
-        if (r.idx[(size_t)c.tid].has_reads) {
+        if (r.ix->idx[(size_t)c.tid].has_reads) {
             uint64_t a = r.voff_lower(c.tid, c.start) >> 16;
-            uint64_t b = c.stop >= r.lens[(size_t)c.tid] ? (r.idx[(size_t)c.tid].voff_end >> 16) : (r.voff_lower(c.tid, c.stop) >> 16);
+            uint64_t b = c.stop >= r.lens[(size_t)c.tid] ? (r.ix->idx[(size_t)c.tid].voff_end >> 16) : (r.voff_lower(c.tid, c.stop) >> 16);
             if (b > a) wt += (double)(b - a);
         }
         w[i + 1] = w[i] + wt;
@@ -1189,7 +1189,7 @@ void plan_shard(const Reader& r, ShardPlan& p, int shard, int nshards) {
         size_t j = i;
         while (j + 1 < p.hi && p.chunks[j + 1].tid == p.chunks[i].tid) j++;
         const Chunk &a = p.chunks[i], &b = p.chunks[j];
-        const RefIndex& ri = r.idx[(size_t)a.tid];
+        const RefIndex& ri = r.ix->idx[(size_t)a.tid];
         if (ri.has_reads) {
             uint64_t v0 = r.voff_lower(a.tid, a.start);
             uint64_t v1 = r.voff_upper(a.tid, b.stop);
@@ -1757,7 +1757,10 @@ void mbfbam_unpin_file(mbfbam_reader* r) {
     if (r->fmap) unpin_all(*r->fmap);
 }
 
-void mbfbam_host_cache_clear(void) { FileMapCache::get().clear(); }
+void mbfbam_host_cache_clear(void) {
+    FileMapCache::get().clear();
+    IndexCache::get().clear();
+}
 
 void mbfbam_release_device(int32_t device) {
     DevSlot& slot = dev_slot(device);

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -315,6 +316,8 @@ struct PyReader {
         std::vector<uint8_t> scanned;
         uint64_t outside = 0;
     };
+    std::unique_ptr<Raw> kept;       // count_reads_raw -> assemble hand-over
+    py::object kept_for = py::none();
 
     void run(int mode, const py::dict& intervals, const py::dict& gene_intervals, bool once, Raw& raw) {
         Flat gv;
@@ -437,18 +440,31 @@ struct PyReader {
     // dense vectors (bytes of u64 / f64) for the one-process-per-GPU merge: the caller all-reduces them
     // and calls assemble()
     py::tuple count_reads_raw(int mode, const py::dict& intervals, const py::dict& gene_intervals, py::object once) {
-        Raw raw;
+        std::unique_ptr<Raw> rawp(new Raw());
+        Raw& raw = *rawp;
         run(mode, intervals, gene_intervals, !once.is_none() && py::cast<bool>(once), raw);
         size_t G = raw.fwd.size() - 1;
         auto b = [](const void* p, size_t n) { return py::bytes((const char*)p, n); };
-        return py::make_tuple(b(raw.fwd.data(), G * 8), b(raw.rev.data(), G * 8), b(raw.wfwd.data(), G * 8),
-                              b(raw.wrev.data(), G * 8), b(raw.scanned.data(), raw.iv.names.size()), raw.outside);
+        py::tuple out = py::make_tuple(b(raw.fwd.data(), G * 8), b(raw.rev.data(), G * 8), b(raw.wfwd.data(), G * 8),
+                                       b(raw.wrev.data(), G * 8), b(raw.scanned.data(), raw.iv.names.size()), raw.outside);
+        // assemble() for the same `intervals` object follows at once (mbf_bam_b200.dist): keep the flattened form
+        kept = std::move(rawp);
+        kept_for = py::reinterpret_borrow<py::object>(intervals);
+        return out;
     }
 
     py::object assemble(int mode, const py::dict& intervals, py::bytes fwd, py::bytes rev, py::bytes wfwd, py::bytes wrev,
                         py::bytes scanned, uint64_t outside) {
-        Raw raw;
-        flatten(intervals, raw.iv);
+        std::unique_ptr<Raw> rawp;
+        if (kept && kept_for.ptr() == intervals.ptr()) {
+            rawp = std::move(kept);
+        } else {
+            rawp.reset(new Raw());
+            flatten(intervals, rawp->iv);
+        }
+        kept.reset();
+        kept_for = py::none();
+        Raw& raw = *rawp;
         size_t G = 0;
         for (uint32_t n : raw.iv.n_genes) G += n;
         auto load = [&](py::bytes& src, void* dst, size_t n) {

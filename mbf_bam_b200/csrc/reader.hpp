@@ -11,6 +11,10 @@
 #include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
+
+#include <list>
+#include <memory>
+#include <mutex>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -64,6 +68,47 @@ struct BaiMap {
     size_t size() const { return n; }
 };
 
+// Everything parsed from one index file.  Shared (through IndexCache) by every Reader that opens the same,
+// unchanged file: a 400 M-read BAM has a 40 MB index, and walking it at every open costs ~10 ms -- more than the
+// rest of the host side of a call.  The only thing that changes after parsing is the lazily filled RefIndex::bins,
+// which `mu` guards (one call fans out over several devices, each planning its shard on its own thread).
+struct IndexData {
+    std::vector<RefIndex> idx;
+    BaiMap bai;
+    int min_shift = 14, depth = 5;  // binning scheme: BAI is fixed at 14 / 5, a CSI header says (SAM spec 5.3 / CSIv1)
+    bool is_csi = false;
+    std::mutex mu;
+};
+
+class IndexCache {
+    std::mutex mu;
+    std::list<std::pair<std::string, std::shared_ptr<IndexData>>> items;
+
+public:
+    static IndexCache& get() {
+        static IndexCache c;
+        return c;
+    }
+    std::shared_ptr<IndexData> find(const std::string& key) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto it = items.begin(); it != items.end(); ++it)
+            if (it->first == key) {
+                items.splice(items.begin(), items, it);
+                return items.front().second;
+            }
+        return nullptr;
+    }
+    void put(const std::string& key, std::shared_ptr<IndexData> v) {
+        std::lock_guard<std::mutex> lk(mu);
+        items.emplace_front(key, std::move(v));
+        while (items.size() > 8) items.pop_back();
+    }
+    void clear() {
+        std::lock_guard<std::mutex> lk(mu);
+        items.clear();
+    }
+};
+
 struct Reader {
     std::string path;
     int fd = -1;
@@ -72,7 +117,7 @@ struct Reader {
     std::vector<uint32_t> lens;
     std::map<std::string, int32_t> name2tid;
     uint64_t first_rec_voff = 0;  // virtual offset of the first alignment record
-    std::vector<RefIndex> idx;
+    std::shared_ptr<IndexData> ix;  // the parsed index (shared between readers of the same file)
     // optional device-resident copy of the whole file (mbfbam_preload)
     int preload_device = -1;
     uint8_t* preload_ptr = nullptr;
@@ -102,13 +147,166 @@ struct Reader {
         if (bai) {
             bp = bai;
         } else {
+            // htslib's sam_index_load order: x.bam.csi, x.csi, then x.bam.bai, x.bai
+            const size_t n = path.size();
+            const bool dotbam = n > 4 && path.compare(n - 4, 4, ".bam") == 0;
+            std::vector<std::string> cands{path + ".csi"};
+            if (dotbam) cands.push_back(path.substr(0, n - 4) + ".csi");
+            cands.push_back(path + ".bai");
+            if (dotbam) cands.push_back(path.substr(0, n - 4) + ".bai");
             bp = path + ".bai";
-            if (access(bp.c_str(), R_OK) != 0) {
-                size_t n = path.size();
-                if (n > 4 && path.compare(n - 4, 4, ".bam") == 0) bp = path.substr(0, n - 4) + ".bai";
+            for (const auto& c : cands)
+                if (access(c.c_str(), R_OK) == 0) { bp = c; break; }
+        }
+        parse_index(bp);
+    }
+
+    // the index file decides its own format: "BAI\1" plain, or a BGZF stream that inflates to "CSI\1"
+    void parse_index(const std::string& bp) {
+        uint8_t m[4] = {0, 0, 0, 0};
+        int f = ::open(bp.c_str(), O_RDONLY);
+        if (f < 0) throw Error(MBFBAM_ERR_IO, "Could not read bam: no index " + bp);
+        struct stat sb;
+        if (fstat(f, &sb) != 0) { ::close(f); throw Error(MBFBAM_ERR_IO, "Could not read bam: cannot stat index " + bp); }
+        ssize_t got = ::read(f, m, 4);
+        ::close(f);
+        // the same index file (name, inode, size, time stamp) for a header with the same targets: parsed before
+        uint64_t hl = names.size();
+        for (uint32_t l : lens) hl = hl * 1099511628211ull + l;
+        char kb[160];
+        snprintf(kb, sizeof kb, "|%llu|%llu|%lld.%09ld|%llu", (unsigned long long)sb.st_ino, (unsigned long long)sb.st_size,
+                 (long long)sb.st_mtim.tv_sec, (long)sb.st_mtim.tv_nsec, (unsigned long long)hl);
+        const std::string key = bp + kb;
+        if ((ix = IndexCache::get().find(key))) return;
+        ix = std::make_shared<IndexData>();
+        if (got == 4 && m[0] == 0x1f && m[1] == 0x8b) parse_csi(bp);
+        else parse_bai(bp);
+        IndexCache::get().put(key, ix);
+    }
+
+    // CSI (coordinate-sorted index, htslib): BGZF-compressed; per bin a `loffset` (what the BAI linear index holds for
+    // the bin's first window) instead of a separate linear index; min_shift / depth in the header.
+    void parse_csi(const std::string& bp) {
+        std::vector<uint8_t> u;
+        {
+            std::vector<uint8_t> raw;
+            {
+                FILE* fh = fopen(bp.c_str(), "rb");
+                if (!fh) throw Error(MBFBAM_ERR_IO, "Could not read bam: no index " + bp);
+                uint8_t buf[1 << 16];
+                size_t k;
+                while ((k = fread(buf, 1, sizeof buf, fh)) > 0) raw.insert(raw.end(), buf, buf + k);
+                fclose(fh);
+            }
+            const uint8_t* d = raw.data();
+            const size_t n = raw.size();
+            std::vector<uint8_t> cb(65536 + 64), ob(65536 + 512);
+            DecoderTables T;
+            for (size_t off = 0; off + 28 <= n;) {
+                if (d[off] != 0x1f || d[off + 1] != 0x8b || d[off + 2] != 8 || !(d[off + 3] & 4))
+                    throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: index is not BGZF: " + bp);
+                const uint32_t xlen = d[off + 10] | (d[off + 11] << 8);
+                int32_t bsize = -1;
+                for (uint32_t q = 0; q + 4 <= xlen && off + 12 + q + 6 <= n;) {
+                    const uint8_t* e = d + off + 12 + q;
+                    const uint32_t slen = e[2] | (e[3] << 8);
+                    if (e[0] == 66 && e[1] == 67 && slen == 2) bsize = e[4] | (e[5] << 8);
+                    q += 4 + slen;
+                }
+                if (bsize < 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: BGZF block without BC field: " + bp);
+                const uint32_t csize = (uint32_t)bsize + 1, hdr = 12 + xlen;
+                if (csize < hdr + 8 || off + csize > n) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: truncated index " + bp);
+                const uint32_t clen = csize - hdr - 8;
+                uint32_t isize;
+                memcpy(&isize, d + off + csize - 4, 4);
+                if (isize > 65536) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: bad ISIZE in " + bp);
+                std::fill(cb.begin(), cb.end(), 0);
+                memcpy(cb.data(), d + off + hdr, clen);
+                if (isize && inflate_member_host(cb.data(), clen, ob.data(), isize, &T))
+                    throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: corrupt index " + bp);
+                u.insert(u.end(), ob.begin(), ob.begin() + isize);
+                off += csize;
             }
         }
-        parse_bai(bp);
+        size_t p = 0;
+        auto take = [&](void* dst, size_t n) {
+            if (p + n > u.size()) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: truncated index " + bp);
+            memcpy(dst, u.data() + p, n);
+            p += n;
+        };
+        char magic[4];
+        take(magic, 4);
+        if (memcmp(magic, "CSI\1", 4) != 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: not a CSI index: " + bp);
+        int32_t min_shift, depth, l_aux, n_ref;
+        take(&min_shift, 4);
+        take(&depth, 4);
+        take(&l_aux, 4);
+        if (min_shift < 1 || min_shift > 29 || depth < 1 || depth > 9 || min_shift + 3 * depth > 32 || l_aux < 0)
+            throw Error(MBFBAM_ERR_UNSUPPORTED, "Could not read bam: CSI binning scheme not supported: " + bp);
+        if (p + (size_t)l_aux > u.size()) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: truncated index " + bp);
+        p += (size_t)l_aux;
+        take(&n_ref, 4);
+        ix->is_csi = true;
+        ix->min_shift = min_shift;
+        ix->depth = depth;
+        const uint32_t leaf0 = ((1u << (3 * depth)) - 1u) / 7u;        // first bin of the deepest level
+        const uint32_t meta_bin = ((1u << (3 * depth + 3)) - 1u) / 7u + 1u;  // 37450 for depth 5
+        ix->idx.assign(names.size(), RefIndex());
+        for (int32_t r = 0; r < n_ref; r++) {
+            RefIndex ri;
+            take(&ri.n_bin, 4);
+            if (ri.n_bin < 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: bad index " + bp);
+            const uint32_t len = (size_t)r < lens.size() ? lens[(size_t)r] : 0;
+            ri.ioffset.assign(((size_t)len >> min_shift) + 1, 0);
+            bool meta = false;
+            uint64_t mn = UINT64_MAX, mx = 0;
+            for (int32_t i = 0; i < ri.n_bin; i++) {
+                uint32_t bin;
+                uint64_t loff;
+                int32_t n_chunk;
+                take(&bin, 4);
+                take(&loff, 8);
+                take(&n_chunk, 4);
+                if (n_chunk < 0 || p + 16 * (size_t)n_chunk > u.size()) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: truncated index " + bp);
+                if (bin == meta_bin) {
+                    if (n_chunk >= 1) {
+                        uint64_t be[2];
+                        memcpy(be, u.data() + p, 16);
+                        ri.voff_beg = be[0];
+                        ri.voff_end = be[1];
+                        meta = true;
+                    }
+                } else if (n_chunk > 0) {
+                    uint64_t bmn = UINT64_MAX, bmx = 0;
+                    for (int32_t c = 0; c < n_chunk; c++) {
+                        uint64_t be[2];
+                        memcpy(be, u.data() + p + 16 * (size_t)c, 16);
+                        bmn = std::min(bmn, be[0]);
+                        bmx = std::max(bmx, be[1]);
+                    }
+                    ri.bins.push_back({bin, {bmn, bmx}});
+                    mn = std::min(mn, bmn);
+                    mx = std::max(mx, bmx);
+                    // loffset = smallest offset of a record overlapping the bin's FIRST window: the linear index entry
+                    // of that window.  Any level gives one (a lower bound is all voff_lower needs).
+                    int l = depth;
+                    uint32_t lo = leaf0;
+                    while (l > 0 && bin < lo) { l--; lo = ((1u << (3 * l)) - 1u) / 7u; }
+                    const uint64_t w = (uint64_t)(bin - lo) << (3 * (depth - l));
+                    if (w < ri.ioffset.size() && loff > ri.ioffset[(size_t)w]) ri.ioffset[(size_t)w] = loff;
+                }
+                p += 16 * (size_t)n_chunk;
+            }
+            // offsets never decrease with the window (the file is sorted): windows without an entry inherit the last one
+            for (size_t w = 1; w < ri.ioffset.size(); w++) ri.ioffset[w] = std::max(ri.ioffset[w], ri.ioffset[w - 1]);
+            ri.bins_parsed = true;
+            ri.has_reads = mn != UINT64_MAX;
+            if (!(meta && ri.has_reads && ri.voff_end > ri.voff_beg)) {
+                ri.voff_beg = ri.has_reads ? mn : 0;
+                ri.voff_end = mx;
+            }
+            if ((size_t)r < ix->idx.size()) ix->idx[(size_t)r] = std::move(ri);
+        }
     }
 
     // BAM header: inflated on the host with the shared DEFLATE core (a few KB, once per open)
@@ -178,10 +376,9 @@ struct Reader {
         }
     }
 
-    BaiMap bai;
-
     // (min chunk begin, max chunk end) of every real bin of one reference, from its raw records
-    static void parse_bins(const RefIndex& ri) {
+    void parse_bins(const RefIndex& ri) const {
+        std::lock_guard<std::mutex> lk(ix->mu);
         if (ri.bins_parsed) return;
         ri.bins.clear();
         ri.bins.reserve((size_t)std::max(0, ri.n_bin));
@@ -208,7 +405,7 @@ struct Reader {
     }
 
     void parse_bai(const std::string& bp) {
-        BaiMap& d = bai;
+        BaiMap& d = ix->bai;
         d.fd = ::open(bp.c_str(), O_RDONLY);
         if (d.fd < 0) throw Error(MBFBAM_ERR_IO, "Could not read bam: no index " + bp);
         {
@@ -235,7 +432,7 @@ struct Reader {
         if (memcmp(magic, "BAI\1", 4) != 0) throw Error(MBFBAM_ERR_FORMAT, "Could not read bam: not a BAI index: " + bp);
         int32_t n_ref;
         take(&n_ref, 4);
-        idx.assign(names.size(), RefIndex());
+        ix->idx.assign(names.size(), RefIndex());
         for (int32_t r = 0; r < n_ref; r++) {
             RefIndex ri;
             take(&ri.n_bin, 4);
@@ -283,15 +480,15 @@ struct Reader {
                 ri.voff_beg = ri.has_reads ? mn : 0;
                 ri.voff_end = mx;
             }
-            if ((size_t)r < idx.size()) idx[(size_t)r] = std::move(ri);
+            if ((size_t)r < ix->idx.size()) ix->idx[(size_t)r] = std::move(ri);
         }
     }
 
     // Lower bound of the virtual offset of any record on `tid` with pos >= start (linear index).
     uint64_t voff_lower(int32_t tid, uint32_t start) const {
-        const RefIndex& ri = idx[(size_t)tid];
+        const RefIndex& ri = ix->idx[(size_t)tid];
         uint64_t v = ri.voff_beg;
-        size_t w = start >> 14;
+        size_t w = start >> ix->min_shift;
         if (w < ri.ioffset.size() && ri.ioffset[w] > v) v = ri.ioffset[w];
         return v;
     }
@@ -303,16 +500,15 @@ struct Reader {
     // valid but loose: one read in a 64 Mb bin drags the range to wherever that read lies, up to 20 % more
     // bytes per shard on the 400M-read file.)
     uint64_t voff_upper(int32_t tid, uint32_t stop) const {
-        const RefIndex& ri = idx[(size_t)tid];
+        const RefIndex& ri = ix->idx[(size_t)tid];
         if (stop >= lens[(size_t)tid] || stop == 0) return ri.voff_end;
-        static const uint32_t lvl_off[6] = {0, 1, 9, 73, 585, 4681};
-        static const int lvl_shift[6] = {29, 26, 23, 20, 17, 14};
         parse_bins(ri);
         uint64_t mn = UINT64_MAX;
         for (const auto& b : ri.bins) {
-            int l = 5;
-            while (l > 0 && b.first < lvl_off[l]) l--;
-            const uint64_t bin_start = (uint64_t)(b.first - lvl_off[l]) << lvl_shift[l];
+            int l = ix->depth;
+            uint32_t lo = ((1u << (3 * l)) - 1u) / 7u;  // first bin of level l (0, 1, 9, 73, 585, 4681 for BAI)
+            while (l > 0 && b.first < lo) { l--; lo = ((1u << (3 * l)) - 1u) / 7u; }
+            const uint64_t bin_start = (uint64_t)(b.first - lo) << (ix->min_shift + 3 * (ix->depth - l));
             if (bin_start >= stop) mn = std::min(mn, b.second.first);
         }
         return mn == UINT64_MAX ? ri.voff_end : std::min(mn, ri.voff_end);

@@ -280,12 +280,97 @@ class BaiBuilder:
         return b"".join(out)
 
 
+def reg2bin_csi(beg: int, end: int, min_shift: int, depth: int) -> int:
+    """CSIv1 specification, reg2bin for a (min_shift, depth) binning scheme."""
+    l, s, t = depth, min_shift, ((1 << (depth * 3)) - 1) // 7
+    end -= 1
+    while l > 0:
+        if beg >> s == end >> s:
+            return t + (beg >> s)
+        l -= 1
+        s += 3
+        t -= 1 << (l * 3)
+    return 0
+
+
+class CsiBuilder:
+    """Accumulates records in file order -> .csi bytes (BGZF compressed), the way htslib's hts_idx_finish lays it out:
+    per bin a `loffset` = linear-index entry of the bin's first window (unset windows filled from the right)."""
+
+    def __init__(self, n_ref: int, min_shift: int = 14, depth: int = 5):
+        self.n_ref, self.min_shift, self.depth = n_ref, min_shift, depth
+        self.bins = [dict() for _ in range(n_ref)]
+        self.lin = [dict() for _ in range(n_ref)]
+        self.meta = [None] * n_ref
+        self.last_bin = [None] * n_ref
+        self.n_no_coor = 0
+
+    def add(self, tid: int, beg: int, end: int, flag: int, v0: int, v1: int):
+        if tid < 0:
+            self.n_no_coor += 1
+            return
+        if beg < 0:
+            beg, end = 0, 1
+        b = reg2bin_csi(beg, end, self.min_shift, self.depth)
+        chunks = self.bins[tid].setdefault(b, [])
+        if chunks and self.last_bin[tid] == b and chunks[-1][1] == v0:
+            chunks[-1][1] = v1
+        else:
+            chunks.append([v0, v1])
+        self.last_bin[tid] = b
+        for w in range(beg >> self.min_shift, ((end - 1) >> self.min_shift) + 1):
+            if w not in self.lin[tid]:
+                self.lin[tid][w] = v0
+        m = self.meta[tid]
+        if m is None:
+            m = self.meta[tid] = [v0, v1, 0, 0]
+        m[1] = v1
+        if flag & 4:
+            m[3] += 1
+        else:
+            m[2] += 1
+
+    def tobytes(self) -> bytes:
+        d, ms = self.depth, self.min_shift
+        meta_bin = ((1 << (d * 3 + 3)) - 1) // 7 + 1
+        out = [b"CSI\1", struct.pack("<iii", ms, d, 0), struct.pack("<i", self.n_ref)]
+        for tid in range(self.n_ref):
+            lin = self.lin[tid]
+            n_intv = (max(lin) + 1) if lin else 0
+            arr = [0] * n_intv
+            nxt = 0
+            for w in range(n_intv - 1, -1, -1):
+                if w in lin:
+                    nxt = lin[w]
+                arr[w] = nxt
+            bins = self.bins[tid]
+            out.append(struct.pack("<i", len(bins) + (1 if self.meta[tid] else 0)))
+            for b in sorted(bins):
+                l, t = d, ((1 << (d * 3)) - 1) // 7
+                while l > 0 and b < t:
+                    l -= 1
+                    t = ((1 << (l * 3)) - 1) // 7
+                w = (b - t) << (3 * (d - l))
+                loff = arr[w] if w < n_intv else 0
+                out.append(struct.pack("<IQi", b, loff, len(bins[b])))
+                for c0, c1 in bins[b]:
+                    out.append(struct.pack("<QQ", c0, c1))
+            if self.meta[tid]:
+                m = self.meta[tid]
+                out.append(struct.pack("<IQiQQQQ", meta_bin, 0, 2, m[0], m[1], m[2], m[3]))
+        out.append(struct.pack("<Q", self.n_no_coor))
+        raw = b"".join(out)
+        comp = b"".join(bgzf_block(raw[i:i + MAX_PAYLOAD]) for i in range(0, len(raw), MAX_PAYLOAD))
+        return comp + BGZF_EOF
+
+
 def write_bam(path: str, refs: Sequence[Tuple[str, int]], records: Iterable[Rec],
               level: int = 6, split_records: bool = False, payload_limit: int = MAX_PAYLOAD,
               strategy: int = zlib.Z_DEFAULT_STRATEGY, sync_every: int = 0,
-              index: bool = True, header_text: str = "") -> int:
-    """Write `records` (already coordinate sorted) + `path`.bai. Returns #records."""
-    bai = BaiBuilder(len(refs))
+              index: bool = True, header_text: str = "", csi: Optional[Tuple[int, int]] = None) -> int:
+    """Write `records` (already coordinate sorted) + `path`.bai -- or, with csi=(min_shift, depth), `path`.csi.
+    Returns #records."""
+    bai = CsiBuilder(len(refs), *csi) if csi else BaiBuilder(len(refs))
     n = 0
     with open(path, "wb") as fh:
         w = BgzfWriter(fh, level, split_records, payload_limit, strategy, sync_every)
@@ -303,7 +388,7 @@ def write_bam(path: str, refs: Sequence[Tuple[str, int]], records: Iterable[Rec]
             n += 1
         w.close()
     if index:
-        with open(path + ".bai", "wb") as fh:
+        with open(path + (".csi" if csi else ".bai"), "wb") as fh:
             fh.write(bai.tobytes())
     return n
 

@@ -525,3 +525,29 @@ def test_page_locked_file_cache(mb, tmp_path, monkeypatch):
     os.replace(path2 + ".bai", path + ".bai")
     assert mb.count_reads_stranded(path, None, iv2, giv2) == c_oracle.count_reads_stranded(path, None, iv2, giv2)
     mb.host_cache_clear()
+
+
+def test_csi_index(mb, tmp_path):
+    """the same file under a CSI index (two binning schemes): identical results, also when sharded"""
+    from synth import small
+
+    contigs, recs, iv, giv = small.simple_case(78, n_reads=30000, n_contigs=3, random_seq=True)
+    pa, pb, pc = (str(tmp_path / n) for n in ("a.bam", "b.bam", "c.bam"))
+    bamio.write_bam(pa, contigs, recs)
+    bamio.write_bam(pb, contigs, recs, csi=(14, 5))
+    bamio.write_bam(pc, contigs, recs, csi=(12, 6))
+    want = c_oracle.count_reads_stranded(pa, None, iv, giv, nthreads=4)
+    want_i = c_oracle.count_introns(pa, nthreads=4)
+    for p in (pb, pc):
+        assert mb.count_reads_stranded(p, None, iv, giv) == want
+        assert mb.count_introns(p) == want_i
+        f, r = {}, {}
+        for s in range(3):
+            rd = mb.Reader(p)
+            rd.set_device(0)
+            rd.set_shard(s, 3)
+            a, b = rd.count_reads(1, iv, giv)
+            for src, dst in ((a, f), (b, r)):
+                for k, v in src.items():
+                    dst[k] = dst.get(k, 0) + v
+        assert (f, r) == want

@@ -183,3 +183,38 @@ def test_no_cpu_fallback(built, has_gpu, tmp_path):
                  lambda: built.cigar_expand([16], 5)):
         with pytest.raises(ValueError, match="no CUDA device"):
             call()
+
+
+def test_csi_index_gives_the_same_plan_as_bai(built, tmp_path):
+    """CSI indices (BGZF compressed, per-bin loffset, min_shift / depth in the header; htslib looks for them before
+    the .bai): chunk table and shard byte ranges must cover what the BAI-derived ones cover."""
+    import shutil
+
+    from synth import bamio, small
+
+    contigs, recs, iv, giv = small.simple_case(77, n_reads=20000, n_contigs=3, random_seq=True)
+    pa, pb, pc = (str(tmp_path / n) for n in ("a.bam", "b.bam", "c.bam"))
+    bamio.write_bam(pa, contigs, recs)
+    bamio.write_bam(pb, contigs, recs, csi=(14, 5))
+    bamio.write_bam(pc, contigs, recs, csi=(12, 6))
+    assert os.path.exists(pb + ".csi") and not os.path.exists(pb + ".bai")
+    ra, rb, rc = built.Reader(pa), built.Reader(pb), built.Reader(pc)
+    assert ra.chunks(giv) == rb.chunks(giv) == rc.chunks(giv) == c_oracle.chunks(pa, None, giv)
+    for n in (1, 2, 5):
+        for i in range(n):
+            lo_a, hi_a, ranges_a = ra.plan(giv, i, n)
+            for r in (rb, rc):
+                lo, hi, ranges = r.plan(giv, i, n)
+                assert (lo, hi) == (lo_a, hi_a)
+                for b, e in ranges_a:   # every byte the BAI plan reads is read under the CSI plan too
+                    assert any(b2 <= b and e <= e2 for b2, e2 in ranges), (n, i, ranges_a, ranges)
+    # an explicit index file name decides by content, not by extension; a .csi beside a .bai wins (htslib's order)
+    shutil.copy(pb + ".csi", str(tmp_path / "explicit.idx"))
+    assert built.Reader(pb, str(tmp_path / "explicit.idx")).chunks(giv) == ra.chunks(giv)
+    open(pb + ".bai", "wb").write(b"not an index")
+    assert built.Reader(pb).chunks(giv) == ra.chunks(giv)
+    with open(pc + ".csi", "r+b") as fh:   # damaged CSI: a ValueError, not a crash
+        fh.seek(40)
+        fh.write(b"\xff" * 30)
+    with pytest.raises(ValueError, match="Could not read bam"):
+        built.Reader(pc)
