@@ -84,7 +84,10 @@ void mbfbam_drop_preload(mbfbam_reader* r);
  * segments, at most MBF_BAM_PIN_MAX_MB, default half of RAM) and later jobs DMA straight out of the page
  * cache.  mbfbam_pin_file page-locks the whole file now (MBFBAM_ERR_UNSUPPORTED when the platform refuses;
  * the reader keeps working through the staging path); mbfbam_unpin_file releases the page locks of this
- * file (no job may be running on it); mbfbam_host_cache_clear drops every cached mapping. */
+ * file (no job may be running on it).  Two more process-wide caches keep repeated calls cheap: parsed indices, keyed
+ * by the index file's identity (name, inode, size, mtime) and the header's targets, and count tables (chunk table,
+ * sorted interval arrays), keyed by the content of the two interval arguments.  mbfbam_host_cache_clear drops all
+ * three. */
 int mbfbam_pin_file(mbfbam_reader* r, char* err, size_t errlen);
 void mbfbam_unpin_file(mbfbam_reader* r);
 void mbfbam_host_cache_clear(void);

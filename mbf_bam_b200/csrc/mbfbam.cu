@@ -1331,6 +1331,13 @@ void build_count_tables(const Reader& r, const mbfbam_count_job* job, CountTable
 // many files and functions against one annotation: the last few results are kept, keyed by the CONTENT of the inputs
 // (a byte-for-byte copy is compared on lookup, so a hit is exact).  Building takes ~6 ms for 20 k genes / 60 k
 // intervals (the replay of bio's tree for the chunk edges is most of it); a lookup ~0.1 ms.
+std::mutex g_tables_mu;
+std::list<std::pair<std::string, std::shared_ptr<const CountTables>>> g_tables;
+void clear_count_tables() {
+    std::lock_guard<std::mutex> lk(g_tables_mu);
+    g_tables.clear();
+}
+
 std::shared_ptr<const CountTables> cached_count_tables(const Reader& r, const mbfbam_count_job* job) {
     std::string key;
     auto put = [&](const void* p, size_t n) { key.append((const char*)p, n); };
@@ -1347,8 +1354,8 @@ std::shared_ptr<const CountTables> cached_count_tables(const Reader& r, const mb
     for (size_t t = 0; t < r.names.size(); t++) { key.append(r.names[t]); key.push_back('\0'); put(&r.lens[t], 4); }
     put_iv(job->intervals);
     put_iv(job->gene_intervals);
-    static std::mutex mu;
-    static std::list<std::pair<std::string, std::shared_ptr<const CountTables>>> cache;
+    std::mutex& mu = g_tables_mu;
+    auto& cache = g_tables;
     {
         std::lock_guard<std::mutex> lk(mu);
         for (auto it = cache.begin(); it != cache.end(); ++it)
@@ -1760,6 +1767,7 @@ void mbfbam_unpin_file(mbfbam_reader* r) {
 void mbfbam_host_cache_clear(void) {
     FileMapCache::get().clear();
     IndexCache::get().clear();
+    clear_count_tables();
 }
 
 void mbfbam_release_device(int32_t device) {
