@@ -128,15 +128,22 @@ inline bool from_py(PyObject* o, double& v) { v = PyFloat_AsDouble(o); return !(
 
 template <class T>
 void dict_add(PyObject* d, PyObject* key, T v) {  // d[key] = d.get(key, 0) + v
-    PyObject* old = PyDict_GetItemWithError(d, key);  // borrowed
-    if (old) {
-        T o;
-        if (!from_py(old, o)) throw py::error_already_set();
-        v += o;
-    } else if (PyErr_Occurred()) {
+    PyObject* nv = to_py(v);
+    if (!nv) throw py::error_already_set();
+    // one lookup inserts the value when the key is new (the usual case: gene ids are unique)
+    PyObject* cur = PyDict_SetDefault(d, key, nv);  // borrowed
+    if (!cur) {
+        Py_DECREF(nv);
         throw py::error_already_set();
     }
-    PyObject* nv = to_py(v);
+    if (cur == nv) {
+        Py_DECREF(nv);
+        return;
+    }
+    Py_DECREF(nv);
+    T o;
+    if (!from_py(cur, o)) throw py::error_already_set();
+    nv = to_py((T)(v + o));
     if (!nv || PyDict_SetItem(d, key, nv) != 0) {
         Py_XDECREF(nv);
         throw py::error_already_set();
@@ -769,6 +776,13 @@ PYBIND11_MODULE(mbf_bam, m) {
           py::arg("filename"), py::arg("index_filename"), py::arg("intervals"), py::arg("gene_intervals"), py::arg("umi_strategy"),
           "python wrapper for py_count_reads_primary_only_right_strand_only_by_barcode (reference src/lib.rs:184)");
     m.def("last_stats", []() { return stats_dict(g_last_stats); }, "measurements of the most recent module-level call");
+    m.def("flatten_stats", [](const py::dict& intervals) {
+        Flat f;
+        flatten(intervals, f);
+        size_t g = 0;
+        for (uint32_t n : f.n_genes) g += n;
+        return py::make_tuple(f.names.size(), g, f.st.size());
+    }, py::arg("intervals"), "(contigs, genes, intervals) of an interval dict after the conversion every count call does");
     m.def("device_count", []() { return mbfbam_device_count(); });
     m.def("release_device", [](int device) { mbfbam_release_device(device); }, py::arg("device") = 0,
           "free the cached pipeline (device + pinned buffers) of a device");
