@@ -164,6 +164,7 @@ struct WinBufs {
     uint32_t scan_len = 0, avail = 0;
     cudaEvent_t ev_front = nullptr, ev_main = nullptr, ev_inf = nullptr;
     cudaEvent_t ev_cfree = nullptr;  // the compressed bytes of this window are no longer read (pass 1 of K1 is done)
+    cudaEvent_t ev_h2d = nullptr;    // the window's bytes are in HBM
     cudaEvent_t t[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     WinMeta front_meta{};
     bool timed = false;
@@ -181,6 +182,8 @@ struct Pipeline {
     uint32_t W;          // window size in compressed bytes
     uint32_t cand_cap;
     cudaStream_t s_front = nullptr, s_main = nullptr, s_inf[2] = {nullptr, nullptr};
+    cudaStream_t s_copy = nullptr;  // H2D of the windows: nothing else, so that window k+1's copy follows window k's at once
+                                    // (behind the scan kernels on s_front the link idled 0.75 ms per window)
     cudaEvent_t ev_reuse = nullptr, ev_job_begin = nullptr, ev_job_end = nullptr;
     WinBufs wb[2];
     DevBuf U[2];
@@ -230,6 +233,7 @@ struct Pipeline {
         int prio_lo = 0, prio_hi = 0;
         CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CK(cudaStreamCreateWithPriority(&s_front, cudaStreamNonBlocking, prio_hi));
+        CK(cudaStreamCreateWithPriority(&s_copy, cudaStreamNonBlocking, prio_hi));
         CK(cudaStreamCreateWithPriority(&s_main, cudaStreamNonBlocking, prio_hi));
         CK(cudaStreamCreateWithPriority(&s_inf[0], cudaStreamNonBlocking, prio_lo));
         CK(cudaStreamCreateWithPriority(&s_inf[1], cudaStreamNonBlocking, prio_lo));
@@ -247,6 +251,7 @@ struct Pipeline {
             CK(cudaEventCreateWithFlags(&w.ev_main, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&w.ev_inf, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&w.ev_cfree, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&w.ev_h2d, cudaEventDisableTiming));
             for (auto& t : w.t) CK(cudaEventCreate(&t));
         }
     }
@@ -257,7 +262,7 @@ struct Pipeline {
     void begin_job(const Source* s, JobKind k, uint64_t job_bytes) {
         CK(cudaSetDevice(device));
         // a previous job may have ended with an exception while work was still queued
-        for (cudaStream_t x : {s_front, s_inf[0], s_inf[1], s_main}) CK(cudaStreamSynchronize(x));
+        for (cudaStream_t x : {s_front, s_copy, s_inf[0], s_inf[1], s_main}) CK(cudaStreamSynchronize(x));
         src = s;
         kind = k;
         st = mbfbam_stats{};
@@ -308,6 +313,7 @@ struct Pipeline {
             if (w.ev_main) cudaEventDestroy(w.ev_main);
             if (w.ev_inf) cudaEventDestroy(w.ev_inf);
             if (w.ev_cfree) cudaEventDestroy(w.ev_cfree);
+            if (w.ev_h2d) cudaEventDestroy(w.ev_h2d);
             for (auto& t : w.t) if (t) cudaEventDestroy(t);
         }
         if (ev_reuse) cudaEventDestroy(ev_reuse);
@@ -315,11 +321,37 @@ struct Pipeline {
         if (ev_job_end) cudaEventDestroy(ev_job_end);
         for (auto& x : s_inf) if (x) cudaStreamDestroy(x);
         if (s_front) cudaStreamDestroy(s_front);
+        if (s_copy) cudaStreamDestroy(s_copy);
         if (s_main) cudaStreamDestroy(s_main);
+    }
+
+    // MBF_BAM_TIMELINE=1 (debug): an event behind every launch and copy; run() prints when each completed, relative
+    // to the start of the job -- the gaps between the entries of a stream are where that stream waited
+    struct TlEv { cudaEvent_t ev; const char* what; char stream; };
+    bool timeline = false;
+    std::vector<TlEv> tl;
+    std::mutex tl_mu;
+    void mark(const char* what, cudaStream_t s) {
+        if (!timeline) return;
+        TlEv e{nullptr, what, s == s_front ? 'F' : s == s_copy ? 'C' : s == s_main ? 'M' : s == s_inf[0] ? 'a' : 'b'};
+        if (cudaEventCreate(&e.ev) != cudaSuccess || cudaEventRecord(e.ev, s) != cudaSuccess) return;
+        std::lock_guard<std::mutex> lk(tl_mu);
+        tl.push_back(e);
+    }
+    void print_timeline() {
+        if (!timeline) return;
+        std::lock_guard<std::mutex> lk(tl_mu);
+        for (const TlEv& e : tl) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev_job_begin, e.ev) == cudaSuccess) fprintf(stderr, "[mbfbam-tl] %8.3f %c %s\n", ms, e.stream, e.what);
+            cudaEventDestroy(e.ev);
+        }
+        tl.clear();
     }
 
     void launched(const char* what, cudaStream_t s) {
         st.n_kernel_launches++;
+        mark(what, s);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw Error(MBFBAM_ERR_CUDA, fmt("launch of %s failed: %s", what, cudaGetErrorString(e)));
         if (sync_debug) {
@@ -362,7 +394,7 @@ struct Pipeline {
     void stage_front(int bi, uint64_t win_off, uint32_t scan_len, uint64_t src_end, int range_start,
                      uint64_t range_off, uint32_t first_uoff) {
         WinBufs& w = wb[bi];
-        CK(cudaStreamWaitEvent(s_front, w.ev_cfree, 0));  // the previous user of this C buffer: pass 1 of window k-2
+        CK(cudaStreamWaitEvent(s_copy, w.ev_cfree, 0));  // the previous user of this C buffer: pass 1 of window k-2
         uint64_t want = (uint64_t)scan_len + 65536 + 64;
         uint64_t avail = std::min<uint64_t>(want, src_end - win_off);
         w.win_off = win_off;
@@ -380,6 +412,7 @@ struct Pipeline {
             st.h2d_bytes += avail;
             w.c_ptr = w.d_c.as<uint8_t>();
         }
+        CK(cudaEventRecord(w.ev_h2d, s_copy));
         st.compressed_bytes += scan_len;
     }
 
@@ -394,6 +427,7 @@ struct Pipeline {
         const uint64_t range_off = w.range_off;
         const uint32_t first_uoff = w.first_uoff;
         CK(cudaStreamWaitEvent(s_front, ev_reuse, 0));
+        CK(cudaStreamWaitEvent(s_front, w.ev_h2d, 0));
         CK(cudaEventRecord(w.t[0], s_front));
         k_win_begin<<<1, 1, 0, s_front>>>(d_chain.as<ChainState>(), dmeta(bi), range_start, range_off, first_uoff);
         launched("k_win_begin", s_front);
@@ -444,10 +478,11 @@ struct Pipeline {
             for (size_t off = 0; off < avail;) {
                 const size_t seg_left = PIN_SEG - (size_t)((win_off + off) % PIN_SEG);
                 const size_t len = std::min(seg_left, avail - off);
-                CK(cudaMemcpyAsync(d + off, hp + off, len, cudaMemcpyHostToDevice, s_front));
+                CK(cudaMemcpyAsync(d + off, hp + off, len, cudaMemcpyHostToDevice, s_copy));
                 off += len;
             }
-            CK(cudaMemsetAsync(d + avail, 0, 128, s_front));
+            mark("h2d(window, from the page-locked mapping)", s_copy);
+            CK(cudaMemsetAsync(d + avail, 0, 128, s_copy));
             st.h2d_pinned_bytes += avail;
             return;
         }
@@ -461,7 +496,7 @@ struct Pipeline {
         if (n_pieces <= 1 || n_threads <= 1) {
             src->read(win_off, avail, h);
             memset(h + avail, 0, 128);
-            CK(cudaMemcpyAsync(d, h, avail + 128, cudaMemcpyHostToDevice, s_front));
+            CK(cudaMemcpyAsync(d, h, avail + 128, cudaMemcpyHostToDevice, s_copy));
             return;
         }
         std::vector<std::atomic<int>> done(n_pieces);
@@ -508,7 +543,7 @@ struct Pipeline {
                 memset(h + avail, 0, 128);
                 len += 128;
             }
-            if (!failed.load() && cerr == cudaSuccess) cerr = cudaMemcpyAsync(d + off, h + off, len, cudaMemcpyHostToDevice, s_front);
+            if (!failed.load() && cerr == cudaSuccess) cerr = cudaMemcpyAsync(d + off, h + off, len, cudaMemcpyHostToDevice, s_copy);
         }
         for (auto& t : th) t.join();
         if (failed.load()) throw Error(MBFBAM_ERR_IO, fail_msg);
@@ -1014,6 +1049,7 @@ struct Pipeline {
         Win wk{}, wn{};
         bool have = next_win(cur_w, wk);
         double t0 = now_ms();
+        timeline = env_u32("MBF_BAM_TIMELINE", 0) != 0;
         CK(cudaEventRecord(ev_job_begin, s_front));
         if (have) {
             stage_front(0, wk.off, wk.scan_len, wk.src_end, wk.range_start, wk.range_off, wk.first_uoff);
@@ -1036,6 +1072,8 @@ struct Pipeline {
             cap = std::max<uint64_t>(cap & ~(uint64_t)0xfffff, 1u << 20);
             const uint64_t grow_pct = env_u32("MBF_BAM_RAMP_PCT", 150);
             cur_w = std::min<uint64_t>(std::min<uint64_t>(W, cap), ramp ? cur_w * grow_pct / 100 : W);
+            // (Halving the last windows of a streamed job, so that little is left to do when the copies end, was tried:
+            // 75.2 instead of 70.6 ms -- a drained pipeline pays ~1 ms of launch and host round-trip latency per window.)
             const bool have_next = next_win(cur_w, wn);
             if (have_next) {
                 // bytes of window k+1 (host read + H2D) while the GPU works on windows k-1 / k -- on a helper
@@ -1055,7 +1093,7 @@ struct Pipeline {
             CK(cudaEventRecord(ev_reuse, s_main));
             double td = now_ms();
             issue_main(bi);
-            stager.join();  // window k+1's copies are queued on s_front: its scan may follow them
+            stager.join();  // window k+1's copies are queued (s_copy, ev_h2d recorded): its scan may be queued behind them
             if (have_next) scan_front(bi ^ 1);
             if (trace)
                 fprintf(stderr, "[mbfbam] win %zu t=%.2f issue_inflate %.2f ms, stage_next %.2f ms, finish_prev %.2f ms, rest %.2f ms (scan_len %u)\n",
@@ -1069,11 +1107,13 @@ struct Pipeline {
         CK(cudaStreamSynchronize(s_inf[1]));
         CK(cudaStreamSynchronize(s_main));
         CK(cudaStreamSynchronize(s_front));
+        CK(cudaStreamSynchronize(s_copy));
         CK(cudaEventRecord(ev_job_end, s_main));  // every stream has drained: this is the end of the device's work
         CK(cudaEventSynchronize(ev_job_end));
         float ms_all = 0;
         CK(cudaEventElapsedTime(&ms_all, ev_job_begin, ev_job_end));
         st.ms_gpu_all = ms_all;
+        print_timeline();
     }
 };
 
