@@ -1,9 +1,11 @@
 // sm_100a kernels of the read-counting path.  One "window" = a slice of the BGZF file resident
 // in HBM; per window the launch sequence is
 //   k_win_begin -> k_scan<count> -> k_excl_scan -> k_scan<emit> -> k_blocks_finalize -> k_excl_scan
-//   -> k_tokens_par (+ k_tokens_bf for the members it hands over) -> k_lz_resolve   (inflate_par.cuh, inflate_twopass.cuh)
+//   -> k_par_headers -> k_tokens_par (+ k_tokens_bf for the members it hands over) -> k_lz_resolve
+//                                                                        (inflate_par.cuh, inflate_twopass.cuh)
 //   -> k_frame_walk<count> -> k_frame_fix -> k_excl_scan -> k_frame_emit (| k_frame_walk<emit>) -> k_carry_copy
-//   -> k_count_reads<MODE> | k_count_introns -> k_mm_insert
+//   -> the job's record kernel: k_count_reads<MODE> (+ k_mm_insert) | k_count_introns | k_count_reads<3> (quantify)
+//      | k_dup_insert | k_barcode_hits
 // Everything reads its sizes from a device-resident WinMeta, so the host never has to wait for a
 // kernel before it can enqueue the next one (it reads WinMeta only for capacity decisions).
 //
@@ -16,6 +18,9 @@
 //                               bio IntervalTree::find
 //   k_mm_insert                 multimapper_dedup HashMap<u32, HashSet<Vec<u8>>> (counters.rs:36,70-73,102-104)
 //   k_count_introns             count_introns (introns.rs:24-51)
+//   k_count_reads<3>            quantify_gene_reads (quantify.rs:98-146)
+//   k_dup_insert, k_dup_hist    py_calculate_duplicate_distribution (duplicate_distribution.rs:44-86)
+//   k_barcode_hits              count_reads_primary_only_right_strand_only_by_barcode (by_barcode.rs:101-182)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
