@@ -246,3 +246,34 @@ def test_each_read_counts_once_oracles_agree(tmp_path, seed, kw):
     assert a["_outside"] == b["_outside"] and a["_total"] <= b["_total"]
     if kw:
         assert a != b  # with dense overlapping genes the flag changes results
+
+
+def test_property_c_oracle_vs_py_oracle_and_host_chunk_table(built, tmp_path):
+    """Random gene sets and reads (hypothesis): the C restatement (tree walk, BAI seeks, threads) against the brute-force
+    Python one, and the product's host-side chunk table against both -- every count, both `each_read_counts_once`
+    settings, introns, chunk edges."""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from synth import small
+
+    @settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.integers(0, 10 ** 6), st.integers(1, 3), st.integers(1, 80), st.booleans(), st.booleans())
+    def prop(seed, n_contigs, genes, exon_mode, paired):
+        contigs, recs, iv, giv = small.simple_case(seed, n_reads=500, n_contigs=n_contigs, contig_len=1_200_000,
+                                                   genes_per_contig=genes, exon_mode=exon_mode, paired=paired)
+        path = str(tmp_path / ("p%d.bam" % seed))
+        bamio.write_bam(path, contigs, recs, level=1)
+        for once in (False, True):
+            assert c_oracle.count_reads_unstranded(path, None, iv, giv, once, nthreads=2) == \
+                py_oracle.count_reads_unstranded(path, None, iv, giv, once)
+            assert c_oracle.count_reads_stranded(path, None, iv, giv, once, nthreads=2) == \
+                py_oracle.count_reads_stranded(path, None, iv, giv, once)
+        assert c_oracle.count_introns(path, nthreads=2) == py_oracle.count_introns(path)
+        name2tid = {n: i for i, (n, _) in enumerate(contigs)}
+        want = [(t, s, e) for _, t, s, e in py_oracle.make_chunks(
+            [(c, name2tid[c], dict(contigs)[c]) for c in giv], {c: py_oracle.build_intervals(giv[c])[0] for c in giv})]
+        assert c_oracle.chunks(path, None, giv) == want
+        assert built.Reader(path).chunks(giv) == want
+        os.unlink(path)
+        os.unlink(path + ".bai")
+
+    prop()
