@@ -8,7 +8,7 @@ gathered and merged key-wise (rayon's `reduce` with add_hashmaps / combine_intro
 returns the whole-job result, assembled by the same host code as the single-process functions.  Multi-mapper
 sets are chunk-local (counters.rs:36,102-104), so shards never share one: there is no other exchange.
 
-    torchrun --nproc-per-node 8 script.py        # script: init_process_group("nccl"), then
+    torchrun --nproc-per-node 8 script.py        # script: torch.cuda.set_device(LOCAL_RANK); init_process_group("nccl")
     from mbf_bam_b200 import dist as mbd
     fwd, rev = mbd.count_reads_stranded(bam, None, intervals, gene_intervals)
 
@@ -54,6 +54,21 @@ def _tensor_device(dist, group, local):
     return torch.device("cuda", local) if dist.get_backend(group) == "nccl" else torch.device("cpu")
 
 
+def _gather_objects(part, group=None):
+    """all_gather_object of `part`; under NCCL the pickled bytes travel through this rank's own GPU (the call uses the
+    *current* CUDA device, which a script that never called torch.cuda.set_device would leave at 0 on every rank)"""
+    dist = _dist()
+    parts = [None] * dist.get_world_size(group)
+    if dist.get_backend(group) == "nccl":
+        import torch
+
+        with torch.cuda.device(_local_device(dist)):
+            dist.all_gather_object(parts, part, group=group)
+    else:
+        dist.all_gather_object(parts, part, group=group)
+    return parts
+
+
 def merge_dense(raw, group=None):
     """Sum the dense per-shard results of Reader.count_reads_raw over the ranks.
 
@@ -82,9 +97,7 @@ def merge_dense(raw, group=None):
 
 def merge_introns(part: dict, group=None) -> dict:
     """reference src/count_reads/introns.rs:12-22 combine_intron_results over the ranks"""
-    dist = _dist()
-    parts = [None] * dist.get_world_size(group)
-    dist.all_gather_object(parts, part, group=group)
+    parts = _gather_objects(part, group)
     out: dict = {}
     for p in parts:
         for contig, d in p.items():
@@ -140,9 +153,7 @@ def count_introns(filename, index_filename=None, group=None, device: Optional[in
 def merge_quantify(part, group=None):
     """reference src/count_reads/quantify.rs:189-203 add_hashmaps over the ranks: per gene id the position lists of the
     shards are disjoint (a position belongs to one chunk) and are concatenated"""
-    dist = _dist()
-    parts = [None] * dist.get_world_size(group)
-    dist.all_gather_object(parts, part, group=group)
+    parts = _gather_objects(part, group)
     out = ({}, {})
     for p in parts:
         for b in (0, 1):
@@ -153,9 +164,7 @@ def merge_quantify(part, group=None):
 
 def merge_hist(part: dict, group=None) -> dict:
     """reference src/duplicate_distribution.rs:8-14 add_hashmaps over the ranks"""
-    dist = _dist()
-    parts = [None] * dist.get_world_size(group)
-    dist.all_gather_object(parts, part, group=group)
+    parts = _gather_objects(part, group)
     out: dict = {}
     for p in parts:
         for k, v in p.items():
@@ -165,9 +174,7 @@ def merge_hist(part: dict, group=None) -> dict:
 
 def merge_by_barcode(part, group=None):
     """reference src/count_reads/by_barcode.rs:74-92 over the ranks' entry lists, in rank (= chunk) order"""
-    dist = _dist()
-    parts = [None] * dist.get_world_size(group)
-    dist.all_gather_object(parts, part, group=group)
+    parts = _gather_objects(part, group)
     genes, barcodes, counts = {}, {}, []
     for g_names, b_names, entries in parts:
         for gi, bi, n in entries:
