@@ -28,8 +28,12 @@ def test_module_surface_matches_reference(built):
 
     import mbf_bam
 
-    for fn in ("count_reads_unstranded", "count_reads_stranded", "count_reads_weighted", "count_introns"):
+    for fn in ("count_reads_unstranded", "count_reads_stranded", "count_reads_weighted", "count_introns", "quantify_gene_reads",
+               "calculate_duplicate_distribution", "count_reads_primary_only_right_strand_only_by_barcode"):
         assert callable(getattr(mbf_bam, fn))
+    for fn in ("subtract_bam", "annotate_barcodes_from_fastq"):   # the writers: present, and honest about it
+        with pytest.raises(NotImplementedError):
+            getattr(mbf_bam, fn)("a", "b", "c")
     assert isinstance(mbf_bam.__version__, str)
     doc = built.count_reads_unstranded.__doc__
     for arg in ("filename", "index_filename", "intervals", "gene_intervals", "each_read_counts_once"):
