@@ -277,3 +277,62 @@ def inflate_buffer(data: bytes, cap: int) -> bytes:
     if n < 0:
         raise ValueError("oracle inflate failed")
     return out[:n].tobytes()
+
+
+def quantify_gene_reads(path, index_path, intervals, gene_intervals, nthreads=1):
+    """reference src/lib.rs:247-264: the C restatement's entries, assembled like quantify.rs:148-203 (per contig the last
+    gene_no of a duplicated id wins; equal ids on two contigs are merged, a shared position is the reference's panic)."""
+    iv, keep1, names, gene_ids = flatten(intervals)
+    gv, keep2, _, _ = flatten(gene_intervals)
+    n = C.c_uint64(0)
+    bucket = C.POINTER(C.c_int32)()
+    gene = C.POINTER(C.c_uint32)()
+    pos = C.POINTER(C.c_uint32)()
+    cnt = C.POINTER(C.c_uint64)()
+    scanned = np.zeros(len(names) + 1, dtype=np.uint8)
+    err = C.create_string_buffer(512)
+    L = lib()
+    rc = L.oracle_quantify(path.encode(), index_path.encode() if index_path else None, C.byref(iv), C.byref(gv), C.c_int(nthreads),
+                           C.byref(n), C.byref(bucket), C.byref(gene), C.byref(pos), C.byref(cnt),
+                           scanned.ctypes.data_as(C.c_void_p), err, C.c_size_t(512))
+    if rc:
+        raise ValueError(err.value.decode())
+    per = ({}, {})
+    for i in range(n.value):
+        per[bucket[i]].setdefault(int(gene[i]), []).append((int(pos[i]), int(cnt[i])))
+    for p in (bucket, gene, pos, cnt):
+        L.oracle_free(p)
+    out = ({}, {})
+    base = 0
+    for ci, c in enumerate(names):
+        ids = gene_ids[ci]
+        if scanned[ci]:
+            last = {gid: g for g, gid in enumerate(ids)}
+            for b in (0, 1):
+                for gid, g in last.items():
+                    lst = per[b].get(base + g, [])
+                    tgt = out[b].setdefault(gid, {})
+                    for p_, n_ in lst:
+                        if p_ in tgt:
+                            raise ValueError("still not disjoint")
+                        tgt[p_] = n_
+        base += len(ids)
+    return tuple({g: sorted(d.items()) for g, d in o.items()} for o in out)
+
+
+def calculate_duplicate_distribution(path, index_path=None, nthreads=1):
+    """reference src/lib.rs:108-116 through the C restatement."""
+    n = C.c_uint64(0)
+    k = C.POINTER(C.c_uint32)()
+    cnt = C.POINTER(C.c_uint64)()
+    nrec = C.c_uint64(0)
+    err = C.create_string_buffer(512)
+    L = lib()
+    rc = L.oracle_duplicate_distribution(path.encode(), index_path.encode() if index_path else None, C.c_int(nthreads),
+                                         C.byref(n), C.byref(k), C.byref(cnt), C.byref(nrec), err, C.c_size_t(512))
+    if rc:
+        raise ValueError(err.value.decode())
+    out = {int(k[i]): int(cnt[i]) for i in range(n.value)}
+    for p in (k, cnt):
+        L.oracle_free(p)
+    return out

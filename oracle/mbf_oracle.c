@@ -548,6 +548,8 @@ typedef struct {
     int mode;
     int once;  /* each_read_counts_once */
     int introns;
+    int quantify; /* quantify_gene_reads: imaps hold (bucket, global gene, pos) -> reads */
+    int dups;     /* duplicate distribution: one chunk per reference, imaps hold (0, k, 0) -> groups of k equal reads */
     int nthreads;
     int failed;
     char err[256];
@@ -610,6 +612,34 @@ static void fail(job_t* j, const char* msg) {
     pthread_mutex_unlock(&j->mu);
 }
 
+/* duplicate_distribution.rs:65-69: every distinct (strand, sequence) among the reads of one position adds 1 to
+ * counts[number of reads that have it] */
+static const uint8_t* dup_base;
+static const uint32_t* dup_offs;
+static __thread const uint8_t* t_dup_base;
+static __thread const uint32_t* t_dup_offs;
+static int dup_cmp(const void* a_, const void* b_) {
+    uint32_t a = *(const uint32_t*)a_, b = *(const uint32_t*)b_;
+    uint32_t la = t_dup_offs[a + 1] - t_dup_offs[a], lb = t_dup_offs[b + 1] - t_dup_offs[b];
+    if (la != lb) return la < lb ? -1 : 1;
+    return memcmp(t_dup_base + t_dup_offs[a], t_dup_base + t_dup_offs[b], la);
+}
+static void dup_flush(imap* im, const uint8_t* grp, const uint32_t* off, size_t n) {
+    if (!n) return;
+    (void)dup_base; (void)dup_offs;
+    uint32_t* order = malloc(n * 4);
+    for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    t_dup_base = grp; t_dup_offs = off;
+    qsort(order, n, 4, dup_cmp);
+    size_t run = 1;
+    for (size_t i = 1; i <= n; i++) {
+        if (i < n && dup_cmp(&order[i - 1], &order[i]) == 0) { run++; continue; }
+        imap_add(im, 0, (uint32_t)run, 0, 1);
+        run = 1;
+    }
+    free(order);
+}
+
 /* one chunk == count_reads_in_region_{unstranded,stranded} (counters.rs:26-106,114-202)
  * or count_introns (introns.rs:24-51) */
 static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, size_t* rcap) {
@@ -623,12 +653,13 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
     bgzf_t b;
     if (bgzf_open(&b, j->bam_path)) { fail(j, "Could not read bam: open failed"); return; } /* counters.rs:223 */
     if (bgzf_seek(&b, voff)) { bgzf_close(&b); fail(j, "Fetch error"); return; }
-    const ivset_t* set = j->introns ? NULL : &j->sets[ck->contig];
-    uint64_t gbase = j->introns ? 0 : j->gene_base[ck->contig];
-    uint32_t ngenes = j->introns ? 0 : j->iv->n_genes[ck->contig];
+    const int no_sets = j->introns || j->dups;
+    const ivset_t* set = no_sets ? NULL : &j->sets[ck->contig];
+    uint64_t gbase = no_sets ? 0 : j->gene_base[ck->contig];
+    uint32_t ngenes = no_sets ? 0 : j->iv->n_genes[ck->contig];
     uint64_t* lf = NULL; uint64_t* lr = NULL;
     double *wf = NULL, *wr = NULL;
-    if (!j->introns) {
+    if (!j->introns && !j->dups && !j->quantify) {
         if (j->mode == MBFBAM_MODE_WEIGHTED) {
             size_t tot = (size_t)j->gene_base[j->iv->n_contigs];
             wf = j->wfwd + (size_t)thread * tot + gbase;
@@ -642,7 +673,10 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
     mm_init(&mm);
     u32vec seen[2] = {{0, 0, 0}, {0, 0, 0}};
     uint64_t outside = 0, nrec = 0;
-    imap* im = j->introns ? &j->imaps[thread] : NULL;
+    imap* im = (j->introns || j->quantify || j->dups) ? &j->imaps[thread] : NULL;
+    /* duplicate distribution: the reads of the current position (duplicate_distribution.rs:57-75) */
+    uint8_t* grp = NULL; size_t grp_len = 0, grp_cap = 0; uint32_t* grp_off = NULL; size_t grp_n = 0, grp_ncap = 0;
+    int64_t grp_pos = -1;
     for (;;) {
         int32_t bs;
         if (bgzf_read(&b, &bs, 4) != 4) break; /* Err(_) ends the loop, counters.rs:41 */
@@ -674,6 +708,49 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
                 if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) p += len;
             }
             imap_add(im, tid, UINT32_MAX, UINT32_MAX - k, 1);
+            continue;
+        }
+        if (j->dups) {
+            /* key = (is_reverse, decoded sequence): l_seq + the packed bases, spare nibble of an odd length cleared */
+            if ((int64_t)pos != grp_pos) {
+                dup_flush(im, grp, grp_off, grp_n);
+                grp_n = 0; grp_len = 0; grp_pos = pos;
+            }
+            const uint8_t* seq = cig + 4 * (size_t)n_cig;
+            size_t nb = ((size_t)l_seq + 1) / 2, klen = 5 + nb;
+            if (grp_len + klen > grp_cap) { grp_cap = (grp_len + klen) * 2 + 64; grp = realloc(grp, grp_cap); }
+            if (grp_n + 2 > grp_ncap) { grp_ncap = grp_ncap ? grp_ncap * 2 : 64; grp_off = realloc(grp_off, grp_ncap * 4); }
+            grp_off[grp_n++] = (uint32_t)grp_len;
+            grp[grp_len] = (flag & 0x10) ? 1 : 0;
+            memcpy(grp + grp_len + 1, &l_seq, 4);
+            memcpy(grp + grp_len + 5, seq, nb);
+            if ((l_seq & 1) && nb) grp[grp_len + 5 + nb - 1] &= 0xf0;
+            grp_len += klen;
+            grp_off[grp_n] = (uint32_t)grp_len;
+            continue;
+        }
+        if (j->quantify) {
+            /* quantify.rs:113-142: one alignment counts once per gene, no NH logic, any flag */
+            seen[0].n = 0;
+            uint32_t p = upos;
+            for (uint32_t i = 0; i < n_cig; i++) {
+                uint32_t c = rd32(cig + 4 * i), op = c & 15, len = c >> 4;
+                if (op == 0 || op == 7 || op == 8) {
+                    uint32_t b0 = p, b1 = p + len;
+                    p += len;
+                    tfind_t f;
+                    t_find_begin(set, &f, b0, b1);
+                    for (int32_t k; (k = t_find_next(set, &f)) >= 0;) {
+                        uint32_t g = set->nd[k].gene;
+                        if (!vec_add_unique(&seen[0], g)) continue;
+                        int rv = (flag & 0x10) != 0, st = set->nd[k].strand;
+                        int congruent = (st == 1 && !rv) || (st != 1 && rv);
+                        imap_add(im, congruent ? 0 : 1, (uint32_t)(gbase + g), upos, 1);
+                    }
+                } else if (op == 2 || op == 3) {
+                    p += len;
+                }
+            }
             continue;
         }
         seen[0].n = seen[1].n = 0;
@@ -721,8 +798,10 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
             for (size_t i = 0; i < seen[1].n; i++) lr[seen[1].v[i]]++;
         }
     }
+    if (j->dups) dup_flush(im, grp, grp_off, grp_n);
+    free(grp); free(grp_off);
     if (b.err) fail(j, "corrupt BGZF block");
-    if (!j->introns && j->mode != MBFBAM_MODE_WEIGHTED) {
+    if (!j->introns && !j->dups && !j->quantify && j->mode != MBFBAM_MODE_WEIGHTED) {
         /* counters.rs:102-104 / :195-200: add the sizes of the multi-mapper sets */
         for (size_t i = 0; i < mm.cap; i++)
             for (mmnode* q = mm.tab[i]; q; q = q->next) (q->bucket ? lr : lf)[q->gene]++;
@@ -906,6 +985,116 @@ int oracle_count_introns(const char* bam, const char* bai, int nthreads, int64_t
     free_idx(&idx);
     return rc;
 }
+/* quantify.rs:20-75 without the String maps.  Entries (bucket 0 congruent / 1 incongruent, global gene slot, pos, reads);
+ * result arrays are malloc'ed; free with oracle_free. */
+int oracle_quantify(const char* bam, const char* bai, const mbfbam_intervals* iv, const mbfbam_intervals* genes, int nthreads,
+                    uint64_t* n_out, int32_t** bucket_out, uint32_t** gene_out, uint32_t** pos_out, uint64_t** count_out,
+                    uint8_t* scanned, char* err, size_t errlen) {
+    bamidx_t idx;
+    int rc = open_idx(bam, bai, &idx, err, errlen);
+    if (rc) return rc;
+    job_t j;
+    memset(&j, 0, sizeof j);
+    pthread_mutex_init(&j.mu, NULL);
+    j.bam_path = bam; j.idx = &idx; j.iv = iv; j.mode = MBFBAM_MODE_STRANDED; j.quantify = 1; j.nthreads = nthreads < 1 ? 1 : nthreads;
+    j.sets = calloc((size_t)iv->n_contigs + 1, sizeof(ivset_t));
+    j.gene_base = calloc((size_t)iv->n_contigs + 1, 8);
+    for (int c = 0; c < iv->n_contigs; c++) {
+        build_ivset(iv, c, &j.sets[c]);
+        j.gene_base[c + 1] = j.gene_base[c] + iv->n_genes[c];
+    }
+    ivset_t* gsets = calloc((size_t)genes->n_contigs + 1, sizeof(ivset_t));
+    for (int c = 0; c < genes->n_contigs; c++) build_ivset(genes, c, &gsets[c]);
+    size_t nck;
+    chunk_t* cks = make_chunks(&idx, genes, gsets, &nck);
+    for (size_t i = 0; i < nck; i++) {
+        const char* nm = genes->contig_names[cks[i].contig];
+        int c2 = -1;
+        for (int c = 0; c < iv->n_contigs; c++) if (!strcmp(iv->contig_names[c], nm)) { c2 = c; break; }
+        if (c2 < 0) { snprintf(err, errlen, "contig %s is in gene_intervals but not in intervals", nm); rc = MBFBAM_ERR_ARG; break; }
+        cks[i].contig = c2;
+        if (scanned) scanned[c2] = 1;
+    }
+    *n_out = 0;
+    if (!rc) {
+        j.chunks = cks; j.n_chunks = nck;
+        j.imaps = calloc((size_t)j.nthreads, sizeof(imap));
+        for (int t = 0; t < j.nthreads; t++) imap_init(&j.imaps[t], 1 << 12);
+        run_pool(&j);
+        imap all;
+        imap_init(&all, 1 << 12);
+        for (int t = 0; t < j.nthreads; t++) {
+            imap* m = &j.imaps[t];
+            for (size_t i = 0; i < m->cap; i++)
+                if (m->tid[i] >= 0) imap_add(&all, m->tid[i], (uint32_t)m->key[i], (uint32_t)(m->key[i] >> 32), m->cnt[i]);
+            imap_free(m);
+        }
+        free(j.imaps);
+        *n_out = all.n;
+        *bucket_out = malloc((all.n + 1) * 4);
+        *gene_out = malloc((all.n + 1) * 4);
+        *pos_out = malloc((all.n + 1) * 4);
+        *count_out = malloc((all.n + 1) * 8);
+        size_t k = 0;
+        for (size_t i = 0; i < all.cap; i++)
+            if (all.tid[i] >= 0) {
+                (*bucket_out)[k] = all.tid[i];
+                (*gene_out)[k] = (uint32_t)all.key[i];
+                (*pos_out)[k] = (uint32_t)(all.key[i] >> 32);
+                (*count_out)[k] = all.cnt[i];
+                k++;
+            }
+        imap_free(&all);
+        if (j.failed) { snprintf(err, errlen, "%s", j.err); rc = MBFBAM_ERR_FORMAT; }
+    }
+    for (int c = 0; c < iv->n_contigs; c++) free_ivset(&j.sets[c]);
+    for (int c = 0; c < genes->n_contigs; c++) free_ivset(&gsets[c]);
+    free(j.sets); free(gsets); free(j.gene_base); free(cks);
+    free_idx(&idx);
+    return rc;
+}
+
+/* duplicate_distribution.rs:44-86: a pool task per reference walks fetch(tid, 0, target_len).  Entries (k, number of
+ * distinct (position, strand, sequence) seen exactly k times); free with oracle_free. */
+int oracle_duplicate_distribution(const char* bam, const char* bai, int nthreads, uint64_t* n_out, uint32_t** k_out,
+                                  uint64_t** count_out, uint64_t* n_records_out, char* err, size_t errlen) {
+    bamidx_t idx;
+    int rc = open_idx(bam, bai, &idx, err, errlen);
+    if (rc) return rc;
+    job_t j;
+    memset(&j, 0, sizeof j);
+    pthread_mutex_init(&j.mu, NULL);
+    j.bam_path = bam; j.idx = &idx; j.dups = 1; j.nthreads = nthreads < 1 ? 1 : nthreads;
+    size_t nck = (size_t)idx.n_ref;
+    chunk_t* cks = calloc(nck + 1, sizeof *cks);
+    for (int t = 0; t < idx.n_ref; t++) cks[t] = (chunk_t){t, t, 0, idx.lens[t]};
+    j.chunks = cks; j.n_chunks = nck;
+    j.imaps = calloc((size_t)j.nthreads, sizeof(imap));
+    for (int t = 0; t < j.nthreads; t++) imap_init(&j.imaps[t], 1 << 8);
+    run_pool(&j);
+    imap all;
+    imap_init(&all, 1 << 8);
+    for (int t = 0; t < j.nthreads; t++) {
+        imap* m = &j.imaps[t];
+        for (size_t i = 0; i < m->cap; i++)
+            if (m->tid[i] >= 0) imap_add(&all, m->tid[i], (uint32_t)m->key[i], (uint32_t)(m->key[i] >> 32), m->cnt[i]);
+        imap_free(m);
+    }
+    free(j.imaps);
+    *n_out = all.n;
+    *k_out = malloc((all.n + 1) * 4);
+    *count_out = malloc((all.n + 1) * 8);
+    size_t k = 0;
+    for (size_t i = 0; i < all.cap; i++)
+        if (all.tid[i] >= 0) { (*k_out)[k] = (uint32_t)all.key[i]; (*count_out)[k] = all.cnt[i]; k++; }
+    imap_free(&all);
+    if (n_records_out) *n_records_out = j.n_records;
+    if (j.failed) { snprintf(err, errlen, "%s", j.err); rc = MBFBAM_ERR_FORMAT; }
+    free(cks);
+    free_idx(&idx);
+    return rc;
+}
+
 void oracle_free(void* p) { free(p); }
 
 int64_t oracle_chunks(const char* bam, const char* bai, const mbfbam_intervals* genes, int32_t* tid,

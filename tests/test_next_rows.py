@@ -10,7 +10,7 @@ import pytest
 from conftest import make_case
 from synth import bamio
 from synth.bamio import Rec, aux_int
-from oracle import py_oracle
+from oracle import c_oracle, py_oracle
 
 
 def pack_seq(bases):
@@ -112,6 +112,15 @@ def test_duplicate_distribution_hand_case(tmp_path):
     p = str(tmp_path / "d.bam")
     bamio.write_bam(p, contigs, recs)
     assert py_oracle.calculate_duplicate_distribution(p) == {3: 1, 1: 5, 2: 2}
+
+
+@pytest.mark.parametrize("seed,kw", [(41, {}), (42, dict(exon_mode=False, genes_per_contig=150)), (43, dict(paired=True, n_contigs=4)),
+                                     (44, dict(split_records=True, level=1))])
+def test_c_oracle_matches_py_oracle_quantify_and_duplicates(tmp_path, seed, kw):
+    """the C restatement (tree walk, BAI seeks, threads) against the brute-force Python one"""
+    path, contigs, recs, iv, giv = dup_case(tmp_path, seed, n_reads=4000, **kw)
+    assert c_oracle.quantify_gene_reads(path, None, iv, giv, nthreads=3) == py_oracle.quantify_gene_reads(path, None, iv, giv)
+    assert c_oracle.calculate_duplicate_distribution(path, nthreads=3) == py_oracle.calculate_duplicate_distribution(path)
 
 
 # ------------------------------------------------------------------------------------------------ GPU
@@ -357,3 +366,18 @@ def test_by_barcode_many_windows_and_shards(mb, tmp_path, monkeypatch):
     finally:
         monkeypatch.delenv("MBF_BAM_WINDOW_MB")
         mb.release_device(0)
+
+
+@pytest.mark.gpu
+def test_quantify_and_duplicates_on_a_bench_shaped_file(mb, tmp_path):
+    """1 M reads of the configs[2] shape (25 human-like contigs, 20 k genes, spliced reads, multi-mappers) against the C
+    restatement: every (gene, position) list and the whole duplicate histogram"""
+    from synth import model
+
+    path = str(tmp_path / "cfg3.bam")
+    iv, giv, info = model.build_config("cfg3", path, reads=1_000_000)
+    got = mb.quantify_gene_reads(path, None, iv, giv)
+    want = c_oracle.quantify_gene_reads(path, None, iv, giv, nthreads=8)
+    assert got == want
+    assert sum(len(v) for v in want[0].values()) > 100_000
+    assert mb.calculate_duplicate_distribution(path) == c_oracle.calculate_duplicate_distribution(path, nthreads=8)
