@@ -255,7 +255,7 @@ def test_property_c_oracle_vs_py_oracle_and_host_chunk_table(built, tmp_path):
     from hypothesis import HealthCheck, given, settings, strategies as st
     from synth import small
 
-    @settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+    @settings(max_examples=20, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
     @given(st.integers(0, 10 ** 6), st.integers(1, 3), st.integers(1, 80), st.booleans(), st.booleans())
     def prop(seed, n_contigs, genes, exon_mode, paired):
         contigs, recs, iv, giv = small.simple_case(seed, n_reads=500, n_contigs=n_contigs, contig_len=1_200_000,
