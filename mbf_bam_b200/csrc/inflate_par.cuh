@@ -19,8 +19,7 @@
 //           number of tokens before it
 //   sync    every lane whose predecessor stopped somewhere else restarts there -- but only until it steps exactly onto
 //           a checkpoint: from there on its path IS the guess path (a decoder's state is its bit position), so the
-//           guess run's count and exit are reused.  Measured on the bench files (tools/selfsync_sim.cpp and a variant of
-//           it; sub-sequences of 1312 bits = 122 tokens): the true chain meets the guess path after 10 tokens on
+//           guess run's count and exit are reused.  Measured on the bench files (tools/merge_sim.cpp; sub-sequences of 1312 bits = 122 tokens): the true chain meets the guess path after 10 tokens on
 //           average, 97 % within 12 words, and 0.09 % of the lanes never do (they decode to the end of their stretch).
 //           Repeated until nobody moves.  Converged <=> every lane started where its predecessor stopped <=> the
 //           chain is the true one (induction from lane 0), whatever the data: speculation is verified, never trusted
