@@ -19,15 +19,16 @@
 //           number of tokens before it
 //   sync    every lane whose predecessor stopped somewhere else restarts there -- but only until it steps exactly onto
 //           a checkpoint: from there on its path IS the guess path (a decoder's state is its bit position), so the
-//           guess run's count and exit are reused.  Measured on the bench files (tools/merge_sim.cpp; sub-sequences of 1312 bits = 122 tokens): the true chain meets the guess path after 10 tokens on
-//           average, 97 % within 12 words, and 0.09 % of the lanes never do (they decode to the end of their stretch).
+//           guess run's count and exit are reused.  Measured on the bench files (tools/merge_sim.cpp; sub-sequences
+//           of 1312 bits = 122 tokens): the true chain meets the guess path after 10 tokens on average, 97 % within
+//           12 words, and 0.09 % of the lanes never do (they decode to the end of their stretch).
 //           Repeated until nobody moves.  Converged <=> every lane started where its predecessor stopped <=> the
 //           chain is the true one (induction from lane 0), whatever the data: speculation is verified, never trusted
 //   emit    token counts -> exclusive scan -> every lane decodes its stretch once more and writes its tokens
 //           (three-decode scheme, the default).  Single-decode scheme (ONEPASS): the guess and sync runs keep their
 //           tokens in a transposed scratch area in HBM (token k of lane j at [32 k + j]: a warp's lanes write whole
 //           lines) and emit is a copy, [the sync run's tokens][the guess run's tokens from the checkpoint on], through
-//           shared-memory tiles.  It issues 15 % fewer instructions and is no faster (measured): every trip
+//           shared-memory tiles.  It issues 6 % fewer instructions and is no faster (measured): every trip
 //           then carries the token arithmetic and a store
 //
 // Stored blocks, members whose tables overflow the second-level pool, and anything that looks corrupt are
