@@ -336,3 +336,40 @@ def calculate_duplicate_distribution(path, index_path=None, nthreads=1):
     for p in (k, cnt):
         L.oracle_free(p)
     return out
+
+
+def count_reads_primary_only_right_strand_only_by_barcode(path, index_path, intervals, gene_intervals, umi_strategy="straight",
+                                                          nthreads=1):
+    """reference src/lib.rs:184-211 through the C restatement; entries ordered (chunk, gene, barcode) and indices handed
+    out in that order, like py_oracle and the product (the reference's order is HashMap iteration)."""
+    if umi_strategy != "straight":
+        raise ValueError("invalid umi_strategy")
+    iv, keep1, names, gene_ids = flatten(intervals)
+    gv, keep2, _, _ = flatten(gene_intervals)
+    n = C.c_uint64(0)
+    gene = C.POINTER(C.c_uint32)()
+    chunk = C.POINTER(C.c_uint32)()
+    cnt = C.POINTER(C.c_uint32)()
+    off = C.POINTER(C.c_uint64)()
+    byt = C.POINTER(C.c_char)()
+    err = C.create_string_buffer(512)
+    L = lib()
+    rc = L.oracle_by_barcode(path.encode(), index_path.encode() if index_path else None, C.byref(iv), C.byref(gv), C.c_int(nthreads),
+                             C.byref(n), C.byref(gene), C.byref(chunk), C.byref(cnt), C.byref(off), C.byref(byt), err,
+                             C.c_size_t(512))
+    if rc:
+        raise ValueError(err.value.decode())
+    flat_ids = [gid for ids in gene_ids for gid in ids]
+    entries = []
+    for i in range(n.value):
+        entries.append((int(chunk[i]), int(gene[i]), C.string_at(C.addressof(byt.contents) + off[i], off[i + 1] - off[i]), int(cnt[i])))
+    for p in (gene, chunk, cnt, off, byt):
+        if p:
+            L.oracle_free(p)
+    entries.sort()
+    genes, barcodes, counts = {}, {}, []
+    for _ck, g, bc, c in entries:
+        gi = genes.setdefault(flat_ids[g], len(genes))
+        bi = barcodes.setdefault(bc.decode(), len(barcodes))
+        counts.append((gi, bi, c))
+    return list(genes), list(barcodes), counts

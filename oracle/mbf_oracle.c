@@ -517,6 +517,45 @@ static int aux_nh(const uint8_t* p, const uint8_t* e, int64_t* val) {
     return 0;
 }
 
+/* rust-htslib Record::aux(tag) for string values (types Z and H -> Aux::String): 1 found, 0 absent, -1 another type,
+ * -2 malformed */
+static int aux_str(const uint8_t* p, const uint8_t* e, char t0, char t1, const uint8_t** sp, size_t* slen) {
+    while (p + 3 <= e) {
+        int match = p[0] == (uint8_t)t0 && p[1] == (uint8_t)t1;
+        uint8_t t = p[2];
+        p += 3;
+        size_t sz;
+        switch (t) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'd': sz = 8; break;
+            case 'Z': case 'H': {
+                const uint8_t* s0 = p;
+                while (p < e && *p) p++;
+                if (p >= e) return -2;
+                if (match) { *sp = s0; *slen = (size_t)(p - s0); return 1; }
+                p++;
+                continue;
+            }
+            case 'B': {
+                if (match) return -1;
+                if (p + 5 > e) return -2;
+                uint8_t st = p[0];
+                uint32_t cnt = rd32(p + 1);
+                size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                p += 5 + (size_t)cnt * es;
+                continue;
+            }
+            default: return -2;
+        }
+        if (p + sz > e) return -2;
+        if (match) return -1;
+        p += sz;
+    }
+    return 0;
+}
+
 /* rust-htslib aligned_blocks / introns through src/bam_ext.rs:28-42. */
 int32_t oracle_cigar_pairs(const uint32_t* cigar, int32_t n_ops, int32_t pos, int32_t want_introns,
                            uint32_t* out, int32_t cap) {
@@ -549,6 +588,7 @@ typedef struct {
     int once;  /* each_read_counts_once */
     int introns;
     int quantify; /* quantify_gene_reads: imaps hold (bucket, global gene, pos) -> reads */
+    int barcode;  /* by_barcode: entries (chunk, gene, barcode, distinct UMIs) appended to bc_* under `mu` */
     int dups;     /* duplicate distribution: one chunk per reference, imaps hold (0, k, 0) -> groups of k equal reads */
     int nthreads;
     int failed;
@@ -561,6 +601,11 @@ typedef struct {
     uint64_t n_records;
     /* introns: per-thread maps merged at the end */
     struct imap* imaps;
+    /* by_barcode */
+    uint32_t *bc_gene, *bc_chunk, *bc_count;
+    uint64_t* bc_off;
+    char* bc_bytes;
+    size_t bc_n, bc_cap, bc_blen, bc_bcap;
 } job_t;
 
 /* (tid,start,stop) -> count, open addressing */
@@ -659,7 +704,7 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
     uint32_t ngenes = no_sets ? 0 : j->iv->n_genes[ck->contig];
     uint64_t* lf = NULL; uint64_t* lr = NULL;
     double *wf = NULL, *wr = NULL;
-    if (!j->introns && !j->dups && !j->quantify) {
+    if (!j->introns && !j->dups && !j->quantify && !j->barcode) {
         if (j->mode == MBFBAM_MODE_WEIGHTED) {
             size_t tot = (size_t)j->gene_base[j->iv->n_contigs];
             wf = j->wfwd + (size_t)thread * tot + gbase;
@@ -677,6 +722,10 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
     /* duplicate distribution: the reads of the current position (duplicate_distribution.rs:57-75) */
     uint8_t* grp = NULL; size_t grp_len = 0, grp_cap = 0; uint32_t* grp_off = NULL; size_t grp_n = 0, grp_ncap = 0;
     int64_t grp_pos = -1;
+    /* by_barcode: scratch key, and one (gene, barcode) entry per distinct (gene, barcode, pos, strand, UMI) */
+    int bc_failed = 0;
+    uint8_t* bkey = NULL; size_t bkey_cap = 0;
+    uint8_t* bent = NULL; size_t bent_len = 0, bent_cap = 0; uint32_t* bent_off = NULL; size_t bent_n = 0, bent_ncap = 0;
     for (;;) {
         int32_t bs;
         if (bgzf_read(&b, &bs, 4) != 4) break; /* Err(_) ends the loop, counters.rs:41 */
@@ -727,6 +776,53 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
             if ((l_seq & 1) && nb) grp[grp_len + 5 + nb - 1] &= 0xf0;
             grp_len += klen;
             grp_off[grp_n] = (uint32_t)grp_len;
+            continue;
+        }
+        if (j->barcode) {
+            /* by_barcode.rs:125-162 */
+            if (bc_failed || (flag & 0x100)) continue;
+            int rv = (flag & 0x10) != 0;
+            uint32_t p = upos;
+            for (uint32_t i = 0; i < n_cig && !bc_failed; i++) {
+                uint32_t c = rd32(cig + 4 * i), op = c & 15, len = c >> 4;
+                if (op == 0 || op == 7 || op == 8) {
+                    uint32_t b0 = p, b1 = p + len;
+                    p += len;
+                    if (b1 < ck->start || b0 >= ck->stop || (b0 < ck->start && b1 >= ck->start)) continue; /* :131 */
+                    tfind_t f;
+                    t_find_begin(set, &f, b0, b1);
+                    for (int32_t k; (k = t_find_next(set, &f)) >= 0;) {
+                        int st = set->nd[k].strand;
+                        if (!((st == 1 && !rv) || (st != 1 && rv))) continue;
+                        const uint8_t *xc, *xm;
+                        size_t lc, lm;
+                        if (aux_str(aux, end, 'X', 'C', &xc, &lc) != 1 || aux_str(aux, end, 'X', 'M', &xm, &lm) != 1) {
+                            bc_failed = 1; /* `?`: the chunk's function returns Err, the driver drops the chunk (:46-68) */
+                            break;
+                        }
+                        /* positions[(gene_no, barcode, pos, is_reverse)].insert(umi) */
+                        size_t kl = 4 + 4 + 1 + 2 + lc + lm;
+                        if (kl > bkey_cap) { bkey_cap = kl * 2; bkey = realloc(bkey, bkey_cap); }
+                        uint32_t g = set->nd[k].gene;
+                        uint16_t lc16 = (uint16_t)lc;
+                        memcpy(bkey, &g, 4); memcpy(bkey + 4, &pos, 4); bkey[8] = (uint8_t)rv; memcpy(bkey + 9, &lc16, 2);
+                        memcpy(bkey + 11, xc, lc); memcpy(bkey + 11 + lc, xm, lm);
+                        if (mm_insert(&mm, 0, 0, bkey, kl)) {
+                            /* a new UMI for this (gene, barcode, pos, strand): one more for (gene, barcode) */
+                            size_t el = 4 + lc;
+                            if (bent_len + el + 8 > bent_cap) { bent_cap = (bent_len + el + 8) * 2; bent = realloc(bent, bent_cap); }
+                            if (bent_n + 2 > bent_ncap) { bent_ncap = bent_ncap ? bent_ncap * 2 : 256; bent_off = realloc(bent_off, bent_ncap * 4); }
+                            bent_off[bent_n++] = (uint32_t)bent_len;
+                            memcpy(bent + bent_len, &g, 4);
+                            memcpy(bent + bent_len + 4, xc, lc);
+                            bent_len += el;
+                            bent_off[bent_n] = (uint32_t)bent_len;
+                        }
+                    }
+                } else if (op == 2 || op == 3) {
+                    p += len;
+                }
+            }
             continue;
         }
         if (j->quantify) {
@@ -800,8 +896,42 @@ static void run_chunk(job_t* j, int thread, const chunk_t* ck, uint8_t** rbuf, s
     }
     if (j->dups) dup_flush(im, grp, grp_off, grp_n);
     free(grp); free(grp_off);
+    if (j->barcode && !bc_failed && bent_n) {
+        /* by_barcode.rs:164-180: sum of the set sizes per (gene_no, barcode) */
+        uint32_t* order = malloc(bent_n * 4);
+        for (size_t i = 0; i < bent_n; i++) order[i] = (uint32_t)i;
+        t_dup_base = bent; t_dup_offs = bent_off;
+        qsort(order, bent_n, 4, dup_cmp);
+        pthread_mutex_lock(&j->mu);
+        size_t run = 1;
+        for (size_t i = 1; i <= bent_n; i++) {
+            if (i < bent_n && dup_cmp(&order[i - 1], &order[i]) == 0) { run++; continue; }
+            const uint8_t* e0 = bent + bent_off[order[i - 1]];
+            size_t el = bent_off[order[i - 1] + 1] - bent_off[order[i - 1]], bl = el - 4;
+            uint32_t g;
+            memcpy(&g, e0, 4);
+            if (j->bc_n + 2 > j->bc_cap) {
+                j->bc_cap = j->bc_cap ? j->bc_cap * 2 : 1024;
+                j->bc_gene = realloc(j->bc_gene, j->bc_cap * 4); j->bc_chunk = realloc(j->bc_chunk, j->bc_cap * 4);
+                j->bc_count = realloc(j->bc_count, j->bc_cap * 4); j->bc_off = realloc(j->bc_off, (j->bc_cap + 1) * 8);
+            }
+            if (j->bc_blen + bl + 1 > j->bc_bcap) { j->bc_bcap = (j->bc_blen + bl + 1) * 2; j->bc_bytes = realloc(j->bc_bytes, j->bc_bcap); }
+            j->bc_gene[j->bc_n] = (uint32_t)(gbase + g);
+            j->bc_chunk[j->bc_n] = (uint32_t)(ck - j->chunks);
+            j->bc_count[j->bc_n] = (uint32_t)run;
+            j->bc_off[j->bc_n] = j->bc_blen;
+            memcpy(j->bc_bytes + j->bc_blen, e0 + 4, bl);
+            j->bc_blen += bl;
+            j->bc_n++;
+            j->bc_off[j->bc_n] = j->bc_blen;
+            run = 1;
+        }
+        pthread_mutex_unlock(&j->mu);
+        free(order);
+    }
+    free(bkey); free(bent); free(bent_off);
     if (b.err) fail(j, "corrupt BGZF block");
-    if (!j->introns && !j->dups && !j->quantify && j->mode != MBFBAM_MODE_WEIGHTED) {
+    if (!j->introns && !j->dups && !j->quantify && !j->barcode && j->mode != MBFBAM_MODE_WEIGHTED) {
         /* counters.rs:102-104 / :195-200: add the sizes of the multi-mapper sets */
         for (size_t i = 0; i < mm.cap; i++)
             for (mmnode* q = mm.tab[i]; q; q = q->next) (q->bucket ? lr : lf)[q->gene]++;
@@ -1091,6 +1221,50 @@ int oracle_duplicate_distribution(const char* bam, const char* bai, int nthreads
     if (n_records_out) *n_records_out = j.n_records;
     if (j.failed) { snprintf(err, errlen, "%s", j.err); rc = MBFBAM_ERR_FORMAT; }
     free(cks);
+    free_idx(&idx);
+    return rc;
+}
+
+/* by_barcode.rs:18-92 without the String maps: entries (global gene slot, chunk index, distinct UMIs, barcode bytes) in
+ * the order the pool produced them; free the arrays with oracle_free. */
+int oracle_by_barcode(const char* bam, const char* bai, const mbfbam_intervals* iv, const mbfbam_intervals* genes, int nthreads,
+                      uint64_t* n_out, uint32_t** gene_out, uint32_t** chunk_out, uint32_t** count_out, uint64_t** off_out,
+                      char** bytes_out, char* err, size_t errlen) {
+    bamidx_t idx;
+    int rc = open_idx(bam, bai, &idx, err, errlen);
+    if (rc) return rc;
+    job_t j;
+    memset(&j, 0, sizeof j);
+    pthread_mutex_init(&j.mu, NULL);
+    j.bam_path = bam; j.idx = &idx; j.iv = iv; j.mode = MBFBAM_MODE_STRANDED; j.barcode = 1; j.nthreads = nthreads < 1 ? 1 : nthreads;
+    j.sets = calloc((size_t)iv->n_contigs + 1, sizeof(ivset_t));
+    j.gene_base = calloc((size_t)iv->n_contigs + 1, 8);
+    for (int c = 0; c < iv->n_contigs; c++) {
+        build_ivset(iv, c, &j.sets[c]);
+        j.gene_base[c + 1] = j.gene_base[c] + iv->n_genes[c];
+    }
+    ivset_t* gsets = calloc((size_t)genes->n_contigs + 1, sizeof(ivset_t));
+    for (int c = 0; c < genes->n_contigs; c++) build_ivset(genes, c, &gsets[c]);
+    size_t nck;
+    chunk_t* cks = make_chunks(&idx, genes, gsets, &nck);
+    for (size_t i = 0; i < nck; i++) {
+        const char* nm = genes->contig_names[cks[i].contig];
+        int c2 = -1;
+        for (int c = 0; c < iv->n_contigs; c++) if (!strcmp(iv->contig_names[c], nm)) { c2 = c; break; }
+        if (c2 < 0) { snprintf(err, errlen, "contig %s is in gene_intervals but not in intervals", nm); rc = MBFBAM_ERR_ARG; break; }
+        cks[i].contig = c2;
+    }
+    *n_out = 0;
+    if (!rc) {
+        j.chunks = cks; j.n_chunks = nck;
+        run_pool(&j);
+        *n_out = j.bc_n;
+        *gene_out = j.bc_gene; *chunk_out = j.bc_chunk; *count_out = j.bc_count; *off_out = j.bc_off; *bytes_out = j.bc_bytes;
+        if (j.failed) { snprintf(err, errlen, "%s", j.err); rc = MBFBAM_ERR_FORMAT; }
+    }
+    for (int c = 0; c < iv->n_contigs; c++) free_ivset(&j.sets[c]);
+    for (int c = 0; c < genes->n_contigs; c++) free_ivset(&gsets[c]);
+    free(j.sets); free(gsets); free(j.gene_base); free(cks);
     free_idx(&idx);
     return rc;
 }

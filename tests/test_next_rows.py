@@ -309,6 +309,14 @@ def test_by_barcode_hand_case(tmp_path):
         getattr(py_oracle, BY_BARCODE)(p, None, iv, giv, "hamming")
 
 
+@pytest.mark.parametrize("seed,kw", [(61, {}), (62, dict(exon_mode=False, genes_per_contig=150, n_contigs=3)),
+                                     (63, dict(paired=True, split_records=True)), (64, dict(bad_chunks=False, level=1))])
+def test_c_oracle_matches_py_oracle_by_barcode(tmp_path, seed, kw):
+    path, contigs, recs, iv, giv = barcode_case(tmp_path, seed, n_reads=4000, **kw)
+    assert getattr(c_oracle, BY_BARCODE)(path, None, iv, giv, "straight", nthreads=3) == \
+        getattr(py_oracle, BY_BARCODE)(path, None, iv, giv, "straight")
+
+
 @pytest.mark.gpu
 def test_by_barcode_hand_case_on_device(mb, tmp_path):
     contigs = [("c1", 2_500_000)]
